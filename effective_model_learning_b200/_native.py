@@ -1,0 +1,204 @@
+"""
+ctypes binding of libeml_b200.so (C ABI declared in include/eml_b200.h).
+
+There is deliberately no fallback: if the shared library or a CUDA device is missing,
+every compute entry point raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libeml_b200.so')
+
+EML_OK = 0
+EML_ERR_NOT_CONVERGED = -4
+TERM_ENERGY, TERM_COUPLING, TERM_LINDBLAD = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA = 0, 1, 2
+
+# every symbol include/eml_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
+           'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count',
+           'eml_plan_kernel_name', 'eml_measure_fp64_peak')
+
+
+class EmlTerm(C.Structure):
+    _fields_ = [('param', C.c_int32), ('kind', C.c_int32), ('site_a', C.c_int32), ('site_b', C.c_int32),
+                ('op_a', C.c_int32), ('op_b', C.c_int32)]
+
+
+class EmlProblemDesc(C.Structure):
+    _fields_ = [('n_tls', C.c_int32), ('n_params', C.c_int32), ('n_terms', C.c_int32),
+                ('terms', C.POINTER(EmlTerm)),
+                ('n_ops', C.c_int32), ('op_table', C.POINTER(C.c_double)),
+                ('rho0', C.POINTER(C.c_double)),
+                ('obs_site', C.c_int32), ('n_obs', C.c_int32), ('obs', C.POINTER(C.c_double)),
+                ('n_times', C.c_int32), ('times', C.POINTER(C.c_double)),
+                ('n_target_sets', C.c_int32), ('targets', C.POINTER(C.c_double))]
+
+
+class EmlOptions(C.Structure):
+    _fields_ = [('theta_target', C.c_double), ('tol', C.c_double), ('kernel', C.c_int32), ('reserved', C.c_int32)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(there is no CPU fallback)')
+        lib = C.CDLL(LIB_PATH)
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+        lib.eml_version.restype = C.c_int
+        lib.eml_last_error_string.restype = C.c_char_p
+        lib.eml_device_count.argtypes = [C.POINTER(C.c_int)]
+        lib.eml_plan_create.argtypes = [C.POINTER(EmlProblemDesc), C.c_int, C.POINTER(EmlOptions), C.POINTER(vp)]
+        lib.eml_plan_destroy.argtypes = [vp]
+        lib.eml_plan_set_targets.argtypes = [vp, C.c_int32, dp]
+        lib.eml_eval_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp]
+        lib.eml_eval_batch_host.argtypes = [vp, C.c_int64, dp, ip, dp, dp]
+        lib.eml_launch_count.restype = C.c_int64
+        lib.eml_plan_kernel_name.argtypes = [vp]
+        lib.eml_plan_kernel_name.restype = C.c_char_p
+        lib.eml_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, dp]
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().eml_last_error_string().decode()
+
+
+def check(rc: int, what: str):
+    if rc != EML_OK:
+        raise RuntimeError(f'{what} failed ({rc}): {last_error()}')
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    load().eml_device_count(C.byref(n))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(load().eml_launch_count())
+
+
+def measure_fp64_peak(device: int = 0, use_mma: bool = False, seconds: float = 0.5) -> float:
+    out = C.c_double(0.0)
+    check(load().eml_measure_fp64_peak(device, int(use_mma), seconds, C.byref(out)), 'eml_measure_fp64_peak')
+    return out.value
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Plan:
+    """Owns one EmlPlan (device copies of the data shared by a batch of models)."""
+
+    def __init__(self, n_tls, n_params, terms, op_table, rho0, obs_site, obs, times, targets=None,
+                 device=0, kernel=KERNEL_AUTO, theta_target=0.0, tol=0.0):
+        lib = load()
+        self._lib = lib
+        self.n_tls, self.n_params = int(n_tls), int(n_params)
+        self.op_table = np.ascontiguousarray(op_table, dtype=np.complex128).reshape(-1, 2, 2)
+        self.rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+        self.obs = np.ascontiguousarray(obs, dtype=np.complex128).reshape(-1, 2, 2)
+        self.times = np.ascontiguousarray(times, dtype=np.float64)
+        self.n_obs, self.n_times = self.obs.shape[0], self.times.shape[0]
+        d = 1 << self.n_tls
+        if self.rho0.shape != (d, d):
+            raise RuntimeError('rho0 has the wrong shape for n_tls')
+        tarr = (EmlTerm * max(1, len(terms)))()
+        for i, t in enumerate(terms):
+            tarr[i] = EmlTerm(*[int(x) for x in t])
+        tg = None
+        nsets = 0
+        if targets is not None:
+            tg = np.ascontiguousarray(targets, dtype=np.complex128)
+            if tg.ndim == 2:
+                tg = tg[None]
+            if tg.shape[1:] != (self.n_obs, self.n_times):
+                raise RuntimeError('targets must have shape [S][K][T]')
+            nsets = tg.shape[0]
+        desc = EmlProblemDesc(self.n_tls, self.n_params, len(terms), tarr,
+                              self.op_table.shape[0], _dptr(self.op_table.view(np.float64)),
+                              _dptr(self.rho0.view(np.float64)),
+                              int(obs_site), self.n_obs, _dptr(self.obs.view(np.float64)),
+                              self.n_times, _dptr(self.times),
+                              nsets, _dptr(tg.view(np.float64)) if tg is not None else None)
+        opts = EmlOptions(float(theta_target), float(tol), int(kernel), 0)
+        handle = C.c_void_p()
+        check(lib.eml_plan_create(C.byref(desc), int(device), C.byref(opts), C.byref(handle)), 'eml_plan_create')
+        self._h = handle
+        self.device = int(device)
+        self.n_target_sets = nsets
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def kernel_name(self) -> str:
+        return self._lib.eml_plan_kernel_name(self._h).decode()
+
+    def set_targets(self, targets):
+        tg = np.ascontiguousarray(targets, dtype=np.complex128)
+        if tg.ndim == 2:
+            tg = tg[None]
+        if tg.shape[1:] != (self.n_obs, self.n_times):
+            raise RuntimeError('targets must have shape [S][K][T]')
+        check(self._lib.eml_plan_set_targets(self._h, tg.shape[0], _dptr(tg.view(np.float64))), 'eml_plan_set_targets')
+        self.n_target_sets = tg.shape[0]
+
+    def eval_host(self, params, target_set=None, want_expect=True, want_loss=True):
+        """params: [B][P] float64 host array.  Returns (expect [B][K][T] complex | None, loss [B] | None)."""
+        params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 0)) \
+            if self.n_params > 0 else np.zeros((int(np.shape(params)[0]), 0))
+        B = params.shape[0]
+        expect = np.empty((B, self.n_obs, self.n_times), dtype=np.complex128) if want_expect else None
+        loss = np.empty(B, dtype=np.float64) if want_loss else None
+        ts = None
+        if target_set is not None:
+            ts = np.ascontiguousarray(target_set, dtype=np.int32)
+            if ts.shape != (B,):
+                raise RuntimeError('target_set must have one entry per model')
+        rc = self._lib.eml_eval_batch_host(
+            self._h, B, _dptr(params) if params.size else None,
+            ts.ctypes.data_as(C.POINTER(C.c_int32)) if ts is not None else None,
+            _dptr(expect.view(np.float64)) if expect is not None else None,
+            _dptr(loss) if loss is not None else None)
+        check(rc, 'eml_eval_batch_host')
+        return expect, loss
+
+    def eval_device(self, n_models, params_ptr, target_set_ptr=0, expect_ptr=0, loss_ptr=0, status_ptr=0, stream=0):
+        """Raw device-pointer entry point (integers from torch's .data_ptr()); no sync, no allocation."""
+        rc = self._lib.eml_eval_batch(self._h, int(n_models), C.c_void_p(params_ptr), C.c_void_p(target_set_ptr or None),
+                                      C.c_void_p(expect_ptr or None), C.c_void_p(loss_ptr or None),
+                                      C.c_void_p(status_ptr or None), C.c_void_p(stream or None))
+        check(rc, 'eml_eval_batch')
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self._lib.eml_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

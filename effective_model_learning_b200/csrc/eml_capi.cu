@@ -1,0 +1,297 @@
+// extern "C" boundary of libeml_b200.so (see include/eml_b200.h).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "eml_common.cuh"
+
+namespace eml {
+cudaError_t launch_generic(const DevProblem& P, long long n_models, const double* params, const int* target_set,
+                           double* expect, double* loss, int* status, cudaStream_t stream);
+size_t generic_smem_bytes(int n, int n_params);
+cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
+                            double* expect, double* loss, int* status, cudaStream_t stream);
+bool warp_mma_supported(const DevProblem& P, bool hermitian);
+cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
+}  // namespace eml
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define EML_CUDA(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess)                                                                                  \
+            return fail(EML_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+    } while (0)
+
+struct EmlPlan {
+    int device = 0;
+    eml::DevProblem P{};
+    int kernel = EML_KERNEL_GENERIC;
+    bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
+    std::vector<void*> owned; // device allocations
+    // staging for the host entry point
+    cudaStream_t stream = nullptr;
+    long long cap_models = 0;
+    double *d_params = nullptr, *d_expect = nullptr, *d_loss = nullptr;
+    int *d_tset = nullptr, *d_status = nullptr;
+    double *h_params = nullptr, *h_expect = nullptr, *h_loss = nullptr;  // pinned
+    int *h_tset = nullptr, *h_status = nullptr;
+    double* d_targets = nullptr;
+    size_t targets_bytes = 0;
+};
+
+template <typename T>
+static int upload(EmlPlan* plan, const T* host, size_t count, const T** out) {
+    *out = nullptr;
+    if (count == 0) return EML_OK;
+    void* d = nullptr;
+    EML_CUDA(cudaMalloc(&d, count * sizeof(T)));
+    plan->owned.push_back(d);
+    EML_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return EML_OK;
+}
+
+static bool op_is_hermitian(const double* op) {
+    // [[a,b],[c,d]] row-major complex
+    const double tol = 1e-15;
+    return std::fabs(op[1]) <= tol && std::fabs(op[7]) <= tol && std::fabs(op[2] - op[4]) <= tol &&
+           std::fabs(op[3] + op[5]) <= tol;
+}
+
+extern "C" {
+
+int eml_version(void) { return EML_VERSION_MAJOR * 1000 + EML_VERSION_MINOR; }
+const char* eml_last_error_string(void) { return g_last_error.c_str(); }
+int64_t eml_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int eml_device_count(int* count) {
+    if (!count) return fail(EML_ERR_INVALID_ARGUMENT, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(EML_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    return EML_OK;
+}
+
+int eml_plan_destroy(EmlPlan* plan) {
+    if (!plan) return EML_OK;
+    cudaSetDevice(plan->device);
+    for (void* p : plan->owned) cudaFree(p);
+    if (plan->d_targets) cudaFree(plan->d_targets);
+    cudaFree(plan->d_params); cudaFree(plan->d_expect); cudaFree(plan->d_loss); cudaFree(plan->d_tset); cudaFree(plan->d_status);
+    cudaFreeHost(plan->h_params); cudaFreeHost(plan->h_expect); cudaFreeHost(plan->h_loss); cudaFreeHost(plan->h_tset); cudaFreeHost(plan->h_status);
+    if (plan->stream) cudaStreamDestroy(plan->stream);
+    delete plan;
+    return EML_OK;
+}
+
+int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* targets) {
+    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n_target_sets < 0 || (n_target_sets > 0 && !targets)) return fail(EML_ERR_INVALID_ARGUMENT, "bad targets");
+    EML_CUDA(cudaSetDevice(plan->device));
+    const size_t bytes = (size_t)n_target_sets * plan->P.n_obs * plan->P.n_times * 2 * sizeof(double);
+    if (bytes > plan->targets_bytes) {
+        EML_CUDA(cudaDeviceSynchronize());
+        if (plan->d_targets) cudaFree(plan->d_targets);
+        plan->d_targets = nullptr;
+        plan->targets_bytes = 0;
+        EML_CUDA(cudaMalloc((void**)&plan->d_targets, bytes));
+        plan->targets_bytes = bytes;
+    }
+    if (bytes) EML_CUDA(cudaMemcpy(plan->d_targets, targets, bytes, cudaMemcpyHostToDevice));
+    plan->P.targets = n_target_sets > 0 ? plan->d_targets : nullptr;
+    plan->P.n_target_sets = n_target_sets;
+    return EML_OK;
+}
+
+int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts, EmlPlan** out) {
+    if (!out) return fail(EML_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!d) return fail(EML_ERR_INVALID_ARGUMENT, "desc is NULL");
+    if (d->n_tls < 1 || d->n_tls > 5) return fail(EML_ERR_UNSUPPORTED, "n_tls must be in 1..5");
+    if (d->n_params < 0 || d->n_terms < 0 || (d->n_terms > 0 && !d->terms))
+        return fail(EML_ERR_INVALID_ARGUMENT, "bad term list");
+    if (d->n_obs < 1 || d->n_obs > eml::MAX_OBS || !d->obs) return fail(EML_ERR_INVALID_ARGUMENT, "n_obs must be in 1..8");
+    if (d->n_times < 1 || !d->times) return fail(EML_ERR_INVALID_ARGUMENT, "need at least one time");
+    if (!d->rho0 || !d->op_table || d->n_ops < 1) return fail(EML_ERR_INVALID_ARGUMENT, "rho0/op_table missing");
+    if (d->obs_site < 0 || d->obs_site >= d->n_tls) return fail(EML_ERR_INVALID_ARGUMENT, "obs_site out of range");
+    for (int k = 1; k < d->n_times; ++k)
+        if (!(d->times[k] >= d->times[k - 1])) return fail(EML_ERR_INVALID_ARGUMENT, "times must be non-decreasing");
+    for (int t = 0; t < d->n_terms; ++t) {
+        const EmlTerm& tm = d->terms[t];
+        const bool coup = tm.kind == EML_TERM_COUPLING;
+        if (tm.kind < 0 || tm.kind > 2 || tm.param < 0 || tm.param >= d->n_params || tm.site_a < 0 ||
+            tm.site_a >= d->n_tls || tm.op_a < 0 || tm.op_a >= d->n_ops ||
+            (coup && (tm.site_b < 0 || tm.site_b >= d->n_tls || tm.site_b == tm.site_a || tm.op_b < 0 || tm.op_b >= d->n_ops)))
+            return fail(EML_ERR_INVALID_ARGUMENT, "term " + std::to_string(t) + " is malformed");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(EML_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(EML_ERR_INVALID_ARGUMENT, "device out of range");
+    EML_CUDA(cudaSetDevice(device));
+
+    EmlPlan* plan = new (std::nothrow) EmlPlan();
+    if (!plan) return fail(EML_ERR_CUDA, "out of host memory");
+    plan->device = device;
+    eml::DevProblem& P = plan->P;
+    P.n_tls = d->n_tls; P.n_params = d->n_params; P.n_terms = d->n_terms; P.n_obs = d->n_obs;
+    P.n_times = d->n_times; P.n_target_sets = 0; P.obs_site = d->obs_site;
+    P.theta_target = (opts && opts->theta_target > 0) ? opts->theta_target : 8.0;
+    P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-14;
+    if (P.theta_target > 8.0) P.theta_target = 8.0;  // MCAP is sized for theta <= 8
+    const int dd = 1 << (2 * d->n_tls);
+    int rc;
+#define EML_TRY(x) if ((rc = (x)) != EML_OK) { eml_plan_destroy(plan); return rc; }
+    EML_TRY(upload(plan, d->terms, (size_t)d->n_terms, &P.terms));
+    EML_TRY(upload(plan, d->op_table, (size_t)d->n_ops * 8, &P.op_table));
+    EML_TRY(upload(plan, d->rho0, (size_t)dd * 2, &P.rho0));
+    EML_TRY(upload(plan, d->obs, (size_t)d->n_obs * 8, &P.obs));
+    EML_TRY(upload(plan, d->times, (size_t)d->n_times, &P.times));
+    EML_TRY(eml_plan_set_targets(plan, d->n_target_sets, d->targets));
+
+    // Hermiticity of the generator inputs decides whether the X + X^dag kernels may be used:
+    // energies use Hermitian ops, every coupling term's op pair is Hermitian (x) Hermitian, rho0 = rho0^dag.
+    bool herm = true;
+    for (int t = 0; t < d->n_terms && herm; ++t) {
+        const EmlTerm& tm = d->terms[t];
+        if (tm.kind == EML_TERM_LINDBLAD) continue;
+        herm = op_is_hermitian(d->op_table + tm.op_a * 8) &&
+               (tm.kind != EML_TERM_COUPLING || op_is_hermitian(d->op_table + tm.op_b * 8));
+    }
+    const int D = 1 << d->n_tls;
+    for (int r = 0; r < D && herm; ++r)
+        for (int c = 0; c < D; ++c)
+            if (std::fabs(d->rho0[2 * (r * D + c)] - d->rho0[2 * (c * D + r)]) > 1e-15 ||
+                std::fabs(d->rho0[2 * (r * D + c) + 1] + d->rho0[2 * (c * D + r) + 1]) > 1e-15) { herm = false; break; }
+    plan->hermitian = herm;
+
+    int want = opts ? opts->kernel : EML_KERNEL_AUTO;
+    if (want == EML_KERNEL_AUTO) want = eml::warp_mma_supported(P, herm) ? EML_KERNEL_WARP_MMA : EML_KERNEL_GENERIC;
+    if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(P, herm)) {
+        eml_plan_destroy(plan);
+        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls == 4 (d = 16) and Hermitian H, rho0");
+    }
+    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA) {
+        eml_plan_destroy(plan);
+        return fail(EML_ERR_INVALID_ARGUMENT, "unknown kernel id");
+    }
+    plan->kernel = want;
+    if (eml::generic_smem_bytes(d->n_tls, d->n_params) > 220 * 1024) {
+        eml_plan_destroy(plan);
+        return fail(EML_ERR_UNSUPPORTED, "parameter vector too long for shared memory");
+    }
+    *out = plan;
+    return EML_OK;
+}
+
+const char* eml_plan_kernel_name(const EmlPlan* plan) {
+    if (!plan) return "";
+    return plan->kernel == EML_KERNEL_WARP_MMA ? "warp_mma" : "generic";
+}
+
+int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
+                   double* loss, int32_t* status, void* stream) {
+    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
+    if (n_models == 0) return EML_OK;
+    if (!params && plan->P.n_params > 0) return fail(EML_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (target_set && plan->P.n_target_sets == 0) return fail(EML_ERR_INVALID_ARGUMENT, "target_set given but plan has no targets");
+    int cur = -1;
+    EML_CUDA(cudaGetDevice(&cur));
+    if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
+    cudaError_t e;
+    if (plan->kernel == EML_KERNEL_WARP_MMA)
+        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
+    else
+        e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
+    g_launches.fetch_add(1);
+    if (cur != plan->device && cur >= 0) cudaSetDevice(cur);
+    if (e != cudaSuccess) return fail(EML_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return EML_OK;
+}
+
+static int ensure_staging(EmlPlan* plan, long long n) {
+    if (!plan->stream) EML_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
+    if (n <= plan->cap_models) return EML_OK;
+    long long cap = plan->cap_models ? plan->cap_models : 1;
+    while (cap < n) cap *= 2;
+    EML_CUDA(cudaStreamSynchronize(plan->stream));
+    cudaFree(plan->d_params); cudaFree(plan->d_expect); cudaFree(plan->d_loss); cudaFree(plan->d_tset); cudaFree(plan->d_status);
+    cudaFreeHost(plan->h_params); cudaFreeHost(plan->h_expect); cudaFreeHost(plan->h_loss); cudaFreeHost(plan->h_tset); cudaFreeHost(plan->h_status);
+    plan->d_params = plan->d_expect = plan->d_loss = nullptr; plan->d_tset = plan->d_status = nullptr;
+    plan->h_params = plan->h_expect = plan->h_loss = nullptr; plan->h_tset = plan->h_status = nullptr;
+    plan->cap_models = 0;
+    const size_t np = (size_t)cap * (plan->P.n_params > 0 ? plan->P.n_params : 1);
+    const size_t ne = (size_t)cap * plan->P.n_obs * plan->P.n_times * 2;
+    EML_CUDA(cudaMalloc((void**)&plan->d_params, np * sizeof(double)));
+    EML_CUDA(cudaMalloc((void**)&plan->d_expect, ne * sizeof(double)));
+    EML_CUDA(cudaMalloc((void**)&plan->d_loss, cap * sizeof(double)));
+    EML_CUDA(cudaMalloc((void**)&plan->d_tset, cap * sizeof(int)));
+    EML_CUDA(cudaMalloc((void**)&plan->d_status, cap * sizeof(int)));
+    EML_CUDA(cudaMallocHost((void**)&plan->h_params, np * sizeof(double)));
+    EML_CUDA(cudaMallocHost((void**)&plan->h_expect, ne * sizeof(double)));
+    EML_CUDA(cudaMallocHost((void**)&plan->h_loss, cap * sizeof(double)));
+    EML_CUDA(cudaMallocHost((void**)&plan->h_tset, cap * sizeof(int)));
+    EML_CUDA(cudaMallocHost((void**)&plan->h_status, cap * sizeof(int)));
+    plan->cap_models = cap;
+    return EML_OK;
+}
+
+int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
+                        double* expect, double* loss) {
+    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
+    if (n_models == 0) return EML_OK;
+    if (!params && plan->P.n_params > 0) return fail(EML_ERR_INVALID_ARGUMENT, "params is NULL");
+    int cur = -1;
+    EML_CUDA(cudaGetDevice(&cur));
+    EML_CUDA(cudaSetDevice(plan->device));
+    int rc = ensure_staging(plan, n_models);
+    if (rc != EML_OK) return rc;
+    const size_t np = (size_t)n_models * plan->P.n_params;
+    const size_t ne = (size_t)n_models * plan->P.n_obs * plan->P.n_times * 2;
+    cudaStream_t s = plan->stream;
+    if (np) {
+        std::memcpy(plan->h_params, params, np * sizeof(double));
+        EML_CUDA(cudaMemcpyAsync(plan->d_params, plan->h_params, np * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    if (target_set) {
+        std::memcpy(plan->h_tset, target_set, n_models * sizeof(int));
+        EML_CUDA(cudaMemcpyAsync(plan->d_tset, plan->h_tset, n_models * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    rc = eml_eval_batch(plan, n_models, plan->d_params, target_set ? plan->d_tset : nullptr,
+                        expect ? plan->d_expect : nullptr, loss ? plan->d_loss : nullptr, plan->d_status, s);
+    if (rc != EML_OK) return rc;
+    if (expect) EML_CUDA(cudaMemcpyAsync(plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (loss) EML_CUDA(cudaMemcpyAsync(plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EML_CUDA(cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s));
+    EML_CUDA(cudaStreamSynchronize(s));
+    if (expect) std::memcpy(expect, plan->h_expect, ne * sizeof(double));
+    if (loss) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
+    if (cur >= 0 && cur != plan->device) cudaSetDevice(cur);
+    for (long long i = 0; i < n_models; ++i)
+        if (plan->h_status[i] != 0)
+            return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " hit the Taylor cap");
+    return EML_OK;
+}
+
+int eml_measure_fp64_peak(int device, int use_mma, double seconds, double* flops_per_s) {
+    if (!flops_per_s) return fail(EML_ERR_INVALID_ARGUMENT, "flops_per_s is NULL");
+    EML_CUDA(cudaSetDevice(device));
+    EML_CUDA(eml::measure_fp64(use_mma, seconds, flops_per_s));
+    return EML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Shared device-side definitions for the Lindblad evaluator kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "eml_b200.h"
+
+namespace eml {
+
+constexpr int QMAX = 16;   // output times covered by one Taylor expansion (dense output)
+constexpr int MCAP = 64;   // hard cap on Taylor terms per expansion (theta <= 8 converges by ~45)
+constexpr int MAX_OBS = 8;
+
+// Device-resident constants of a plan; passed to kernels by value.
+struct DevProblem {
+    int n_tls, n_params, n_terms, n_obs, n_times, n_target_sets, obs_site;
+    const EmlTerm* terms;   // [n_terms]
+    const double* op_table; // [n_ops][8]
+    const double* rho0;     // [d*d][2]
+    const double* obs;      // [K][8]
+    const double* times;    // [T]
+    const double* targets;  // [S][K][T][2] or nullptr
+    double theta_target;
+    double tol;
+};
+
+struct cplx {
+    double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cconj(cplx a) { return {a.re, -a.im}; }
+__device__ __forceinline__ cplx ld_op(const double* __restrict__ op_table, int op, int row, int col) {
+    const double* p = op_table + op * 8 + (row * 2 + col) * 2;
+    return {p[0], p[1]};
+}
+
+// Macro-step schedule shared by all kernels so that they produce the same expansion points:
+// starting at output index k (state known at times[k]) choose q >= 1 output intervals to cover
+// with one expansion such that nu * span <= theta (at least one), and nsub >= 1 sub-steps when
+// a single interval alone exceeds theta.
+__device__ __forceinline__ void choose_step(const double* __restrict__ times, int T, int k, double nu, double theta,
+                                            int& q, int& nsub, double& htot) {
+    const double t0 = times[k];
+    q = 1;
+    while (q < QMAX && k + q < T - 1 && nu * (times[k + q + 1] - t0) <= theta) ++q;
+    htot = times[k + q] - t0;
+    nsub = 1;
+    if (q == 1) {
+        const double th = nu * htot;
+        if (th > theta) nsub = (int)ceil(th / theta);
+    }
+}
+
+}  // namespace eml

@@ -1,0 +1,137 @@
+/*
+ * eml_b200.h -- C ABI of the B200-native Lindblad model evaluator.
+ *
+ * This is the drop-in boundary for ONE hot path of henry104413/effective_model_learning:
+ *
+ *     LearningChain.total_dev(model)            reference learning_chain.py:714-742
+ *       -> BasicModel.calculate_dynamics(...)   reference basic_model.py:314-393
+ *            -> qutip.mesolve(H, rho0, times, c_ops, e_ops)      basic_model.py:381-388
+ *
+ * i.e. "parameters of a TLS model -> <O_m>(t_k) for every observable and time -> mean
+ * squared deviation from the target data".  The reference has no FFI of its own (it is
+ * pure Python calling qutip); these entry points are what a ctypes binding inserted at
+ * basic_model.py:381 would call instead of qutip.mesolve.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all matrices row-major, complex numbers as
+ *     interleaved (re, im) doubles; site 0 is the MOST significant factor of the
+ *     Kronecker product (qutip.tensor order, reference definitions.py:28-38).
+ *   - every function returns EML_OK (0) or a negative EmlStatus; nothing throws across
+ *     the ABI; eml_last_error_string() gives the thread-local message.
+ *   - a plan owns device copies of everything shared by a batch (operator library,
+ *     rho0, observables, times, targets).  eml_eval_batch() takes DEVICE pointers,
+ *     allocates nothing, does not synchronise and launches on the caller's stream.
+ *     eml_eval_batch_host() takes HOST pointers and stages through buffers owned by the
+ *     plan (host<->device copies included), returning after the results are on the host.
+ *   - a plan is bound to one device; calls on one plan must not overlap in time
+ *     (different plans / devices are independent).
+ */
+#ifndef EML_B200_H
+#define EML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EML_VERSION_MAJOR 0
+#define EML_VERSION_MINOR 1
+
+typedef enum EmlStatus {
+    EML_OK = 0,
+    EML_ERR_INVALID_ARGUMENT = -1,
+    EML_ERR_CUDA = -2,
+    EML_ERR_UNSUPPORTED = -3,   /* e.g. n_tls outside 1..5 */
+    EML_ERR_NOT_CONVERGED = -4, /* a model hit the Taylor cap (reported by the host entry point) */
+    EML_ERR_NO_DEVICE = -5
+} EmlStatus;
+
+/* How one library process enters the generator.  `param` selects the column of the
+ * per-model parameter vector that carries its value v (0.0 = process absent,
+ * reference basic_model.py:575-765 `vectorise_under_library`). */
+typedef enum EmlTermKind {
+    EML_TERM_ENERGY = 0,   /* H += v   * op_a@site_a                     basic_model.py:206-221 */
+    EML_TERM_COUPLING = 1, /* H += v^2 * op_a@site_a (x) op_b@site_b     basic_model.py:226-251 (strength on both factors) */
+    EML_TERM_LINDBLAD = 2  /* c  = sqrt(v) * op_a@site_a                 basic_model.py:152-189 */
+} EmlTermKind;
+
+typedef struct EmlTerm {
+    int32_t param;  /* column of params[b][*] */
+    int32_t kind;   /* EmlTermKind */
+    int32_t site_a; /* 0 .. n_tls-1 */
+    int32_t site_b; /* coupling partner, else -1 */
+    int32_t op_a;   /* row of op_table */
+    int32_t op_b;   /* row of op_table (couplings), else -1 */
+} EmlTerm;
+
+/* Everything shared by the models of a batch.  All pointers are HOST pointers and are
+ * copied by eml_plan_create. */
+typedef struct EmlProblemDesc {
+    int32_t n_tls;    /* number of two-level systems n; d = 2^n; 1 <= n <= 5 */
+    int32_t n_params; /* P: length of one model's parameter vector */
+    int32_t n_terms;
+    const EmlTerm* terms; /* [n_terms] */
+    int32_t n_ops;
+    const double* op_table; /* [n_ops][8]: 2x2 complex, row-major (definitions.py:42-61) */
+    const double* rho0;     /* [d*d][2]: initial density matrix (basic_model.py:259-281) */
+    int32_t obs_site;       /* site the observables act on (first qubit, basic_model.py:365-375) */
+    int32_t n_obs;          /* K, 1..8 */
+    const double* obs;      /* [K][8]: 2x2 complex operators */
+    int32_t n_times;        /* T >= 1; rho0 sits at times[0] (qutip semantics) */
+    const double* times;    /* [T], non-decreasing */
+    int32_t n_target_sets;  /* S >= 0 */
+    const double* targets;  /* [S][K][T][2] complex targets, or NULL when S == 0 */
+} EmlProblemDesc;
+
+typedef struct EmlPlan EmlPlan; /* opaque */
+
+/* Tunables of the evaluator (0 / negative = keep default). */
+typedef struct EmlOptions {
+    double theta_target; /* norm-bound * step targeted per Taylor expansion (default 8) */
+    double tol;          /* absolute per-element stopping tolerance (default 1e-14) */
+    int32_t kernel;      /* EML_KERNEL_AUTO or a specific kernel, for tests/benchmarks */
+    int32_t reserved;
+} EmlOptions;
+
+#define EML_KERNEL_AUTO 0
+#define EML_KERNEL_GENERIC 1 /* one CTA per model, rho in shared memory, FP64 FMA */
+#define EML_KERNEL_WARP_MMA 2 /* one warp per model, rho in registers, FP64 DMMA (n_tls == 4) */
+
+int eml_version(void);
+const char* eml_last_error_string(void);
+int eml_device_count(int* count);
+
+int eml_plan_create(const EmlProblemDesc* desc, int device, const EmlOptions* opts, EmlPlan** out);
+int eml_plan_destroy(EmlPlan* plan);
+/* replace the targets of an existing plan (same K, T); host pointer */
+int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* targets);
+
+/*
+ * Evaluate n_models models.  DEVICE pointers:
+ *   params      [n_models][P]            parameter vectors
+ *   target_set  [n_models] or NULL       which target set each model is scored against (NULL = set 0)
+ *   expect      [n_models][K][T][2] or NULL   <O_m>(t_k), complex
+ *   loss        [n_models] or NULL       sum_m sum_k |expect - target|^2 / (T*K)   (learning_chain.py:738-742)
+ *   status      [n_models] or NULL       0 = ok, 1 = Taylor cap hit
+ * `stream` is a cudaStream_t passed as void*.
+ */
+int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
+                   double* expect, double* loss, int32_t* status, void* stream);
+
+/* Same with HOST pointers; copies in, launches, copies out and synchronises. */
+int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
+                        double* expect, double* loss);
+
+/* Number of kernels launched through this library since load (for bench accounting). */
+int64_t eml_launch_count(void);
+/* Name of the kernel the plan dispatches to ("generic", "warp_mma", ...). */
+const char* eml_plan_kernel_name(const EmlPlan* plan);
+/* FP64 microbenchmarks used to establish the roofline denominator (flops per second). */
+int eml_measure_fp64_peak(int device, int use_mma, double seconds, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EML_B200_H */

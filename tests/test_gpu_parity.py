@@ -1,0 +1,99 @@
+"""GPU parity: CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import lindblad_oracle as lo
+from tests.helpers import OBS3, model_from_spec, assert_close, max_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8   # north_star: observables within 1e-8 (relative, floor 1) of the exact solution
+
+
+@pytest.mark.parametrize('n_defects', [0, 1, 2, 3])
+def test_random_library_models_match_oracle(n_defects):
+    ts = np.linspace(0.0, 2.5, 200)
+    worst = 0.0
+    for b in range(6):
+        spec = lo.random_library_spec(np.random.default_rng(1000 + b), 1, n_defects)
+        want = lo.expect_exact(spec, ts, OBS3)
+        got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
+        assert_close(got, want, TOL, f'D={n_defects} b={b}')
+        assert all(g.dtype == np.float64 for g in got)
+        worst = max(worst, max_err(got, want))
+    print(f'd={2 ** (1 + n_defects)} worst abs err vs exact oracle: {worst:.2e}')
+
+
+def test_two_qubits_three_defects_d32():
+    ts = np.linspace(0.0, 2.5, 60)
+    spec = lo.random_library_spec(np.random.default_rng(7), 2, 3)
+    want = lo.expect_exact(spec, ts, OBS3)
+    got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
+    assert_close(got, want, TOL, 'd=32')
+
+
+def test_default_observable_and_nonhermitian_observable():
+    ts = np.linspace(0.0, 1.0, 33)
+    spec = lo.random_library_spec(np.random.default_rng(3), 1, 2)
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(ts)                       # default 'exc'
+    assert_close(got, lo.expect_exact(spec, ts, False), TOL, 'exc')
+    got = m.calculate_dynamics(ts, ['sigmap', 'sigmam', 'sigmaz'])
+    want = lo.expect_exact(spec, ts, ['sigmap', 'sigmam', 'sigmaz'])
+    assert got[0].dtype == np.complex128 and got[2].dtype == np.float64
+    assert_close(got, want, TOL, 'non-hermitian obs')
+
+
+def test_nonuniform_grid_and_repeated_times():
+    rng = np.random.default_rng(11)
+    ts = np.sort(np.concatenate([[0.3], 0.3 + np.cumsum(rng.uniform(1e-4, 0.2, 70))]))
+    ts[10] = ts[9]                                        # a repeated time point (zero-length interval)
+    spec = lo.random_library_spec(np.random.default_rng(5), 1, 2)
+    got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
+    assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, 'non-uniform')
+
+
+def test_long_interval_needs_substeps():
+    ts = np.array([0.0, 5.0, 5.5, 30.0])
+    spec = lo.random_library_spec(np.random.default_rng(9), 1, 2)
+    got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
+    assert_close(got, lo.expect_zvode(spec, ts, OBS3), 1e-7, 'long intervals (vs tight ZVODE)')
+    assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, 'long intervals')
+
+
+def test_general_ops_nonhermitian_generator():
+    """sigmam/sigmap jump operators, asymmetric op pairs (non-Hermitian H), non-default initial states."""
+    spec = {'tls': [
+        {'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmam': 0.2, 'sigmaz': 0.05}, 'initial_state': lo.OPS['2e+1g'],
+         'couplings': [(1, 0.8, [('sigmap', 'sigmam'), ('sigmam', 'sigmap')]), (2, 0.5, [('sigmap', 'sigmam')])]},
+        {'is_qubit': False, 'energy': 0.3, 'Ls': {'sigmap': 0.1, 'sigmax': 0.07}, 'initial_state': None, 'couplings': []},
+        {'is_qubit': False, 'energy': 0.2, 'Ls': {'exc': 0.3}, 'initial_state': lo.OPS['mm'],
+         'couplings': [(1, 1.1, [('sigmax', 'sigmaz')])]},
+    ]}
+    ts = np.linspace(0, 3, 50)
+    got = model_from_spec(spec).calculate_dynamics(ts, ['sigmax', 'sigmap', 'exc'])
+    assert_close(got, lo.expect_exact(spec, ts, ['sigmax', 'sigmap', 'exc']), TOL, 'general ops')
+
+
+def test_single_time_and_single_qubit():
+    spec = {'tls': [{'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmaz': 0.1}, 'initial_state': None, 'couplings': []}]}
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(np.array([0.7]), OBS3)
+    assert_close(got, lo.expect_exact(spec, np.array([0.7]), OBS3), TOL, 'single time')
+    ts = np.linspace(0, 4, 101)
+    got = m.calculate_dynamics(ts, OBS3)
+    # closed form: plus state under E sigmaz with sigmaz dephasing gamma (SURVEY.md section 4 iii, iv)
+    np.testing.assert_allclose(got[0], np.exp(-2 * 0.1 * ts) * np.cos(2 * ts), atol=1e-10)
+    np.testing.assert_allclose(got[1], np.exp(-2 * 0.1 * ts) * np.sin(2 * ts), atol=1e-10)
+    np.testing.assert_allclose(got[2], 0 * ts, atol=1e-10)
+
+
+def test_errors_match_reference_contract():
+    from effective_model_learning_b200 import BasicModel
+    m = BasicModel()
+    m.add_TLS('qubit', True, 1.0)
+    with pytest.raises(RuntimeError):
+        m.calculate_dynamics(np.linspace(0, 1, 5))       # build_operators() not called
+    m.build_operators()
+    with pytest.raises(RuntimeError):
+        m.calculate_dynamics(np.linspace(0, 1, 5), observable_ops=[1, 2])
