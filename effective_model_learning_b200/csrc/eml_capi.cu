@@ -282,7 +282,7 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     if (loss) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
     if (cur >= 0 && cur != plan->device) cudaSetDevice(cur);
     for (long long i = 0; i < n_models; ++i)
-        if (plan->h_status[i] != 0)
+        if (plan->h_status[i] < 0)
             return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " hit the Taylor cap");
     return EML_OK;
 }

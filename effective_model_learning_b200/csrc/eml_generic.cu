@@ -172,7 +172,8 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
     if (active) { acc_re = P.rho0[2 * tid]; acc_im = P.rho0[2 * tid + 1]; }
     double y_re[QMAX], y_im[QMAX], xs[QMAX], xp[QMAX];
     double my_loss = 0.0;
-    int my_status = 0;
+    int n_apply = 0;
+    bool capped = false;
     const int tset = (target_set != nullptr) ? target_set[b] : 0;
     const double* tgt = (P.targets != nullptr) ? P.targets + (size_t)tset * K * T * 2 : nullptr;
 
@@ -297,7 +298,8 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
                     small = 0;
                 }
             }
-            if (j >= MCAP) my_status = 1;
+            n_apply += (j < MCAP) ? j + 1 : MCAP;
+            if (j >= MCAP) capped = true;
         }
         emit(q, k + 1);
         k += q;
@@ -313,7 +315,7 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
             for (int i = 0; i < nlb; ++i) s += lossbuf[i];
             loss[b] = (tgt != nullptr) ? s / ((double)T * (double)K) : 0.0;
         }
-        if (status != nullptr) status[b] = my_status;
+        if (status != nullptr) status[b] = capped ? -1 : n_apply;
     }
 }
 

@@ -114,7 +114,8 @@ int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* tar
  *   target_set  [n_models] or NULL       which target set each model is scored against (NULL = set 0)
  *   expect      [n_models][K][T][2] or NULL   <O_m>(t_k), complex
  *   loss        [n_models] or NULL       sum_m sum_k |expect - target|^2 / (T*K)   (learning_chain.py:738-742)
- *   status      [n_models] or NULL       0 = ok, 1 = Taylor cap hit
+ *   status      [n_models] or NULL       >= 0: number of generator applications (Taylor terms) the model
+ *                                        needed; -1: the Taylor cap was hit (result not converged)
  * `stream` is a cudaStream_t passed as void*.
  */
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,

@@ -24,3 +24,14 @@ def pytest_collection_modifyitems(config, items):
     # GPU tests are selected with -m gpu; when selected on a box without a device they must
     # fail loudly rather than skip, so nothing is done here beyond registering the marker.
     return
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """Route EvalContext.evaluate to the CPU oracle (host-logic tests on a box without a GPU)."""
+    from effective_model_learning_b200 import engine
+    from tests.helpers import oracle_evaluate
+    monkeypatch.setattr(engine.EvalContext, 'evaluate', oracle_evaluate)
+    engine.clear_contexts()
+    yield
+    engine.clear_contexts()

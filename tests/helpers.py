@@ -37,3 +37,38 @@ def assert_close(got, want, tol=1e-8, what=''):
 
 def max_err(got, want):
     return max(float(np.abs(np.asarray(a) - np.asarray(b)).max()) for a, b in zip(got, want))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU stand-in for the device, for host-logic tests ONLY (tests may use the oracle; the product
+# never does).  It receives exactly what the C ABI would receive -- the context's library and one
+# parameter row per model -- so it also checks the marshalling.
+def spec_from_context_row(ctx, row):
+    tls = [{'is_qubit': (k == ctx.obs_site), 'energy': 0.0, 'Ls': {}, 'couplings': [],
+            'initial_state': np.array(ctx.site_states[k])} for k in range(ctx.n_tls)]
+    for key, col in ctx.columns.items():
+        v = float(row[col])
+        if v == 0.0:
+            continue
+        if key[0] == 'E':
+            tls[key[1]]['energy'] = v
+        elif key[0] == 'C':
+            tls[key[1]]['couplings'].append((key[2], v, list(key[3])))
+        else:
+            tls[key[1]]['Ls'][key[2]] = v
+    return {'tls': tls}
+
+
+def oracle_evaluate(ctx, params, target_set=None, want_expect=True, want_loss=False):
+    params = np.atleast_2d(params)
+    B, K, T = params.shape[0], len(ctx.obs_names), len(ctx.times)
+    expect = np.zeros((B, K, T), dtype=np.complex128)
+    for b in range(B):
+        ex = lo.expect_exact(spec_from_context_row(ctx, params[b]), ctx.times, list(ctx.obs_names))
+        expect[b] = np.array([np.asarray(e, dtype=complex) for e in ex])
+    loss = None
+    if want_loss:
+        tg = ctx.targets if ctx.targets.ndim == 3 else ctx.targets[None]
+        sets = np.zeros(B, dtype=int) if target_set is None else np.asarray(target_set)
+        loss = np.array([np.sum(np.abs(expect[b] - tg[sets[b]]) ** 2) / (T * K) for b in range(B)])
+    return (expect if want_expect else None), loss

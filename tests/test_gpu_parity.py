@@ -97,3 +97,41 @@ def test_errors_match_reference_contract():
     m.build_operators()
     with pytest.raises(RuntimeError):
         m.calculate_dynamics(np.linspace(0, 1, 5), observable_ops=[1, 2])
+
+
+@pytest.mark.parametrize('D', [1, 2])
+def test_chain_on_gpu_replays_reference_accept_reject_sequence(D):
+    """north_star: for fixed seeds the accept/reject sequence matches the reference's (losses to 1e-8)."""
+    import json
+    import os
+    import effective_model_learning_b200 as eml
+    from effective_model_learning_b200 import configs, definitions
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', f'reference_chain_D{D}.json')))
+    config = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[g['config_index']])
+    config['iterations_till_progress_update'] = False
+    np.random.seed(g['seed'])
+    chain = eml.LearningChain(target_times=np.array(g['target_times']),
+                              target_datasets=[np.array(t) for t in g['targets']], target_observables=OBS3,
+                              initial=(1, D), qubit_initial_state=definitions.ops['plus'],
+                              defect_initial_state=definitions.ops['mm'], max_chain_steps=g['steps'], **config)
+    replay = iter(g['coupling_holder_is_first'])
+    chain.process_handler.coupling_holder_choice = lambda first, second: next(replay)
+    with np.errstate(over='ignore'):
+        chain.run()
+    assert chain.run_step_type_tracker == g['step_types']
+    assert [bool(x) for x in chain.run_acceptance_tracker] == g['acceptance']
+    np.testing.assert_allclose(chain.explored_loss, g['loss'], rtol=1e-8, atol=1e-12)
+
+
+def test_frozen_golden_observables_d4_to_d32():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'oracle_observables.npz'))
+    ts = z['times']
+    from effective_model_learning_b200 import engine
+    for (Q, D) in ((1, 1), (1, 2), (1, 3), (2, 3)):
+        seeds = z[f'seeds_Q{Q}_D{D}']
+        models = [model_from_spec(lo.random_library_spec(np.random.default_rng(int(s)), Q, D)) for s in seeds]
+        expect, _ = engine.evaluate_models(models, ts, OBS3)
+        err = np.abs(expect.real - z[f'expect_Q{Q}_D{D}']).max()
+        assert err < TOL, (Q, D, err)
+        assert np.abs(expect.imag).max() < 1e-12

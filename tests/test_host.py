@@ -1,0 +1,184 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU: the device is replaced by the oracle)."""
+import copy
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import effective_model_learning_b200 as eml
+from effective_model_learning_b200 import _native, configs, definitions, engine
+from oracle import lindblad_oracle as lo
+from tests.helpers import OBS3, model_from_spec
+from tests.test_oracle import spec_from_json
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+ROOT = os.path.dirname(os.path.dirname(__file__))
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {(k if isinstance(k, str) else repr(k)): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    return x
+
+
+def test_configs_equal_reference_dump():
+    ref = json.load(open(os.path.join(GOLD, 'reference_configs.json')))
+    assert _jsonable(configs.default_chain_hyperparams) == ref['default_chain_hyperparams']
+    assert list(configs.specific_experiment_chain_hyperparams) == ref['order']
+    assert _jsonable(configs.specific_experiment_chain_hyperparams) == ref['specific_experiment_chain_hyperparams']
+    h = configs.get_hyperparams(ref['order'][0])
+    assert list(h['qubit_Ls_library']) == ['sigmaz'] and h['acceptance_window'] == 10
+
+
+def test_ops_table_is_the_oracles():
+    assert list(definitions.ops) == list(lo.OPS)
+    for k in lo.OPS:
+        assert np.array_equal(definitions.ops[k], lo.OPS[k]), k
+    assert definitions.T(1, definitions.ops['id2']) is definitions.ops['id2']
+    assert definitions.T(definitions.ops['sigmax'], definitions.ops['sigmaz']).shape == (4, 4)
+
+
+def test_model_operators_match_reference_golden():
+    z = np.load(os.path.join(GOLD, 'reference_operators.npz'))
+    meta = json.load(open(os.path.join(GOLD, 'reference_operators_specs.json')))
+    for i, js in enumerate(meta['specs']):
+        m = model_from_spec(spec_from_json(js))
+        assert np.array_equal(m.H, z[f'H_{i}']), i
+        assert len(m.Ls) == z[f'Ls_{i}'].shape[0]
+        for a, b in zip(m.Ls, z[f'Ls_{i}']):
+            assert np.array_equal(a, b)
+        assert np.array_equal(m.initial_DM, z[f'rho0_{i}'])
+
+
+def test_calculate_dynamics_contract(oracle_backend):
+    meta = json.load(open(os.path.join(GOLD, 'reference_operators_specs.json')))
+    z = np.load(os.path.join(GOLD, 'reference_operators.npz'))
+    ts = np.array(meta['times'])
+    for i in (0, 3, 7, 13, 17, 20, 23):
+        m = model_from_spec(spec_from_json(meta['specs'][i]))
+        got = m.calculate_dynamics(ts, OBS3)
+        want = z[f'expect_{i}']
+        assert len(got) == 3
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, atol=1e-12)
+    # default observable, string wrapping, custom function, legacy method names, errors
+    m = model_from_spec(lo.random_library_spec(np.random.default_rng(0), 1, 1))
+    a = m.calculate_dynamics(ts)
+    b = m.calculate_dynamics(ts, 'exc', dynamics_method='qutip')
+    assert len(a) == 1 and np.array_equal(a[0], b[0]) and a[0].dtype == np.float64
+    assert m.calculate_dynamics(ts, ['sigmap'])[0].dtype == np.complex128
+    assert m.calculate_dynamics(ts, 'sigmaz', custom_function_on_return=lambda r: 'wrapped') == 'wrapped'
+    with pytest.raises(RuntimeError):
+        m.calculate_dynamics(ts, [1])
+    with pytest.raises(RuntimeError):
+        eml.BasicModel().calculate_dynamics(ts)
+
+
+def test_no_cpu_fallback_without_device():
+    if _native.device_count() > 0:
+        pytest.skip('a GPU is present')
+    m = model_from_spec(lo.random_library_spec(np.random.default_rng(0), 1, 1))
+    engine.clear_contexts()
+    with pytest.raises(RuntimeError, match='no CUDA device|eml_plan_create'):
+        m.calculate_dynamics(np.linspace(0, 1, 5))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib = _native.load()
+    header = open(os.path.join(ROOT, 'include', 'eml_b200.h')).read()
+    declared = set(re.findall(r'\b(eml_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.eml_version() == 1
+
+
+def test_add_TLS_input_normalisation():
+    m = eml.BasicModel()
+    q = m.add_TLS('qubit', True, 1.0)
+    d = m.add_TLS('d', False, 0.2, couplings={'qubit': (0.5, ('sigmax', 'sigmax'))})
+    assert d.couplings == {q: [(0.5, [('sigmax', 'sigmax')])]}
+    with pytest.raises(RuntimeError):
+        m.add_TLS('bad', False, 0.2, couplings={'qubit': [(0.5, 'sigmax', 'sigmax')]})
+    assert 'Qubit' in m.model_description_str()
+    assert m.model_description_dict()['1']['couplings:'] == {'0': [(0.5, [('sigmax', 'sigmax')])]}
+
+
+def test_vectorise_matches_reference_and_round_trips():
+    meta = json.load(open(os.path.join(GOLD, 'reference_operators_specs.json')))
+    vec = json.load(open(os.path.join(GOLD, 'reference_vectorise.json')))
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    for i in range(12):
+        spec = spec_from_json(meta['specs'][i])
+        m = model_from_spec(spec, eml.LearningModel)
+        vals, labels, latex = m.vectorise_under_library(hyper)
+        assert labels == vec[i]['labels']
+        assert [float(v) for v in vals] == vec[i]['values']
+        D = len(spec['tls']) - 1
+        back = eml.LearningModel().configure_to_params_vector((vals, labels, latex), D=D, default_qubit_energy=1.0,
+                                                              qubit_initial_state=definitions.ops['plus'],
+                                                              defect_initial_state=definitions.ops['mm'])
+        assert back.vectorise_under_library(hyper)[0] == vals
+        np.testing.assert_allclose(back.H, m.H, atol=1e-15)
+
+
+def test_marshalling_canonical_processes():
+    m = eml.BasicModel()
+    q = m.add_TLS('qubit', True, 1.0, Ls={'sigmaz': 0.1})
+    d = m.add_TLS('d', False, 0.2, couplings={'qubit': [(0.5, [('sigmax', 'sigmay')]), (0.7, [('sigmax', 'sigmay')])]})
+    m.build_operators()
+    procs = dict(engine.model_processes(m))
+    # held by the defect with (op_defect, op_qubit): canonical form puts the qubit (site 0) first and swaps the pair
+    assert procs[('C', 0, 1, (('sigmay', 'sigmax'),), 0)] == 0.5
+    assert procs[('C', 0, 1, (('sigmay', 'sigmax'),), 1)] == 0.7     # repeated type keeps its own column (s^2 does not add)
+    assert procs[('L', 0, 'sigmaz')] == 0.1 and procs[('E', 1)] == 0.2
+
+
+def test_deepcopy_is_independent():
+    m = model_from_spec(lo.random_library_spec(np.random.default_rng(3), 1, 2), eml.LearningModel)
+    c = copy.deepcopy(m)
+    assert c.vectorise_under_library(configs.default_chain_hyperparams)[0] == m.vectorise_under_library(configs.default_chain_hyperparams)[0]
+    for t, u in zip(m.TLSs, c.TLSs):
+        assert t is not u and u.model is c
+        for p in u.couplings:
+            assert p in c.TLSs
+    c.TLSs[1].Ls['sigmax'] = 0.123
+    c.TLSs[1].energy = 9.0
+    assert m.TLSs[1].Ls.get('sigmax') != 0.123 and m.TLSs[1].energy != 9.0
+
+
+@pytest.mark.parametrize('D', [1, 2])
+def test_chain_replays_reference_trajectory(oracle_backend, D):
+    """
+    Same seed, same hyperparameters as the REAL reference chain recorded in make_golden.py: the port must
+    propose the same moves, compute the same losses and take the same accept/reject decisions.
+    """
+    g = json.load(open(os.path.join(GOLD, f'reference_chain_D{D}.json')))
+    config = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[g['config_index']])
+    config['iterations_till_progress_update'] = False
+    np.random.seed(g['seed'])
+    chain = eml.LearningChain(target_times=np.array(g['target_times']),
+                              target_datasets=[np.array(t) for t in g['targets']], target_observables=OBS3,
+                              initial=(1, D), qubit_initial_state=definitions.ops['plus'],
+                              defect_initial_state=definitions.ops['mm'], max_chain_steps=g['steps'],
+                              store_all_proposals=True, **config)
+    replay = iter(g['coupling_holder_is_first'])
+    chain.process_handler.coupling_holder_choice = lambda first, second: next(replay)
+    with np.errstate(over='ignore'):
+        best = chain.run()
+    assert chain.run_step_type_tracker == g['step_types']
+    assert [bool(x) for x in chain.run_acceptance_tracker] == g['acceptance']
+    np.testing.assert_allclose(chain.explored_loss, g['loss'], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(chain.explored_acceptance_probability, g['acceptance_probability'], rtol=1e-5)
+    assert [chain.tot_RJ_steps, chain.acc_RJ_steps, chain.tot_tweak_steps, chain.acc_tweak_steps] == g['counters']
+    vals, labels, _ = best.vectorise_under_library(config)
+    assert labels == g['best_labels']
+    np.testing.assert_allclose(vals, g['best_values'], rtol=1e-12)
+    assert best.final_loss == pytest.approx(g['best_loss'], rel=1e-9)
+    assert set(chain.all_proposals) == {'proposals', 'loss', 'acceptance', 'log_posterior', 'log_likelihood_prior',
+                                        'acceptance_probability', 'annealed', 'step_types'}
+    assert len(chain.explored_proposals) == 1 + sum(g['acceptance'])
