@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""
+Benchmark of the hot path: model evaluations per second for the 4-TLS (d = 16) library
+(BASELINE.json `metric`, workload `configs[2]`: 1 qubit + 3 defects, 4096 chains per GPU, 200 evaluation
+times, 3 observables).  One "step" = one pass of the hot path over one batch: every chain's current proposal
+(4096 parameter vectors per GPU) -> Lindblad dynamics at the target times -> observables -> loss.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (CUDA kernels)
+    python bench.py --impl reference [...]                         # the reference's CPU path (emulated qutip mesolve)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how every field is measured.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OBS3 = ['sigmax', 'sigmay', 'sigmaz']
+N_TIMES = 200
+T_SPAN = (0.0, 2.5)
+CONFIG_INDEX = 11          # configs.py "EVERYTHING" library
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--chains', type=int, default=4096, help='chains (models per step) per GPU')
+    ap.add_argument('--defects', type=int, default=3)
+    ap.add_argument('--qubits', type=int, default=1)
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'warp_mma'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='models in the CPU-baseline sample (0 = 8 per core)')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# shared workload (product-side generator; tests check it equals the oracle's random_library_spec)
+def make_layout(args):
+    from effective_model_learning_b200 import configs, synthetic
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[CONFIG_INDEX])
+    return synthetic.LibraryLayout(args.qubits, args.defects, hyper), hyper
+
+
+def workload_name(args):
+    d = 2 ** (args.qubits + args.defects)
+    return (f'{args.qubits} qubit + {args.defects} defects (d={d}), {args.chains} chains/GPU, '
+            f'{N_TIMES} times on [0,2.5], observables sx,sy,sz, library config {CONFIG_INDEX}')
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference path: the reference evaluates one model per qutip.mesolve call, chains as parallel OS
+# processes (launch_execute_learning_multiset.sh:60-63).  qutip is not installable, so the timed code is
+# the oracle's restatement of qutip 4.7.5 mesolve (CSR Liouvillian + ZVODE adams/12, atol 1e-8, rtol 1e-6).
+def _cpu_worker(rows):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle import lindblad_oracle as lo
+    from effective_model_learning_b200 import configs, synthetic
+    (Q, D, rows, targets) = rows
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[CONFIG_INDEX])
+    layout = synthetic.LibraryLayout(Q, D, hyper)
+    ts = np.linspace(*T_SPAN, N_TIMES)
+    out = []
+    for row in rows:
+        spec = lo.spec_from_model(layout.model_from_params(row))
+        ex = lo.expect_qutip_emulation(spec, ts, OBS3)
+        out.append(lo.total_dev(ex, targets, N_TIMES))
+    return out
+
+
+class CpuPool:
+    def __init__(self):
+        import multiprocessing as mp
+        self.cores = os.cpu_count() or 1
+        for v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+            os.environ[v] = '1'
+        self.pool = mp.get_context('spawn').Pool(self.cores)
+
+    def evaluate(self, Q, D, rows, targets):
+        chunks = [c for c in np.array_split(np.asarray(rows), self.cores) if len(c)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [(Q, D, c, targets) for c in chunks])
+        dt = time.perf_counter() - t0
+        return dt, [x for r in res for x in r]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_targets(args, layout):
+    """Targets for the CPU arm: exact observables of the ground-truth model + N(0, 0.01^2) (oracle allowed here)."""
+    from oracle import lindblad_oracle as lo
+    truth = layout.random_params(np.random.default_rng(20260000 + 10 * args.qubits + args.defects))
+    ts = np.linspace(*T_SPAN, N_TIMES)
+    ex = lo.expect_exact(lo.spec_from_model(layout.model_from_params(truth)), ts, OBS3)
+    noise = np.random.default_rng(4242)
+    return [np.asarray(e) + noise.normal(0, 0.01, N_TIMES) for e in ex]
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    layout, _ = make_layout(args)
+    targets = cpu_targets(args, layout)
+    pool = CpuPool()
+    per_step = args.cpu_sample or 8 * pool.cores
+    per_step = min(per_step, args.chains)
+    rows = layout.batch_params(1000 + np.arange(per_step))
+    for _ in range(max(1, min(args.warmup, 1))):
+        pool.evaluate(args.qubits, args.defects, rows[:pool.cores], targets)
+    t_total = 0.0
+    for _ in range(args.steps):
+        dt, _ = pool.evaluate(args.qubits, args.defects, rows, targets)
+        t_total += dt
+    pool.close()
+    value = per_step * args.steps / t_total
+    sample = f'{per_step} of the {args.chains} models of the batch per step (seeds 1000..{1000 + per_step - 1})'
+    line = {
+        'impl': 'reference', 'metric': 'model evaluations/sec (4-TLS, d=16)' if (args.qubits, args.defects) == (1, 3)
+        else 'model evaluations/sec', 'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (complex128)', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'algorithm': 'emulated qutip 4.7.5 mesolve: CSR Liouvillian + '
+                   'scipy ZVODE adams/12 atol 1e-8 rtol 1e-6, one OS process per core (qutip itself is not installable)'},
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': pool.cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(device)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for (t, line) in self.rows:
+            if not (t0 - 0.05 <= t <= t1 + 0.05):
+                continue
+            parts = [p.strip() for p in line.split(',')]
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, p in zip(names, parts[3:7]):
+                if p.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:   # region shorter than the sampling period: use the nearest samples
+            for (t, line) in self.rows[-3:]:
+                parts = [p.strip() for p in line.split(',')]
+                try:
+                    sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def canonical_dense_flops(n_tls, T, K):
+    """Pade-13 scaling-and-squaring expm (s=0) + T-1 mat-vecs + traces, N = d^2."""
+    N = 4 ** n_tls
+    return 8 * N ** 3 * 6 + (32 / 3) * N ** 3 + 8 * N * N * (T - 1) + 8 * N * K * T + 3 * K * T
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from effective_model_learning_b200 import _native, engine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC, 'warp_mma': _native.KERNEL_WARP_MMA}[args.kernel]
+
+    layout, _ = make_layout(args)
+    ts = np.linspace(*T_SPAN, N_TIMES)
+    ctx = layout.context(ts, OBS3, device=local, kernel=kernel)
+    # targets: ground-truth model evaluated by the kernels themselves (parity with the oracle is what the
+    # tests establish) + N(0, 0.01^2), execute_learning_full.py:114
+    truth = layout.random_params(np.random.default_rng(20260000 + 10 * args.qubits + args.defects))
+    ex, _ = ctx.evaluate(truth[None], want_expect=True)
+    noise = np.random.default_rng(4242)
+    targets = ex[0].real + noise.normal(0, 0.01, (3, N_TIMES))
+    ctx.set_targets(targets)
+    plan = ctx.plan
+
+    B = args.chains
+    params_host = layout.batch_params(1000 + rank * B + np.arange(B))         # this rank's chains
+    params = torch.from_numpy(params_host).to(dev)
+    loss = torch.zeros(B, dtype=torch.float64, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        flush.zero_()                               # L2 flush between iterations (inputs are far smaller than L2)
+        plan.eval_device(B, params.data_ptr(), 0, 0, loss.data_ptr(), status.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    st = status.cpu().numpy()
+    if (st < 0).any():
+        raise RuntimeError('a model hit the Taylor cap during warm-up')
+    applications = float(st.sum())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.25)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _native.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        flush.zero_()
+        k_ev[i][0].record()
+        plan.eval_device(B, params.data_ptr(), 0, 0, loss.data_ptr(), status.data_ptr(), stream)
+        k_ev[i][1].record()
+    if world > 1:
+        # the path's only collective: per-chain statistics gathered at a checkpoint (once per timed region)
+        gathered = [torch.empty_like(loss) for _ in range(world)]
+        dist.all_gather(gathered, loss)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+    value = B * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end through the public host API: host params in, host loss out, every step
+    for _ in range(2):
+        ctx.evaluate(params_host, want_expect=False, want_loss=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, loss_host = ctx.evaluate(params_host, want_expect=False, want_loss=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = B * world * args.steps / e2e_s
+    if not np.allclose(loss_host, loss.cpu().numpy(), rtol=0, atol=0):
+        raise RuntimeError('host-API and device-API losses differ')
+
+    # ---- roofline of the (single) kernel: FP64 FLOPs it executes / CUDA-event time, vs measured FP64 peak
+    fp64_fma = _native.measure_fp64_peak(local, False, 0.3)
+    fp64_mma = _native.measure_fp64_peak(local, True, 0.3)
+    peak = max(fp64_fma, fp64_mma)
+    flops_per_app = engine.flops_per_application(plan.kernel_name, layout.n_tls)
+    flops_launch = flops_per_app * applications
+    achieved = flops_launch / (kernel_ms * 1e-3)
+    canon = canonical_dense_flops(layout.n_tls, N_TIMES, 3)
+    roofline = {
+        'bound': 'tensor', 'pipe': 'fp64 (DFMA/DMMA)', 'kernel': plan.kernel_name,
+        'achieved': achieved / 1e12, 'peak': peak / 1e12, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+        'peak_source': 'measured in this run: eml_measure_fp64_peak (register-resident DFMA / DMMA m8n8k4 chains); '
+                       'MEASURED_PEAKS.json has no FP64 figure',
+        'flops_per_launch': flops_launch, 'generator_applications_per_eval': applications / B,
+        'flops_per_application': flops_per_app, 'kernel_ms': kernel_ms,
+        'canonical_dense_gflop_per_eval': canon / 1e9,
+        'canonical_dense_equivalent_tflops': canon * B / (kernel_ms * 1e-3) / 1e12,
+        'algorithmic_hbm_bytes_per_eval': 8 * layout.n_params + 8 + 4,
+    }
+
+    line = {
+        'metric': 'model evaluations/sec (4-TLS, d=16)' if (args.qubits, args.defects) == (1, 3) else 'model evaluations/sec',
+        'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 (complex128)', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'kernel': plan.kernel_name,
+                   'algorithm': 'Taylor action on the d x d density matrix with dense output (DESIGN.md section 4)',
+                   'l2': 'flushed between iterations (256 MB memset); inputs are 1.1 MB per step',
+                   'partitioning': f'chains sharded contiguously over {world} GPU(s), no data-path collective; '
+                                   'one all_gather of per-chain loss per timed region when n_gpus > 1'},
+        'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(B * layout.n_params * 8),
+                'd2h_bytes_per_step': int(B * 8 + B * 4)},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'clocks': clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pool = CpuPool()
+        n = args.cpu_sample or 8 * pool.cores
+        n = min(n, B)
+        rows = params_host[:n]
+        tg = [targets[m] for m in range(3)]
+        pool.evaluate(args.qubits, args.defects, rows[:pool.cores], tg)      # warm the workers (imports)
+        dt, cpu_loss = pool.evaluate(args.qubits, args.defects, rows, tg)
+        pool.close()
+        line['cpu_baseline'] = {'value': n / dt, 'unit': 'evals/s', 'cores': pool.cores, 'kind': 'port',
+                                'sample': f'first {n} models of the batch, emulated qutip 4.7.5 mesolve '
+                                          '(ZVODE adams/12, atol 1e-8, rtol 1e-6), one process per core',
+                                'max_abs_loss_diff_vs_gpu': float(np.abs(np.array(cpu_loss) - loss_host[:n]).max())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

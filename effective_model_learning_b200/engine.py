@@ -213,3 +213,20 @@ def evaluate_models(models, evaluation_times, obs_names, targets=None, want_expe
     elif ctx.targets is not None:
         ctx.set_targets(None)
     return ctx.evaluate(params, want_expect=want_expect, want_loss=targets is not None)
+
+
+def flops_per_application(kernel_name: str, n_tls: int) -> float:
+    """
+    FP64 floating-point operations one application of the Lindblad generator to the d x d density
+    matrix costs in each kernel (used for the roofline in bench.py).
+      generic : per element 2 complex dot products of length d (G rho and rho Gt, 8 flops per complex
+                multiply-add), n 4-term site stencils, scale and accumulate.
+      warp_mma: one complex d^3 product on the DMMA pipe (rho Hermitian => rho G^dag = (G rho)^dag),
+                the X + X^dag combine, n 4-term REAL-weighted site stencils, scale and accumulate.
+    """
+    d = 2 ** n_tls
+    if kernel_name == 'generic':
+        return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
+    if kernel_name == 'warp_mma':
+        return 8.0 * d ** 3 + d * d * (2.0 + 4.0 * (n_tls + 1) + 4.0)
+    raise RuntimeError('unknown kernel ' + kernel_name)

@@ -184,6 +184,20 @@ def liouvillian(H: np.ndarray, c_ops: list[np.ndarray]) -> np.ndarray:
     return L
 
 
+def liouvillian_csr(H: np.ndarray, c_ops: list[np.ndarray]):
+    """Same superoperator assembled sparse (CSR), the way qutip's `liouvillian` does it."""
+    sp = scipy.sparse
+    d = H.shape[0]
+    I = sp.identity(d, dtype=complex, format='csr')
+    Hs = sp.csr_matrix(H)
+    L = -1j * (sp.kron(I, Hs, format='csr') - sp.kron(Hs.T, I, format='csr'))
+    for c in c_ops:
+        cs = sp.csr_matrix(c)
+        cdc = cs.conj().T @ cs
+        L = L + sp.kron(cs.conj(), cs, format='csr') - 0.5 * sp.kron(I, cdc, format='csr') - 0.5 * sp.kron(cdc.T, I, format='csr')
+    return sp.csr_matrix(L)
+
+
 def _is_herm(a: np.ndarray) -> bool:
     return bool(np.allclose(a, a.conj().T, rtol=0, atol=1e-12))
 
@@ -247,9 +261,7 @@ def expect_zvode(spec: dict, times, observable_ops=False, *, atol=1e-13, rtol=1e
     c_ops = build_c_ops(spec)
     rho0 = build_rho0(spec)
     obs = build_observables(spec, observable_ops)
-    L = liouvillian(H, c_ops)
-    if sparse:
-        L = scipy.sparse.csr_matrix(L)
+    L = liouvillian_csr(H, c_ops) if sparse else liouvillian(H, c_ops)
     W = _trace_rows(obs)
 
     def rhs(t, y):
