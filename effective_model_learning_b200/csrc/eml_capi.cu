@@ -14,7 +14,8 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
                            double* expect, double* loss, int* status, cudaStream_t stream);
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, cudaStream_t stream);
+                            double* expect, double* loss, int* status, unsigned int* counter, cudaStream_t stream);
+bool jump_op_is_diag_flip_real(const double* op);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 }  // namespace eml
@@ -48,6 +49,7 @@ struct EmlPlan {
     int *h_tset = nullptr, *h_status = nullptr;
     double* d_targets = nullptr;
     size_t targets_bytes = 0;
+    unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
 };
 
 template <typename T>
@@ -175,13 +177,24 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         for (int c = 0; c < D; ++c)
             if (std::fabs(d->rho0[2 * (r * D + c)] - d->rho0[2 * (c * D + r)]) > 1e-15 ||
                 std::fabs(d->rho0[2 * (r * D + c) + 1] + d->rho0[2 * (c * D + r) + 1]) > 1e-15) { herm = false; break; }
+    // the warp kernel additionally needs every jump operator's A (x) conj(A) to be real, diagonal + both-flipped
+    for (int t = 0; t < d->n_terms && herm; ++t)
+        if (d->terms[t].kind == EML_TERM_LINDBLAD && !eml::jump_op_is_diag_flip_real(d->op_table + d->terms[t].op_a * 8))
+            herm = false;
     plan->hermitian = herm;
+    {
+        void* c = nullptr;
+        cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int));
+        if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
+        plan->owned.push_back(c);
+        plan->d_counter = (unsigned int*)c;
+    }
 
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
     if (want == EML_KERNEL_AUTO) want = eml::warp_mma_supported(P, herm) ? EML_KERNEL_WARP_MMA : EML_KERNEL_GENERIC;
     if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(P, herm)) {
         eml_plan_destroy(plan);
-        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls == 4 (d = 16) and Hermitian H, rho0");
+        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls == 4 (d = 16), Hermitian H and rho0, diag/flip-real jump operators");
     }
     if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA) {
         eml_plan_destroy(plan);
@@ -213,7 +226,7 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
-        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
+        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);

@@ -1,8 +1,486 @@
-// placeholder until the DMMA kernel lands
+// d = 16 (n_tls = 4) evaluator: ONE WARP PER MODEL, density matrix and Taylor terms resident in
+// registers in the FP64 mma.m8n8k4 accumulator layout, generator product on the DMMA pipe.
+//
+//   L rho = X + X^dag + J(rho),  X = G rho  (rho Hermitian => rho G^dag = X^dag),  G = -iH - 1/2 sum c^dag c
+//   J(rho)[r,c] = W0[r,c] rho[r,c] + sum_sites F_s[r_s,c_s] rho[r ^ m_s, c ^ m_s]   (real weights)
+//
+// Layout ("C layout"): lane l = 4g + t (g = l/4, t = l%4) holds, for tile (I,J) and e in {0,1}, the element
+// (r, c) = (8I + g, 8J + 2t + e) -- exactly the m8n8 accumulator fragment, so X lands where rho lives.
+// Because rho is Hermitian the B operand rho[k][n] = conj(rho[n][k]) is ALSO in the lane's own registers when
+// the k index of k-step ks is permuted to pi(ks,t) = 8(ks/2) + 2t + (ks%2); G's A fragments are loaded once per
+// model with the same permutation.  X^dag needs 32 shuffles per application, the site stencils 32 per site
+// (none for the site mapped to the tile bits), the partial trace for the observables 12.
+//
+// Requirements (checked at plan creation, else the generic kernel runs): n_tls == 4, Hermitian H and rho0,
+// every jump operator A has A (x) conj(A) real with only "diagonal" and "both bits flipped" entries
+// (sigmax/y/z/p/m, exc, gnd, id2, mm all qualify).
+//
+// Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
 #include "eml_common.cuh"
+
 namespace eml {
-bool warp_mma_supported(const DevProblem& P, bool hermitian) { (void)P; (void)hermitian; return false; }
-cudaError_t launch_warp_mma(const DevProblem&, long long, const double*, const int*, double*, double*, int*, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+constexpr int WQ = 16;          // outputs per expansion (two per lane: p = lane&7 and (lane&7)+8)
+constexpr int WARPS_PER_CTA = 4;
+constexpr int MAXP = 64;        // parameter-vector cap for this kernel
+
+struct WarpScratch {
+    double G_re[16][17];
+    double G_im[16][17];
+    double par[MAXP];
+    double jw[32];      // [bitpos][type(0 diag,1 flip)][ra][ca]
+    double colsum[16];
+    double misc[4];
+};
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double neg(double v) { return -v; }
+
+// host-side structural test of the jump operators: A (x) conj(A) restricted to diag / both-flipped, real
+bool jump_op_is_diag_flip_real(const double* op) {
+    for (int ra = 0; ra < 2; ++ra)
+        for (int ca = 0; ca < 2; ++ca)
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    const double xr = op[(ra * 2 + a) * 2], xi = op[(ra * 2 + a) * 2 + 1];
+                    const double yr = op[(ca * 2 + b) * 2], yi = -op[(ca * 2 + b) * 2 + 1];
+                    const double re = xr * yr - xi * yi, im = xr * yi + xi * yr;
+                    const bool diag = (a == ra && b == ca), flip = (a != ra && b != ca);
+                    if (fabs(im) > 1e-15) return false;
+                    if (!diag && !flip && fabs(re) > 1e-15) return false;
+                }
+    return true;
 }
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
+                     const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
+                     int* __restrict__ status, unsigned int* __restrict__ counter) {
+    constexpr int N = 4, D = 16;
+    __shared__ WarpScratch scratch_all[WARPS_PER_CTA];
+    WarpScratch& S = scratch_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int T = P.n_times, K = P.n_obs;
+
+    // site -> bit position: the observable's site sits on bit 3 (tile bits I,J), the others follow in order
+    const int obs_site = P.obs_site;
+    auto pos = [&](int s) { return (s == obs_site) ? 3 : (s < obs_site ? 2 - s : 3 - s); };
+    // permuted index -> original (site 0 most significant) index, for reading rho0
+    auto orig_index = [&](int x) {
+        int o = 0;
+#pragma unroll
+        for (int s = 0; s < N; ++s) o |= ((x >> pos(s)) & 1) << (N - 1 - s);
+        return o;
+    };
+
+    // transposition sources (see header): round A serves dest e = g&1, round B dest e = 1-(g&1)
+    const int gp = g & 1;
+    const int srcA = 4 * (2 * t + gp) + (g >> 1);
+    const int srcB = 4 * (2 * t + 1 - gp) + (g >> 1);
+    const bool diag_lane = (t == (g >> 1));      // holds the partial-trace elements (rest_r == rest_c), e = g&1
+
+    for (;;) {
+        // ---- dynamic model fetch (one atomic per warp)
+        unsigned int bidx = 0;
+        if (lane == 0) bidx = atomicAdd(counter, 1u);
+        bidx = __shfl_sync(0xffffffffu, bidx, 0);
+        if ((long long)bidx >= n_models) break;
+        const long long b = bidx;
+
+        // ---- parameters, clear G
+        for (int i = lane; i < P.n_params; i += 32) S.par[i] = params[b * P.n_params + i];
+        for (int i = lane; i < 16 * 17; i += 32) { (&S.G_re[0][0])[i] = 0.0; (&S.G_im[0][0])[i] = 0.0; }
+        __syncwarp();
+
+        // ---- K1: assemble G (lane r < 16 owns row r) and the real jump weights (one entry per lane)
+        if (lane < D) {
+            const int r = lane;
+            for (int ti = 0; ti < P.n_terms; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                const int sa = pos(tm.site_a);
+                const int ra = (r >> sa) & 1;
+                if (tm.kind == EML_TERM_ENERGY) {
+                    for (int a = 0; a < 2; ++a) {
+                        const cplx A = ld_op(P.op_table, tm.op_a, ra, a);
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        S.G_re[r][c] += v * A.im;        // -i h
+                        S.G_im[r][c] -= v * A.re;
+                    }
+                } else if (tm.kind == EML_TERM_COUPLING) {
+                    const int sb = pos(tm.site_b);
+                    const int rb = (r >> sb) & 1;
+                    const double v2 = v * v;
+                    for (int a = 0; a < 2; ++a)
+                        for (int bb = 0; bb < 2; ++bb) {
+                            const cplx AB = cmul(ld_op(P.op_table, tm.op_a, ra, a), ld_op(P.op_table, tm.op_b, rb, bb));
+                            const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
+                            S.G_re[r][c] += v2 * AB.im;
+                            S.G_im[r][c] -= v2 * AB.re;
+                        }
+                } else {
+                    for (int a = 0; a < 2; ++a) {
+                        cplx M = {0.0, 0.0};
+                        for (int z = 0; z < 2; ++z) {
+                            const cplx m = cmul(cconj(ld_op(P.op_table, tm.op_a, z, ra)), ld_op(P.op_table, tm.op_a, z, a));
+                            M.re += m.re; M.im += m.im;
+                        }
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        S.G_re[r][c] -= 0.5 * v * M.re;
+                        S.G_im[r][c] -= 0.5 * v * M.im;
+                    }
+                }
+            }
+        }
+        {
+            const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
+            const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
+            double w = 0.0;
+            for (int ti = 0; ti < P.n_terms; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                const cplx x = cmul(ld_op(P.op_table, tm.op_a, ra, a), cconj(ld_op(P.op_table, tm.op_a, ca, bb)));
+                w += v * x.re;
+            }
+            S.jw[lane] = w;
+        }
+        __syncwarp();
+
+        // ---- norm bound: 2 * max column sum |G| (G^dag supplies the row-sum term) + sum_s ||S_s||_1
+        if (lane < D) {
+            double cs = 0.0;
+            for (int i = 0; i < D; ++i) cs += hypot(S.G_re[i][lane], S.G_im[i][lane]);
+            S.colsum[lane] = cs;   // vec(rho G^dag) = (conj(G) (x) I) vec(rho) has the same 1-norm: factor 2 below
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double mc = 0.0;
+            for (int i = 0; i < D; ++i) mc = fmax(mc, S.colsum[i]);
+            double nu = 2.0 * mc;
+            for (int bp = 0; bp < N; ++bp) {
+                double best = 0.0;
+                for (int a = 0; a < 2; ++a)
+                    for (int bb = 0; bb < 2; ++bb)
+                        best = fmax(best, fabs(S.jw[bp * 8 + a * 2 + bb]) + fabs(S.jw[bp * 8 + 4 + (1 - a) * 2 + (1 - bb)]));
+                nu += best;
+            }
+            S.misc[0] = nu;
+        }
+        __syncwarp();
+        const double nu = S.misc[0];
+
+        // ---- A fragments of G with the permuted k index; stencil weights in registers
+        double a_re[2][4], a_im[2][4];
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+                a_re[I][ks] = S.G_re[8 * I + g][k];
+                a_im[I][ks] = S.G_im[8 * I + g][k];
+            }
+        double W0[2][2][2];
+        double F3[2][2];
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J) {
+                F3[I][J] = S.jw[3 * 8 + 4 + I * 2 + J];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    W0[I][J][e] = S.jw[3 * 8 + I * 2 + J] + S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] +
+                                  S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] + S.jw[0 * 8 + (g & 1) * 2 + e];
+            }
+        const double f2 = S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
+        const double f1 = S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
+        const double f0[2] = {S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        bool use3 = false, use2 = false, use1 = false, use0 = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            use3 |= S.jw[3 * 8 + 4 + i] != 0.0; use2 |= S.jw[2 * 8 + 4 + i] != 0.0;
+            use1 |= S.jw[1 * 8 + 4 + i] != 0.0; use0 |= S.jw[0 * 8 + 4 + i] != 0.0;
+        }
+
+        // ---- state: acc = rho(t_k) in C layout (rho0 permuted to the kernel's bit order)
+        double acc_re[2][2][2], acc_im[2][2][2];
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = orig_index(8 * I + g), c = orig_index(8 * J + 2 * t + e);
+                    acc_re[I][J][e] = P.rho0[2 * (r * D + c)];
+                    acc_im[I][J][e] = P.rho0[2 * (r * D + c) + 1];
+                }
+
+        const int tset = (target_set != nullptr) ? target_set[b] : 0;
+        const double* tgt = (P.targets != nullptr) ? P.targets + (size_t)tset * K * T * 2 : nullptr;
+        double my_loss = 0.0;
+        int n_apply = 0;
+        bool capped = false;
+
+        // partial trace over the non-observed sites of a C-layout operand, reduce-scattered over the warp:
+        // afterwards every lane holds the total of value index vi = lane >> 3 (0: rho00.re, 1: rho11.re,
+        // 2: rho01.re, 3: rho01.im)
+        auto partial_trace = [&](const double (&xr)[2][2][2], const double (&xi)[2][2][2]) -> double {
+            double v0 = diag_lane ? (gp ? xr[0][0][1] : xr[0][0][0]) : 0.0;
+            double v1 = diag_lane ? (gp ? xr[1][1][1] : xr[1][1][0]) : 0.0;
+            double v2 = diag_lane ? (gp ? xr[0][1][1] : xr[0][1][0]) : 0.0;
+            double v3 = diag_lane ? (gp ? xi[0][1][1] : xi[0][1][0]) : 0.0;
+            const bool up16 = lane & 16;
+            // lanes with bit4 = 0 keep (v0, v1), bit4 = 1 keep (v2, v3)
+            double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;
+            s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+            double k0 = (up16 ? v2 : v0) + s0, k1 = (up16 ? v3 : v1) + s1;
+            const bool up8 = lane & 8;
+            double s = up8 ? k0 : k1;
+            s = __shfl_xor_sync(0xffffffffu, s, 8);
+            double k = (up8 ? k1 : k0) + s;
+            k += __shfl_xor_sync(0xffffffffu, k, 4);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            return k;   // value index = 2*bit4 + bit3 = lane >> 3
+        };
+
+        // emit q outputs starting at time index kbase; y0/y1 are this lane's accumulators for outputs
+        // p = lane&7 and (lane&7)+8 of value index lane>>3
+        auto emit = [&](int q, int kbase, double y0, double y1) {
+            const int p = lane;   // lane p < q finalises output p
+            const int srcl = p & 7;
+            double r[4];
+#pragma unroll
+            for (int vi = 0; vi < 4; ++vi) {
+                const double lo = shfl(y0, vi * 8 + srcl), hi = shfl(y1, vi * 8 + srcl);
+                r[vi] = (p & 8) ? hi : lo;
+            }
+            if (p < q) {
+                const int k = kbase + p;
+                for (int m = 0; m < K; ++m) {
+                    const double* O = P.obs + m * 8;
+                    // Tr(O rho_red) = O00 r00 + O11 r11 + O01 r10 + O10 r01,  r10 = conj(r01)
+                    const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
+                    const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
+                    if (expect != nullptr) {
+                        double* e = expect + (((size_t)b * K + m) * T + k) * 2;
+                        e[0] = ere; e[1] = eim;
+                    }
+                    if (tgt != nullptr) {
+                        const double dre = ere - tgt[((size_t)m * T + k) * 2], dim = eim - tgt[((size_t)m * T + k) * 2 + 1];
+                        my_loss += dre * dre + dim * dim;
+                    }
+                }
+            }
+        };
+
+        {
+            const double v = partial_trace(acc_re, acc_im);
+            emit(1, 0, v, 0.0);
+        }
+
+        const unsigned tol_hi = (unsigned)(__double2hiint(P.tol)) & 0x7fffffffu;
+        int kidx = 0;
+        while (kidx < T - 1) {
+            int q, nsub;
+            double htot;
+            {
+                // same rule as choose_step() with this kernel's output capacity
+                const double t0 = P.times[kidx];
+                q = 1;
+                while (q < WQ && kidx + q < T - 1 && nu * (P.times[kidx + q + 1] - t0) <= P.theta_target) ++q;
+                htot = P.times[kidx + q] - t0;
+                nsub = 1;
+                if (q == 1) {
+                    const double th = nu * htot;
+                    if (th > P.theta_target) nsub = (int)ceil(th / P.theta_target);
+                }
+            }
+            const double h = htot / nsub;
+            const double t0 = P.times[kidx];
+            const int p0 = lane & 7, p1 = p0 + 8;
+            const double xs0 = (p0 < q) ? ((nsub == 1) ? (P.times[kidx + 1 + p0] - t0) / htot : 1.0) : 0.0;
+            const double xs1 = (p1 < q) ? (P.times[kidx + 1 + p1] - t0) / htot : 0.0;
+            double y0 = 0.0, y1 = 0.0;
+
+            for (int sub = 0; sub < nsub; ++sub) {
+                const bool last = (sub == nsub - 1);
+                double v_re[2][2][2], v_im[2][2][2];
+#pragma unroll
+                for (int I = 0; I < 2; ++I)
+#pragma unroll
+                    for (int J = 0; J < 2; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) { v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e]; }
+                double xp0 = 1.0, xp1 = 1.0;
+                if (last) {
+                    const double v = partial_trace(v_re, v_im);
+                    y0 = v; y1 = v;
+                }
+                int small = 0;
+                int j = 0;
+                for (; j < MCAP; ++j) {
+                    // ---- X = G v on the DMMA pipe (B fragments = conj of own registers)
+                    double x_re[2][2][2], x_im[2][2][2];
+#pragma unroll
+                    for (int I = 0; I < 2; ++I)
+#pragma unroll
+                        for (int J = 0; J < 2; ++J) { x_re[I][J][0] = x_re[I][J][1] = 0.0; x_im[I][J][0] = x_im[I][J][1] = 0.0; }
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int J = 0; J < 2; ++J) {
+                            const double b_re = v_re[J][ks >> 1][ks & 1];
+                            const double b_im = v_im[J][ks >> 1][ks & 1];     // B.im = -b_im
+                            const double nb_im = neg(b_im);
+#pragma unroll
+                            for (int I = 0; I < 2; ++I) {
+                                // X.re += a.re*B.re - a.im*B.im = a.re*b_re + a.im*b_im
+                                dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
+                                dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
+                                // X.im += a.re*B.im + a.im*B.re = -a.re*b_im + a.im*b_re
+                                dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
+                                dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
+                            }
+                        }
+                    // ---- w = f (X + X^dag + J(v))
+                    const double f = h / (double)(j + 1);
+                    double w_re[2][2][2], w_im[2][2][2];
+#pragma unroll
+                    for (int I = 0; I < 2; ++I)
+#pragma unroll
+                        for (int J = 0; J < 2; ++J) {
+                            // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I)
+                            const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
+                            const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
+                            const double rAr = shfl(sAr, srcA), rBr = shfl(sBr, srcB);
+                            const double rAi = shfl(sAi, srcA), rBi = shfl(sBi, srcB);
+                            const double t_re[2] = {gp ? rBr : rAr, gp ? rAr : rBr};
+                            const double t_im[2] = {gp ? rBi : rAi, gp ? rAi : rBi};
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                double ore = x_re[I][J][e] + t_re[e];
+                                double oim = x_im[I][J][e] - t_im[e];
+                                ore = fma(W0[I][J][e], v_re[I][J][e], ore);
+                                oim = fma(W0[I][J][e], v_im[I][J][e], oim);
+                                w_re[I][J][e] = ore; w_im[I][J][e] = oim;
+                            }
+                        }
+                    if (use3) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    w_re[I][J][e] = fma(F3[I][J], v_re[I ^ 1][J ^ 1][e], w_re[I][J][e]);
+                                    w_im[I][J][e] = fma(F3[I][J], v_im[I ^ 1][J ^ 1][e], w_im[I][J][e]);
+                                }
+                    }
+                    if (use2) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    w_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), w_re[I][J][e]);
+                                    w_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), w_im[I][J][e]);
+                                }
+                    }
+                    if (use1) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    w_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), w_re[I][J][e]);
+                                    w_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), w_im[I][J][e]);
+                                }
+                    }
+                    if (use0) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    w_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), w_re[I][J][e]);
+                                    w_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), w_im[I][J][e]);
+                                }
+                    }
+                    unsigned mx = 0;
+#pragma unroll
+                    for (int I = 0; I < 2; ++I)
+#pragma unroll
+                        for (int J = 0; J < 2; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const double wr = w_re[I][J][e] * f, wi = w_im[I][J][e] * f;
+                                v_re[I][J][e] = wr; v_im[I][J][e] = wi;
+                                acc_re[I][J][e] += wr; acc_im[I][J][e] += wi;
+                                mx = max(mx, (unsigned)__double2hiint(wr) & 0x7fffffffu);
+                                mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
+                            }
+                    if (last) {
+                        const double v = partial_trace(v_re, v_im);
+                        xp0 *= xs0; xp1 *= xs1;
+                        y0 = fma(xp0, v, y0);
+                        y1 = fma(xp1, v, y1);
+                    }
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    if (mx <= tol_hi) {
+                        if (++small >= 2) break;
+                    } else {
+                        small = 0;
+                    }
+                }
+                n_apply += (j < MCAP) ? j + 1 : MCAP;
+                if (j >= MCAP) capped = true;
+            }
+            emit(q, kidx + 1, y0, y1);
+            kidx += q;
+        }
+
+        // ---- K5: loss, fixed-order warp reduction
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+        if (lane == 0) {
+            if (loss != nullptr) loss[b] = (tgt != nullptr) ? my_loss / ((double)T * (double)K) : 0.0;
+            if (status != nullptr) status[b] = capped ? -1 : n_apply;
+        }
+        __syncwarp();
+    }
+}
+
+bool warp_mma_supported(const DevProblem& P, bool hermitian) {
+    return hermitian && P.n_tls == 4 && P.n_params <= MAXP;
+}
+
+cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
+                            double* expect, double* loss, int* status, unsigned int* counter, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    long long warps_needed = n_models;
+    long long ctas = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const long long max_ctas = (long long)sms * 2;       // persistent: 2 CTAs of 4 warps per SM
+    if (ctas > max_ctas) ctas = max_ctas;
+    eval_warp_mma_kernel<<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set, expect, loss,
+                                                                            status, counter);
+    return cudaGetLastError();
+}
+
+}  // namespace eml

@@ -135,3 +135,98 @@ def test_frozen_golden_observables_d4_to_d32():
         err = np.abs(expect.real - z[f'expect_Q{Q}_D{D}']).max()
         assert err < TOL, (Q, D, err)
         assert np.abs(expect.imag).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# d = 16 specialised kernel (one warp per model, FP64 DMMA) against the oracle and the generic kernel
+@pytest.fixture
+def use_kernel():
+    from effective_model_learning_b200 import engine, _native
+    saved = engine.default_kernel
+
+    def select(name):
+        engine.default_kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC,
+                                 'warp_mma': _native.KERNEL_WARP_MMA}[name]
+        engine.clear_contexts()
+    yield select
+    engine.default_kernel = saved
+    engine.clear_contexts()
+
+
+def _d16_specs():
+    specs = [lo.random_library_spec(np.random.default_rng(1000 + b), 1, 3) for b in range(12)]
+    # qubit NOT first (observable site = 2), amplitude-damping style jumps, projector jumps, default initial states
+    specs.append({'tls': [
+        {'is_qubit': False, 'energy': 0.3, 'Ls': {'sigmam': 0.2, 'sigmax': 0.05}, 'initial_state': None, 'couplings': []},
+        {'is_qubit': False, 'energy': 0.12, 'Ls': {'exc': 0.3, 'sigmap': 0.11}, 'initial_state': lo.OPS['mm'],
+         'couplings': [(0, 1.4, [('sigmax', 'sigmax')]), (2, 0.9, [('sigmay', 'sigmay'), ('sigmaz', 'sigmaz')])]},
+        {'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmaz': 0.07, 'sigmam': 0.13, 'gnd': 0.2},
+         'initial_state': lo.OPS['2e+1g'], 'couplings': [(3, 2.2, [('sigmax', 'sigmax')])]},
+        {'is_qubit': True, 'energy': 0.8, 'Ls': {'sigmay': 0.3}, 'initial_state': None,
+         'couplings': [(0, 0.6, [('sigmaz', 'sigmax')])]},
+    ]})
+    return specs
+
+
+@pytest.mark.parametrize('kernel', ['warp_mma', 'generic'])
+def test_d16_kernels_match_oracle(use_kernel, kernel):
+    from effective_model_learning_b200 import engine
+    use_kernel(kernel)
+    ts = np.linspace(0.0, 2.5, 200)
+    worst = 0.0
+    for i, spec in enumerate(_d16_specs()):
+        m = model_from_spec(spec)
+        got = m.calculate_dynamics(ts, OBS3)
+        assert engine.context_for(m, OBS3, ts).plan.kernel_name == kernel
+        want = lo.expect_exact(spec, ts, OBS3)
+        assert_close(got, want, TOL, f'{kernel} model {i}')
+        worst = max(worst, max_err(got, want))
+    print(f'{kernel}: worst abs err {worst:.2e}')
+
+
+def test_warp_mma_nonuniform_grid_long_steps_and_complex_observables(use_kernel):
+    use_kernel('warp_mma')
+    rng = np.random.default_rng(4)
+    ts = np.sort(np.concatenate([[0.1], 0.1 + np.cumsum(rng.uniform(1e-4, 0.3, 60)), [40.0]]))
+    ts[20] = ts[19]
+    for spec in _d16_specs()[10:]:
+        m = model_from_spec(spec)
+        obs = ['sigmap', 'exc', 'sigmay']
+        assert_close(m.calculate_dynamics(ts, obs), lo.expect_exact(spec, ts, obs), TOL, 'warp_mma non-uniform')
+
+
+def test_warp_mma_loss_and_batch_equals_generic(use_kernel):
+    from effective_model_learning_b200 import engine
+    ts = np.linspace(0.0, 2.5, 200)
+    specs = [lo.random_library_spec(np.random.default_rng(2000 + b), 1, 3) for b in range(300)]
+    models = [model_from_spec(s) for s in specs]
+    targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
+    out = {}
+    for kernel in ('generic', 'warp_mma'):
+        use_kernel(kernel)
+        out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
+    assert np.abs(out['generic'][0] - out['warp_mma'][0]).max() < 1e-10
+    np.testing.assert_allclose(out['generic'][1], out['warp_mma'][1], rtol=1e-9, atol=1e-14)
+    want = np.array([lo.total_dev(lo.expect_exact(s, ts, OBS3), list(targets), len(ts)) for s in specs[:8]])
+    np.testing.assert_allclose(out['warp_mma'][1][:8], want, rtol=1e-8, atol=1e-14)
+
+
+def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use_kernel):
+    from effective_model_learning_b200 import engine
+    use_kernel('auto')
+    ts = np.linspace(0, 1, 20)
+    spec = lo.random_library_spec(np.random.default_rng(1), 1, 3)
+    m = model_from_spec(spec)
+    m.calculate_dynamics(ts, OBS3)
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'warp_mma'
+    spec['tls'][0]['couplings'].append((1, 0.7, [('sigmap', 'sigmam')]))      # non-Hermitian H
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(ts, OBS3)
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'generic'
+    assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, 'fallback')
+    spec = lo.random_library_spec(np.random.default_rng(1), 1, 3)
+    spec['tls'][1]['Ls']['plus'] = 0.2                                       # dense real jump operator
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(ts, OBS3)
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'generic'
+    assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, 'fallback 2')
