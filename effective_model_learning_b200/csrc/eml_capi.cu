@@ -14,7 +14,7 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
                            double* expect, double* loss, int* status, cudaStream_t stream);
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, unsigned int* counter, cudaStream_t stream);
+                            double* expect, double* loss, int* status, unsigned int* counter, bool real_h, cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
@@ -39,6 +39,7 @@ struct EmlPlan {
     eml::DevProblem P{};
     int kernel = EML_KERNEL_GENERIC;
     bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
+    bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs
     std::vector<void*> owned; // device allocations
     // staging for the host entry point
     cudaStream_t stream = nullptr;
@@ -182,6 +183,20 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         if (d->terms[t].kind == EML_TERM_LINDBLAD && !eml::jump_op_is_diag_flip_real(d->op_table + d->terms[t].op_a * 8))
             herm = false;
     plan->hermitian = herm;
+    // real H: every energy op and every coupling op-pair product has no imaginary entries
+    bool realh = herm;
+    for (int t = 0; t < d->n_terms && realh; ++t) {
+        const EmlTerm& tm = d->terms[t];
+        if (tm.kind == EML_TERM_LINDBLAD) continue;
+        const double* A = d->op_table + tm.op_a * 8;
+        for (int i = 0; i < 4 && realh; ++i) {
+            if (tm.kind == EML_TERM_ENERGY) { if (std::fabs(A[2 * i + 1]) > 1e-15) realh = false; continue; }
+            const double* B = d->op_table + tm.op_b * 8;
+            for (int j = 0; j < 4; ++j)
+                if (std::fabs(A[2 * i] * B[2 * j + 1] + A[2 * i + 1] * B[2 * j]) > 1e-15) realh = false;
+        }
+    }
+    plan->real_h = realh;
     {
         void* c = nullptr;
         cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int));
@@ -211,7 +226,8 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
 
 const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (!plan) return "";
-    return plan->kernel == EML_KERNEL_WARP_MMA ? "warp_mma" : "generic";
+    if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
+    return "generic";
 }
 
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
@@ -226,7 +242,7 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
-        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, (cudaStream_t)stream);
+        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->real_h, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);

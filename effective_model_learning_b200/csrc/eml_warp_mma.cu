@@ -22,6 +22,10 @@ namespace eml {
 
 constexpr int WQ = 16;          // outputs per expansion (two per lane: p = lane&7 and (lane&7)+8)
 constexpr int WARPS_PER_CTA = 4;
+#ifndef EML_CTAS_PER_SM
+#define EML_CTAS_PER_SM 2
+#endif
+constexpr int CTAS_PER_SM = EML_CTAS_PER_SM;   // 2 -> 8 warps per SM (<= 255 regs); 3 -> 12 warps (<= 168 regs)
 constexpr int MAXP = 64;        // parameter-vector cap for this kernel
 
 struct WarpScratch {
@@ -34,12 +38,15 @@ struct WarpScratch {
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+// warp-uniform predicate the compiler can SEE is uniform (vote result): keeps shuffles free of divergence guards
+#define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
+
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ double neg(double v) { return -v; }
+__device__ __forceinline__ double neg(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 
 // host-side structural test of the jump operators: A (x) conj(A) restricted to diag / both-flipped, real
 bool jump_op_is_diag_flip_real(const double* op) {
@@ -57,7 +64,8 @@ bool jump_op_is_diag_flip_real(const double* op) {
     return true;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+template <bool REAL_H>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter) {
@@ -90,7 +98,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         unsigned int bidx = 0;
         if (lane == 0) bidx = atomicAdd(counter, 1u);
         bidx = __shfl_sync(0xffffffffu, bidx, 0);
-        if ((long long)bidx >= n_models) break;
+        if (UNI((long long)bidx >= n_models)) break;
         const long long b = bidx;
 
         // ---- parameters, clear G
@@ -178,37 +186,37 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         __syncwarp();
         const double nu = S.misc[0];
 
-        // ---- A fragments of G with the permuted k index; stencil weights in registers
+        // ---- A fragments of G with the permuted k index.  REAL_H: H is real, so G.re = -K/2 is diagonal and is
+        //      folded into the diagonal stencil weight; only G.im = -H goes through the DMMA pipe.
         double a_re[2][4], a_im[2][4];
 #pragma unroll
         for (int I = 0; I < 2; ++I)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
-                a_re[I][ks] = S.G_re[8 * I + g][k];
+                a_re[I][ks] = REAL_H ? 0.0 : S.G_re[8 * I + g][k];
                 a_im[I][ks] = S.G_im[8 * I + g][k];
             }
+        // Stencil weights are stored HALVED: the DMMA accumulators start from J(v)/2, so that
+        // X' + X'^dag = G v + v G^dag + J(v)  (J(v) is Hermitian).
         double W0[2][2][2];
         double F3[2][2];
 #pragma unroll
         for (int I = 0; I < 2; ++I)
 #pragma unroll
             for (int J = 0; J < 2; ++J) {
-                F3[I][J] = S.jw[3 * 8 + 4 + I * 2 + J];
+                F3[I][J] = 0.5 * S.jw[3 * 8 + 4 + I * 2 + J];
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    W0[I][J][e] = S.jw[3 * 8 + I * 2 + J] + S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] +
-                                  S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] + S.jw[0 * 8 + (g & 1) * 2 + e];
+                for (int e = 0; e < 2; ++e) {
+                    double w = S.jw[3 * 8 + I * 2 + J] + S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] +
+                               S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] + S.jw[0 * 8 + (g & 1) * 2 + e];
+                    if (REAL_H) w += S.G_re[8 * I + g][8 * I + g] + S.G_re[8 * J + 2 * t + e][8 * J + 2 * t + e];
+                    W0[I][J][e] = 0.5 * w;
+                }
             }
-        const double f2 = S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
-        const double f1 = S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
-        const double f0[2] = {S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
-        bool use3 = false, use2 = false, use1 = false, use0 = false;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            use3 |= S.jw[3 * 8 + 4 + i] != 0.0; use2 |= S.jw[2 * 8 + 4 + i] != 0.0;
-            use1 |= S.jw[1 * 8 + 4 + i] != 0.0; use0 |= S.jw[0 * 8 + 4 + i] != 0.0;
-        }
+        const double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
+        const double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
+        const double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
 
         // ---- state: acc = rho(t_k) in C layout (rho0 permuted to the kernel's bit order)
         double acc_re[2][2][2], acc_im[2][2][2];
@@ -290,14 +298,14 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 
         const unsigned tol_hi = (unsigned)(__double2hiint(P.tol)) & 0x7fffffffu;
         int kidx = 0;
-        while (kidx < T - 1) {
+        while (UNI(kidx < T - 1)) {
             int q, nsub;
             double htot;
             {
                 // same rule as choose_step() with this kernel's output capacity
                 const double t0 = P.times[kidx];
                 q = 1;
-                while (q < WQ && kidx + q < T - 1 && nu * (P.times[kidx + q + 1] - t0) <= P.theta_target) ++q;
+                while (UNI(q < WQ && kidx + q < T - 1 && nu * (P.times[kidx + q + 1] - t0) <= P.theta_target)) ++q;
                 htot = P.times[kidx + q] - t0;
                 nsub = 1;
                 if (q == 1) {
@@ -312,7 +320,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             const double xs1 = (p1 < q) ? (P.times[kidx + 1 + p1] - t0) / htot : 0.0;
             double y0 = 0.0, y1 = 0.0;
 
-            for (int sub = 0; sub < nsub; ++sub) {
+            for (int sub = 0; UNI(sub < nsub); ++sub) {
                 const bool last = (sub == nsub - 1);
                 double v_re[2][2][2], v_im[2][2][2];
 #pragma unroll
@@ -322,38 +330,103 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll
                         for (int e = 0; e < 2; ++e) { v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e]; }
                 double xp0 = 1.0, xp1 = 1.0;
-                if (last) {
-                    const double v = partial_trace(v_re, v_im);
-                    y0 = v; y1 = v;
-                }
+                if (last) { y0 = 0.0; y1 = 0.0; }
                 int small = 0;
                 int j = 0;
-                for (; j < MCAP; ++j) {
-                    // ---- X = G v on the DMMA pipe (B fragments = conj of own registers)
+                for (; UNI(j < MCAP); ++j) {
+                    // ---- dense output: y += x^j Tr_rest(v_j) for the term that is the INPUT of this application
+                    //      (independent of the DMMAs below, so the shuffles overlap with them)
+                    {
+                        const double tr = partial_trace(v_re, v_im);
+                        y0 = fma(xp0, tr, y0);
+                        y1 = fma(xp1, tr, y1);
+                        xp0 *= xs0; xp1 *= xs1;
+                    }
+                    // ---- accumulators start from J(v)/2: real-weighted site stencils (depend only on v)
                     double x_re[2][2][2], x_im[2][2][2];
 #pragma unroll
                     for (int I = 0; I < 2; ++I)
 #pragma unroll
-                        for (int J = 0; J < 2; ++J) { x_re[I][J][0] = x_re[I][J][1] = 0.0; x_im[I][J][0] = x_im[I][J][1] = 0.0; }
+                        for (int J = 0; J < 2; ++J)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
+                            for (int e = 0; e < 2; ++e) {
+                                x_re[I][J][e] = W0[I][J][e] * v_re[I][J][e];
+                                x_im[I][J][e] = W0[I][J][e] * v_im[I][J][e];
+                            }
+                    {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    x_re[I][J][e] = fma(F3[I][J], v_re[I ^ 1][J ^ 1][e], x_re[I][J][e]);
+                                    x_im[I][J][e] = fma(F3[I][J], v_im[I ^ 1][J ^ 1][e], x_im[I][J][e]);
+                                }
+                    }
+                    {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), x_re[I][J][e]);
+                                    x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), x_im[I][J][e]);
+                                }
+                    }
+                    {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), x_re[I][J][e]);
+                                    x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), x_im[I][J][e]);
+                                }
+                    }
+                    {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I)
+#pragma unroll
+                            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), x_re[I][J][e]);
+                                    x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), x_im[I][J][e]);
+                                }
+                    }
+                    // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
+                    //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (!REAL_H) {
+#pragma unroll
+                            for (int J = 0; J < 2; ++J) {
+                                const double b_re = v_re[J][ks >> 1][ks & 1];
+                                const double nb_im = neg(v_im[J][ks >> 1][ks & 1]);
+#pragma unroll
+                                for (int I = 0; I < 2; ++I) {
+                                    dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
+                                    dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
+                                }
+                            }
+                        }
 #pragma unroll
                         for (int J = 0; J < 2; ++J) {
                             const double b_re = v_re[J][ks >> 1][ks & 1];
-                            const double b_im = v_im[J][ks >> 1][ks & 1];     // B.im = -b_im
-                            const double nb_im = neg(b_im);
+                            const double b_im = v_im[J][ks >> 1][ks & 1];
 #pragma unroll
                             for (int I = 0; I < 2; ++I) {
-                                // X.re += a.re*B.re - a.im*B.im = a.re*b_re + a.im*b_im
-                                dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
                                 dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
-                                // X.im += a.re*B.im + a.im*B.re = -a.re*b_im + a.im*b_re
-                                dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
                                 dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
                             }
                         }
-                    // ---- w = f (X + X^dag + J(v))
+                    }
+                    // ---- next term = f (X' + X'^dag)
                     const double f = h / (double)(j + 1);
+                    unsigned mx = 0;
                     double w_re[2][2][2], w_im[2][2][2];
 #pragma unroll
                     for (int I = 0; I < 2; ++I)
@@ -368,85 +441,33 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             const double t_im[2] = {gp ? rBi : rAi, gp ? rAi : rBi};
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                double ore = x_re[I][J][e] + t_re[e];
-                                double oim = x_im[I][J][e] - t_im[e];
-                                ore = fma(W0[I][J][e], v_re[I][J][e], ore);
-                                oim = fma(W0[I][J][e], v_im[I][J][e], oim);
-                                w_re[I][J][e] = ore; w_im[I][J][e] = oim;
+                                const double wr = (x_re[I][J][e] + t_re[e]) * f;
+                                const double wi = (x_im[I][J][e] - t_im[e]) * f;
+                                w_re[I][J][e] = wr; w_im[I][J][e] = wi;
+                                mx = max(mx, (unsigned)__double2hiint(wr) & 0x7fffffffu);
+                                mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
                             }
                         }
-                    if (use3) {
-#pragma unroll
-                        for (int I = 0; I < 2; ++I)
-#pragma unroll
-                            for (int J = 0; J < 2; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    w_re[I][J][e] = fma(F3[I][J], v_re[I ^ 1][J ^ 1][e], w_re[I][J][e]);
-                                    w_im[I][J][e] = fma(F3[I][J], v_im[I ^ 1][J ^ 1][e], w_im[I][J][e]);
-                                }
-                    }
-                    if (use2) {
-#pragma unroll
-                        for (int I = 0; I < 2; ++I)
-#pragma unroll
-                            for (int J = 0; J < 2; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    w_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), w_re[I][J][e]);
-                                    w_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), w_im[I][J][e]);
-                                }
-                    }
-                    if (use1) {
-#pragma unroll
-                        for (int I = 0; I < 2; ++I)
-#pragma unroll
-                            for (int J = 0; J < 2; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    w_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), w_re[I][J][e]);
-                                    w_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), w_im[I][J][e]);
-                                }
-                    }
-                    if (use0) {
-#pragma unroll
-                        for (int I = 0; I < 2; ++I)
-#pragma unroll
-                            for (int J = 0; J < 2; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    w_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), w_re[I][J][e]);
-                                    w_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), w_im[I][J][e]);
-                                }
-                    }
-                    unsigned mx = 0;
 #pragma unroll
                     for (int I = 0; I < 2; ++I)
 #pragma unroll
                         for (int J = 0; J < 2; ++J)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                const double wr = w_re[I][J][e] * f, wi = w_im[I][J][e] * f;
-                                v_re[I][J][e] = wr; v_im[I][J][e] = wi;
-                                acc_re[I][J][e] += wr; acc_im[I][J][e] += wi;
-                                mx = max(mx, (unsigned)__double2hiint(wr) & 0x7fffffffu);
-                                mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
+                                v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
+                                acc_re[I][J][e] += w_re[I][J][e]; acc_im[I][J][e] += w_im[I][J][e];
                             }
-                    if (last) {
-                        const double v = partial_trace(v_re, v_im);
-                        xp0 *= xs0; xp1 *= xs1;
-                        y0 = fma(xp0, v, y0);
-                        y1 = fma(xp1, v, y1);
-                    }
                     mx = __reduce_max_sync(0xffffffffu, mx);
-                    if (mx <= tol_hi) {
-                        if (++small >= 2) break;
-                    } else {
-                        small = 0;
-                    }
+                    small = (mx <= tol_hi) ? small + 1 : 0;      // mx is warp-uniform (REDUX result)
+                    if (UNI(small >= 2)) { ++j; break; }
                 }
-                n_apply += (j < MCAP) ? j + 1 : MCAP;
-                if (j >= MCAP) capped = true;
+                {   // the final term computed above has not been traced yet
+                    const double tr = partial_trace(v_re, v_im);
+                    y0 = fma(xp0, tr, y0);
+                    y1 = fma(xp1, tr, y1);
+                }
+                n_apply += j;
+                if (j >= MCAP && small < 2) capped = true;
             }
             emit(q, kidx + 1, y0, y1);
             kidx += q;
@@ -463,12 +484,16 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
+template __global__ void eval_warp_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*);
+template __global__ void eval_warp_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*);
+
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && P.n_tls == 4 && P.n_params <= MAXP;
 }
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, unsigned int* counter, cudaStream_t stream) {
+                            double* expect, double* loss, int* status, unsigned int* counter, bool real_h,
+                            cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -476,10 +501,14 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     long long warps_needed = n_models;
     long long ctas = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const long long max_ctas = (long long)sms * 2;       // persistent: 2 CTAs of 4 warps per SM
+    const long long max_ctas = (long long)sms * CTAS_PER_SM;   // persistent grid
     if (ctas > max_ctas) ctas = max_ctas;
-    eval_warp_mma_kernel<<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set, expect, loss,
-                                                                            status, counter);
+    if (real_h)
+        eval_warp_mma_kernel<true><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
+                                                                                      expect, loss, status, counter);
+    else
+        eval_warp_mma_kernel<false><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
+                                                                                       expect, loss, status, counter);
     return cudaGetLastError();
 }
 

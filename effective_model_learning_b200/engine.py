@@ -222,11 +222,15 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
       generic : per element 2 complex dot products of length d (G rho and rho Gt, 8 flops per complex
                 multiply-add), n 4-term site stencils, scale and accumulate.
       warp_mma: one complex d^3 product on the DMMA pipe (rho Hermitian => rho G^dag = (G rho)^dag),
-                the X + X^dag combine, n 4-term REAL-weighted site stencils, scale and accumulate.
+                the X + X^dag combine, n REAL-weighted site stencils, scale and accumulate;
+      warp_mma_realH: the same with a real Hamiltonian, where only G.im = -H needs the DMMA pipe.
     """
     d = 2 ** n_tls
     if kernel_name == 'generic':
         return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
-    if kernel_name == 'warp_mma':
-        return 8.0 * d ** 3 + d * d * (2.0 + 4.0 * (n_tls + 1) + 4.0)
+    if kernel_name in ('warp_mma', 'warp_mma_realH'):
+        # DMMA: 4 (complex H) or 2 (real H: G.re diagonal, folded into the stencil) real d^3 products;
+        # per complex element: diagonal weight 2, n site stencils 4n, X + X^dag 2, scale 2, accumulate 2
+        mma = (4.0 if kernel_name == 'warp_mma' else 2.0) * 2.0 * d ** 3
+        return mma + d * d * (2.0 + 4.0 * n_tls + 6.0)
     raise RuntimeError('unknown kernel ' + kernel_name)
