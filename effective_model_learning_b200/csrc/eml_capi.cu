@@ -14,7 +14,8 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
                            double* expect, double* loss, int* status, cudaStream_t stream);
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, unsigned int* counter, bool real_h, cudaStream_t stream);
+                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
+                            cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
@@ -51,6 +52,7 @@ struct EmlPlan {
     double* d_targets = nullptr;
     size_t targets_bytes = 0;
     unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
+    int* d_order = nullptr;             // LPT model order (capacity 2^18 models)
 };
 
 template <typename T>
@@ -151,9 +153,9 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     eml::DevProblem& P = plan->P;
     P.n_tls = d->n_tls; P.n_params = d->n_params; P.n_terms = d->n_terms; P.n_obs = d->n_obs;
     P.n_times = d->n_times; P.n_target_sets = 0; P.obs_site = d->obs_site;
-    P.theta_target = (opts && opts->theta_target > 0) ? opts->theta_target : 8.0;
-    P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-14;
-    if (P.theta_target > 8.0) P.theta_target = 8.0;  // MCAP is sized for theta <= 8
+    P.theta_target = (opts && opts->theta_target > 0) ? opts->theta_target : 12.0;
+    P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
+    if (P.theta_target > 12.0) P.theta_target = 12.0;  // MCAP = 64 terms converge to 1e-15 for theta <= 12
     const int dd = 1 << (2 * d->n_tls);
     int rc;
 #define EML_TRY(x) if ((rc = (x)) != EML_OK) { eml_plan_destroy(plan); return rc; }
@@ -203,6 +205,13 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
         plan->owned.push_back(c);
         plan->d_counter = (unsigned int*)c;
+        if (eml::warp_mma_supported(P, herm)) {
+            void* o = nullptr;
+            ce = cudaMalloc(&o, sizeof(int) * (1 << 18));
+            if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(order)"); }
+            plan->owned.push_back(o);
+            plan->d_order = (int*)o;
+        }
     }
 
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
@@ -242,10 +251,11 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
-        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->real_h, (cudaStream_t)stream);
+        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
+                                 (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)
     if (cur != plan->device && cur >= 0) cudaSetDevice(cur);
     if (e != cudaSuccess) return fail(EML_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return EML_OK;

@@ -64,11 +64,54 @@ bool jump_op_is_diag_flip_real(const double* op) {
     return true;
 }
 
+// Longest-processing-time-first ordering: the work of a model grows with the size of its generator, so the
+// persistent warps fetch models in order of decreasing  sum |energy| + sum strength^2 + sum rate  (a proxy for
+// the norm bound).  One CTA: cost, 256-bin histogram, scan, scatter.  Without it the last warps to finish
+// determine the kernel time (3.5 models per warp at 4096 chains).
+constexpr int ORDER_BINS = 256;
+constexpr int ORDER_MAX_MODELS = 1 << 18;
+
+__global__ void __launch_bounds__(1024) order_models_kernel(const DevProblem P, const int n_models,
+                                                            const double* __restrict__ params, int* __restrict__ order) {
+    __shared__ unsigned int hist[ORDER_BINS];
+    __shared__ unsigned int start[ORDER_BINS];
+    __shared__ float smax;
+    const int tid = threadIdx.x;
+    if (tid < ORDER_BINS) hist[tid] = 0;
+    if (tid == 0) smax = 0.f;
+    __syncthreads();
+    auto cost_of = [&](int b) {
+        float c = 0.f;
+        for (int ti = 0; ti < P.n_terms; ++ti) {
+            const EmlTerm tm = P.terms[ti];
+            const float v = (float)params[(size_t)b * P.n_params + tm.param];
+            c += (tm.kind == EML_TERM_COUPLING) ? v * v : fabsf(v);
+        }
+        return c;
+    };
+    float mymax = 0.f;
+    for (int b = tid; b < n_models; b += blockDim.x) mymax = fmaxf(mymax, cost_of(b));
+    atomicMax((int*)&smax, __float_as_int(mymax));      // non-negative floats order like ints
+    __syncthreads();
+    const float scale = (smax > 0.f) ? (ORDER_BINS - 1) / smax : 0.f;
+    for (int b = tid; b < n_models; b += blockDim.x) atomicAdd(&hist[ORDER_BINS - 1 - (int)(cost_of(b) * scale)], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int run = 0;
+        for (int i = 0; i < ORDER_BINS; ++i) { start[i] = run; run += hist[i]; }
+    }
+    __syncthreads();
+    for (int b = tid; b < n_models; b += blockDim.x) {
+        const unsigned int slot = atomicAdd(&start[ORDER_BINS - 1 - (int)(cost_of(b) * scale)], 1u);
+        order[slot] = b;
+    }
+}
+
 template <bool REAL_H>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
-                     int* __restrict__ status, unsigned int* __restrict__ counter) {
+                     int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
     constexpr int N = 4, D = 16;
     __shared__ WarpScratch scratch_all[WARPS_PER_CTA];
     WarpScratch& S = scratch_all[threadIdx.x >> 5];
@@ -99,7 +142,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         if (lane == 0) bidx = atomicAdd(counter, 1u);
         bidx = __shfl_sync(0xffffffffu, bidx, 0);
         if (UNI((long long)bidx >= n_models)) break;
-        const long long b = bidx;
+        const long long b = (order != nullptr) ? order[bidx] : bidx;
 
         // ---- parameters, clear G
         for (int i = lane; i < P.n_params; i += 32) S.par[i] = params[b * P.n_params + i];
@@ -484,31 +527,37 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-template __global__ void eval_warp_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*);
-template __global__ void eval_warp_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*);
+template __global__ void eval_warp_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+template __global__ void eval_warp_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
 
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && P.n_tls == 4 && P.n_params <= MAXP;
 }
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, unsigned int* counter, bool real_h,
-                            cudaStream_t stream) {
+                            double* expect, double* loss, int* status, unsigned int* counter, int* order,
+                            bool real_h, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
+    const int* use_order = nullptr;
+    if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {
+        order_models_kernel<<<1, 1024, 0, stream>>>(P, (int)n_models, params, order);
+        use_order = order;
+    }
     long long warps_needed = n_models;
     long long ctas = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * CTAS_PER_SM;   // persistent grid
     if (ctas > max_ctas) ctas = max_ctas;
     if (real_h)
         eval_warp_mma_kernel<true><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
-                                                                                      expect, loss, status, counter);
+                                                                                      expect, loss, status, counter, use_order);
     else
         eval_warp_mma_kernel<false><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
-                                                                                       expect, loss, status, counter);
+                                                                                       expect, loss, status, counter, use_order);
     return cudaGetLastError();
 }
 
