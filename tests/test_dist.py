@@ -1,0 +1,65 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: partitioning and the checkpoint all_gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from effective_model_learning_b200 import dist as edist
+
+
+def test_partition_covers_every_chain_once():
+    for n in (0, 1, 7, 8, 4096, 8191):
+        for world in (1, 2, 3, 8):
+            spans = [edist.partition(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == edist.partition_sizes(n, world)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_chains, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    r, w = edist.init('gloo')
+    assert (r, w) == (rank, world)
+    lo, hi = edist.partition(n_chains, world, rank)
+    chains = np.arange(lo, hi, dtype=np.float64)
+    local = np.stack([chains * 10 + f for f in range(len(edist.CHAIN_STATS_FIELDS))], axis=1)
+    table = edist.gather_chain_stats(local, n_chains)
+    q.put((rank, table))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_chains', [9, 16])
+def test_gather_chain_stats_two_ranks_gloo(n_chains):
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_chains, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = np.stack([np.arange(n_chains) * 10.0 + f for f in range(len(edist.CHAIN_STATS_FIELDS))], axis=1)
+    for r in range(world):
+        assert np.array_equal(got[r], want)
+
+
+def test_single_process_gather_is_identity():
+    x = np.random.default_rng(0).normal(size=(5, len(edist.CHAIN_STATS_FIELDS)))
+    assert np.array_equal(edist.gather_chain_stats(x), x)
+    with pytest.raises(RuntimeError):
+        edist.gather_chain_stats(np.zeros((3, 2)))
