@@ -23,7 +23,10 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA = 0, 1, 2
 # every symbol include/eml_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
            'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count',
-           'eml_plan_kernel_name', 'eml_measure_fp64_peak')
+           'eml_plan_kernel_name', 'eml_measure_fp64_peak', 'eml_chains_create', 'eml_chains_destroy',
+           'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device')
+CHAIN_STATS = 8
+COL_DEFECT_ENERGY, COL_Q2D_COUPLING, COL_D2D_COUPLING, COL_QUBIT_L, COL_DEFECT_L, COL_FIXED = range(6)
 
 
 class EmlTerm(C.Structure):
@@ -43,6 +46,14 @@ class EmlProblemDesc(C.Structure):
 
 class EmlOptions(C.Structure):
     _fields_ = [('theta_target', C.c_double), ('tol', C.c_double), ('kernel', C.c_int32), ('reserved', C.c_int32)]
+
+
+class EmlChainHyper(C.Structure):
+    _fields_ = [('n_params', C.c_int32), ('acceptance_window', C.c_int32), ('col_class', C.POINTER(C.c_int32)),
+                ('priority', C.c_double * 9), ('temperature', C.c_double), ('temperature_scale', C.c_double),
+                ('complexity_factor', C.c_double), ('bounds_lo', C.c_double * 3), ('bounds_hi', C.c_double * 3),
+                ('jump_initial', C.c_double * 3), ('jump_annealed', C.c_double * 3), ('jump_rescale', C.c_double),
+                ('acceptance_target', C.c_double), ('acceptance_band', C.c_double), ('shock_anneal_at', C.c_int64)]
 
 
 _lib = None
@@ -74,6 +85,12 @@ def load():
         lib.eml_plan_kernel_name.argtypes = [vp]
         lib.eml_plan_kernel_name.restype = C.c_char_p
         lib.eml_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, dp]
+        lib.eml_chains_create.argtypes = [vp, C.POINTER(EmlChainHyper), C.c_int64, dp, ip, C.c_uint64, C.POINTER(vp)]
+        lib.eml_chains_destroy.argtypes = [vp]
+        lib.eml_chains_run.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+        lib.eml_chains_read.argtypes = [vp, dp, dp, dp, dp, dp]
+        lib.eml_chains_stats_device.argtypes = [vp]
+        lib.eml_chains_stats_device.restype = vp
         _lib = lib
     return _lib
 

@@ -21,39 +21,11 @@ bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 }  // namespace eml
 
-static thread_local std::string g_last_error;
+#include "eml_plan.hpp"
+
 static std::atomic<long long> g_launches{0};
+std::string& eml_last_error_ref() { static thread_local std::string e; return e; }
 
-static int fail(int code, const std::string& msg) {
-    g_last_error = msg;
-    return code;
-}
-#define EML_CUDA(expr)                                                                                          \
-    do {                                                                                                        \
-        cudaError_t _e = (expr);                                                                                \
-        if (_e != cudaSuccess)                                                                                  \
-            return fail(EML_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
-    } while (0)
-
-struct EmlPlan {
-    int device = 0;
-    eml::DevProblem P{};
-    int kernel = EML_KERNEL_GENERIC;
-    bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
-    bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs
-    std::vector<void*> owned; // device allocations
-    // staging for the host entry point
-    cudaStream_t stream = nullptr;
-    long long cap_models = 0;
-    double *d_params = nullptr, *d_expect = nullptr, *d_loss = nullptr;
-    int *d_tset = nullptr, *d_status = nullptr;
-    double *h_params = nullptr, *h_expect = nullptr, *h_loss = nullptr;  // pinned
-    int *h_tset = nullptr, *h_status = nullptr;
-    double* d_targets = nullptr;
-    size_t targets_bytes = 0;
-    unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
-    int* d_order = nullptr;             // LPT model order (capacity 2^18 models)
-};
 
 template <typename T>
 static int upload(EmlPlan* plan, const T* host, size_t count, const T** out) {
@@ -77,7 +49,7 @@ static bool op_is_hermitian(const double* op) {
 extern "C" {
 
 int eml_version(void) { return EML_VERSION_MAJOR * 1000 + EML_VERSION_MINOR; }
-const char* eml_last_error_string(void) { return g_last_error.c_str(); }
+const char* eml_last_error_string(void) { return eml_last_error_ref().c_str(); }
 int64_t eml_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int eml_device_count(int* count) {

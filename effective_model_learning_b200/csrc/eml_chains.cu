@@ -1,0 +1,419 @@
+// Batched reversible-jump MCMC on device-resident parameter vectors (scope row N1).
+// One thread per chain for the proposal and the accept/reject kernels; the evaluation in between is the
+// ordinary eml_eval_batch on the proposal matrix.  Per-chain semantics: LearningChain.run
+// (reference learning_chain.py:346-596), LearningModel.change_params (learning_model.py:112-194),
+// ProcessHandler add/remove moves (process_handling.py:60-602).
+#include <cmath>
+#include <new>
+
+#include "eml_plan.hpp"
+
+namespace eml {
+
+constexpr int N_MOVES = 9;
+// move indices (reference order of chain_step_options)
+enum { MV_TWEAK = 0, MV_ADD_QL, MV_REM_QL, MV_ADD_DL, MV_REM_DL, MV_ADD_Q2D, MV_REM_Q2D, MV_ADD_D2D, MV_REM_D2D };
+
+struct ChainHyperDev {
+    int n_params, window;
+    const int* col_class;
+    double priority[N_MOVES];   // normalised
+    double temperature, temperature_scale, complexity_factor;
+    double lo[3], hi[3], jump_initial[3], jump_annealed[3];
+    double jump_rescale, acc_target, acc_band;
+    long long shock_anneal_at;
+};
+
+// per-chain scalar state (structure of arrays in one allocation)
+struct ChainState {
+    double* cur;        // [C][P]
+    double* prop;       // [C][P]
+    double* best;       // [C][P]
+    double* cur_loss;   // [C]
+    double* prop_loss;  // [C]
+    double* best_loss;  // [C]
+    double* jump;       // [C][3]  current jump lengths: couplings, energies, Ls
+    double* log_ratio;  // [C]  log(p_back / p_there) + log prior ratio of the pending proposal
+    double* temp;       // [C]  MH temperature of the pending proposal
+    double* stats;      // [C][8]
+    unsigned long long* rng_ctr;   // [C]
+    unsigned long long* window_bits;  // [C] last accept flags, newest in bit 0
+    long long* step;    // [C] iteration counter i of the reference loop
+    int* kwin;          // [C] counter k of the acceptance window
+    int* move;          // [C] pending move
+    int* counters;      // [C][4] tot_RJ, acc_RJ, tot_tweak, acc_tweak
+    int* annealed;      // [C]
+    double* last_ratio; // [C] last window acceptance ratio
+};
+
+// ---- counter-based RNG: splitmix64 of (key ^ counter * golden); mirrored in tests/chain_reference.py
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    unsigned long long key, ctr;
+    __device__ unsigned long long next() { return splitmix64(key ^ (ctr++ * 0x9E3779B97F4A7C15ull)); }
+    __device__ double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }   // [0,1)
+    __device__ double normal() {
+        const double u1 = 1.0 - uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+    __device__ double gamma(double shape, double scale) {   // Marsaglia-Tsang
+        double boost = 1.0;
+        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+        const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 64; ++it) {
+            const double x = normal();
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = uniform();
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v * scale;
+        }
+        return boost * d * scale;
+    }
+};
+__host__ __device__ inline unsigned long long chain_key(unsigned long long seed, long long chain) {
+    return splitmix64(seed ^ splitmix64((unsigned long long)chain));
+}
+
+__device__ inline double Phi(double y) { return 0.5 * (1.0 + erf(y * 0.70710678118654752440)); }
+__device__ inline double xi(double m, double s, double a, double b) { return Phi((b - m) / s) - Phi((a - m) / s); }
+
+// parameter class (0 couplings, 1 energies, 2 Ls) of a column class
+__device__ inline int pclass(int cc) { return (cc == EML_COL_DEFECT_ENERGY) ? 1 : (cc == EML_COL_Q2D_COUPLING || cc == EML_COL_D2D_COUPLING) ? 0 : 2; }
+__device__ inline bool tweakable(int cc, double v) { return cc == EML_COL_DEFECT_ENERGY || (cc != EML_COL_FIXED && v != 0.0); }
+
+// number of ways of each move on a parameter row, and the number of processes (model complexity)
+__device__ inline void count_ways(const ChainHyperDev& H, const double* row, double* ways, int& n_proc) {
+    int present[5] = {0, 0, 0, 0, 0}, total[5] = {0, 0, 0, 0, 0};
+    for (int p = 0; p < H.n_params; ++p) {
+        const int cc = H.col_class[p];
+        if (cc >= 5) continue;
+        total[cc]++;
+        if (row[p] != 0.0) present[cc]++;
+    }
+    ways[MV_TWEAK] = 1;
+    ways[MV_ADD_QL] = total[EML_COL_QUBIT_L] - present[EML_COL_QUBIT_L];
+    ways[MV_REM_QL] = present[EML_COL_QUBIT_L];
+    ways[MV_ADD_DL] = total[EML_COL_DEFECT_L] - present[EML_COL_DEFECT_L];
+    ways[MV_REM_DL] = present[EML_COL_DEFECT_L];
+    ways[MV_ADD_Q2D] = total[EML_COL_Q2D_COUPLING] - present[EML_COL_Q2D_COUPLING];
+    ways[MV_REM_Q2D] = present[EML_COL_Q2D_COUPLING];
+    ways[MV_ADD_D2D] = total[EML_COL_D2D_COUPLING] - present[EML_COL_D2D_COUPLING];
+    ways[MV_REM_D2D] = present[EML_COL_D2D_COUPLING];
+    n_proc = present[1] + present[2] + present[3] + present[4];
+}
+__device__ inline int move_class(int mv) {
+    return (mv == MV_ADD_QL || mv == MV_REM_QL) ? EML_COL_QUBIT_L : (mv == MV_ADD_DL || mv == MV_REM_DL) ? EML_COL_DEFECT_L
+         : (mv == MV_ADD_Q2D || mv == MV_REM_Q2D) ? EML_COL_Q2D_COUPLING : EML_COL_D2D_COUPLING;
+}
+__device__ inline bool is_add(int mv) { return mv == MV_ADD_QL || mv == MV_ADD_DL || mv == MV_ADD_Q2D || mv == MV_ADD_D2D; }
+__device__ inline int complement(int mv) { return mv == MV_TWEAK ? MV_TWEAK : (is_add(mv) ? mv + 1 : mv - 1); }
+
+__device__ inline double xi_product(const ChainHyperDev& H, const double* row, const double* jump) {
+    double out = 1.0;
+    for (int p = 0; p < H.n_params; ++p) {
+        const int cc = H.col_class[p];
+        if (!tweakable(cc, row[p])) continue;
+        const int pc = pclass(cc);
+        out *= xi(row[p], jump[pc], H.lo[pc], H.hi[pc]);
+    }
+    return out;
+}
+
+__global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
+                                      const unsigned long long seed) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const int P = H.n_params;
+    double* cur = S.cur + c * P;
+    double* prop = S.prop + c * P;
+    double* jump = S.jump + c * 3;
+    Rng rng{chain_key(seed, c), S.rng_ctr[c]};
+
+    // shock annealing: switch to the annealed jump lengths and restart from the best model (learning_chain.py:349-367)
+    if (H.shock_anneal_at > 0 && S.step[c] == H.shock_anneal_at) {
+        for (int k = 0; k < 3; ++k) jump[k] = H.jump_annealed[k];
+        S.annealed[c] = 1;
+        S.step[c] += 1;
+        for (int p = 0; p < P; ++p) cur[p] = S.best[c * P + p];
+        S.cur_loss[c] = S.best_loss[c];
+        S.window_bits[c] = (S.window_bits[c] << 1) | 1ull;
+    }
+    // MH temperature (learning_chain.py:371, 945-958)
+    const double T = (H.temperature_scale > 0.0) ? rng.gamma(H.temperature, H.temperature_scale) : H.temperature;
+    S.temp[c] = T;
+    // acceptance window -> jump length adaptation (learning_chain.py:374-388)
+    if (S.kwin[c] >= H.window) {
+        S.kwin[c] = 0;
+        const unsigned long long mask = (H.window >= 64) ? ~0ull : ((1ull << H.window) - 1ull);
+        const double ratio = (double)__popcll(S.window_bits[c] & mask) / (double)H.window;
+        S.last_ratio[c] = ratio;
+        if (ratio - H.acc_target > H.acc_band) { for (int k = 0; k < 3; ++k) jump[k] *= 1.0 / H.jump_rescale; }
+        else if (ratio - H.acc_target < -H.acc_band) { for (int k = 0; k < 3; ++k) jump[k] *= H.jump_rescale; }
+    }
+    S.kwin[c] += 1;
+
+    // move choice: probability ~ priority x number of ways (learning_chain.py:409-414)
+    double ways[N_MOVES];
+    int n_cur;
+    count_ways(H, cur, ways, n_cur);
+    double wsum = 0.0;
+    for (int m = 0; m < N_MOVES; ++m) wsum += H.priority[m] * ways[m];
+    const double u = rng.uniform();
+    int mv = N_MOVES - 1;
+    {
+        double cdf = 0.0;
+        for (int m = 0; m < N_MOVES; ++m) {
+            cdf += H.priority[m] * ways[m] / wsum;
+            if (cdf > u) { mv = m; break; }
+        }
+        while (mv > 0 && ways[mv] == 0.0) --mv;    // guard against round-off at the end of the cdf
+    }
+    for (int p = 0; p < P; ++p) prop[p] = cur[p];
+
+    double p_there, p_back;
+    if (mv == MV_TWEAK) {
+        // Gaussian jitter, up to 10 redraws into the class bounds (learning_model.py:144-191)
+        for (int p = 0; p < P; ++p) {
+            const int cc = H.col_class[p];
+            if (!tweakable(cc, cur[p])) continue;
+            const int pc = pclass(cc);
+            for (int a = 0; a < 10; ++a) {
+                const double cand = cur[p] + jump[pc] * rng.normal();
+                if (cand >= H.lo[pc] && cand <= H.hi[pc]) { prop[p] = cand; break; }
+            }
+        }
+        p_there = xi_product(H, prop, jump);    // learning_chain.py:454-487
+        p_back = xi_product(H, cur, jump);
+    } else {
+        const int cc = move_class(mv);
+        const bool add = is_add(mv);
+        const int n = (int)ways[mv];
+        int pick = (int)(rng.uniform() * n);
+        if (pick >= n) pick = n - 1;
+        for (int p = 0; p < P; ++p) {
+            if (H.col_class[p] != cc || ((cur[p] == 0.0) != add)) continue;
+            if (pick-- == 0) {
+                const int pc = pclass(cc);
+                prop[p] = add ? H.lo[pc] + (H.hi[pc] - H.lo[pc]) * rng.uniform() : 0.0;   // process_handling.py:98-103
+                break;
+            }
+        }
+        double ways_p[N_MOVES];
+        int n_dummy;
+        count_ways(H, prop, ways_p, n_dummy);
+        double wsum_p = 0.0;
+        for (int m = 0; m < N_MOVES; ++m) wsum_p += H.priority[m] * ways_p[m];
+        p_there = H.priority[mv] / wsum;                           // learning_chain.py:493-498
+        p_back = H.priority[complement(mv)] / wsum_p;
+    }
+    int n_prop;
+    {
+        double wtmp[N_MOVES];
+        count_ways(H, prop, wtmp, n_prop);
+    }
+    // prior ratio exp(-n/cf) with the reference's sub-precision guards (learning_chain.py:792-800)
+    const double PP = exp(-(double)n_prop / H.complexity_factor), PC = exp(-(double)n_cur / H.complexity_factor);
+    double prior_ratio;
+    if (fabs(PP) < 1e-40 && fabs(PC) < 1e-40) prior_ratio = 1.0;
+    else if (fabs(PC) < 1e-40) prior_ratio = INFINITY;
+    else prior_ratio = PP / PC;
+    S.log_ratio[c] = prior_ratio * p_back / p_there;     // stored as a plain ratio
+    S.move[c] = mv;
+    S.counters[c * 4 + (mv == MV_TWEAK ? 2 : 0)] += 1;
+    S.rng_ctr[c] = rng.ctr;
+}
+
+__global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
+                                     const unsigned long long seed, double* hist_loss, double* hist_aprob, int* hist_code) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const int P = H.n_params;
+    Rng rng{chain_key(seed, c), S.rng_ctr[c]};
+    const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
+    const double a = exp(-1.0 / S.temp[c] * (Lp - Lc)) * S.log_ratio[c];     // learning_chain.py:802-805
+    const bool accept = rng.uniform() < a;
+    const int mv = S.move[c];
+    if (accept) {
+        for (int p = 0; p < P; ++p) S.cur[c * P + p] = S.prop[c * P + p];
+        S.cur_loss[c] = Lp;
+        if (Lp < S.best_loss[c]) {
+            S.best_loss[c] = Lp;
+            for (int p = 0; p < P; ++p) S.best[c * P + p] = S.prop[c * P + p];
+        }
+        S.counters[c * 4 + (mv == MV_TWEAK ? 3 : 1)] += 1;
+    }
+    S.window_bits[c] = (S.window_bits[c] << 1) | (accept ? 1ull : 0ull);
+    S.step[c] += 1;
+    S.rng_ctr[c] = rng.ctr;
+    if (hist_loss) hist_loss[c] = Lp;
+    if (hist_aprob) hist_aprob[c] = a;
+    if (hist_code) hist_code[c] = (mv << 1) | (accept ? 1 : 0);
+    // statistics record for the checkpoint all_gather
+    int n_proc = 0;
+    for (int p = 0; p < P; ++p) {
+        const int cc = H.col_class[p];
+        if (cc >= 1 && cc <= 4 && S.cur[c * P + p] != 0.0) ++n_proc;
+    }
+    double* st = S.stats + c * EML_CHAIN_STATS;
+    st[0] = S.cur_loss[c]; st[1] = S.best_loss[c];
+    st[2] = S.counters[c * 4 + 3]; st[3] = S.counters[c * 4 + 2];
+    st[4] = S.counters[c * 4 + 1]; st[5] = S.counters[c * 4 + 0];
+    st[6] = S.last_ratio[c]; st[7] = n_proc;
+}
+
+__global__ void chains_init_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const int P = H.n_params;
+    for (int p = 0; p < P; ++p) { S.best[c * P + p] = S.cur[c * P + p]; S.prop[c * P + p] = S.cur[c * P + p]; }
+    S.cur_loss[c] = S.prop_loss[c];
+    S.best_loss[c] = S.prop_loss[c];
+    for (int k = 0; k < 3; ++k) S.jump[c * 3 + k] = H.jump_initial[k];
+    S.rng_ctr[c] = 0; S.window_bits[c] = 0; S.step[c] = 0; S.kwin[c] = 0; S.move[c] = 0; S.annealed[c] = 0;
+    S.last_ratio[c] = 0.0;
+    for (int k = 0; k < 4; ++k) S.counters[c * 4 + k] = 0;
+    int n_proc = 0;
+    for (int p = 0; p < P; ++p) {
+        const int cc = H.col_class[p];
+        if (cc >= 1 && cc <= 4 && S.cur[c * P + p] != 0.0) ++n_proc;
+    }
+    double* st = S.stats + c * EML_CHAIN_STATS;
+    st[0] = st[1] = S.prop_loss[c];
+    st[2] = st[3] = st[4] = st[5] = st[6] = 0.0;
+    st[7] = n_proc;
+}
+
+}  // namespace eml
+
+struct EmlChains {
+    EmlPlan* plan = nullptr;
+    long long n = 0;
+    unsigned long long seed = 0;
+    eml::ChainHyperDev H{};
+    eml::ChainState S{};
+    std::vector<void*> owned;
+    int* d_target_set = nullptr;
+    int* d_status = nullptr;
+};
+
+template <typename T>
+static int dalloc(EmlChains* ch, T** out, size_t count) {
+    void* p = nullptr;
+    EML_CUDA(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    ch->owned.push_back(p);
+    *out = (T*)p;
+    return EML_OK;
+}
+
+extern "C" {
+
+int eml_chains_destroy(EmlChains* ch) {
+    if (!ch) return EML_OK;
+    cudaSetDevice(ch->plan->device);
+    cudaDeviceSynchronize();
+    for (void* p : ch->owned) cudaFree(p);
+    delete ch;
+    return EML_OK;
+}
+
+int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, const double* initial_params,
+                      const int32_t* target_set, uint64_t seed, EmlChains** out) {
+    if (!out) return fail(EML_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!plan || !h || !initial_params) return fail(EML_ERR_INVALID_ARGUMENT, "plan/hyper/initial_params is NULL");
+    if (n_chains < 1 || n_chains > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_chains out of range");
+    if (h->n_params != plan->P.n_params) return fail(EML_ERR_INVALID_ARGUMENT, "hyper.n_params != plan n_params");
+    if (h->acceptance_window < 1 || h->acceptance_window > 64) return fail(EML_ERR_INVALID_ARGUMENT, "acceptance_window must be in 1..64");
+    if (plan->P.n_target_sets < 1) return fail(EML_ERR_INVALID_ARGUMENT, "the plan has no targets");
+    if (!(h->complexity_factor > 0) || !(h->jump_rescale > 0)) return fail(EML_ERR_INVALID_ARGUMENT, "bad hyperparameters");
+    for (int k = 0; k < 3; ++k)
+        if (!(h->bounds_hi[k] > h->bounds_lo[k]) || !(h->jump_initial[k] > 0)) return fail(EML_ERR_INVALID_ARGUMENT, "bounds/jump lengths required");
+    double psum = 0;
+    for (int m = 0; m < eml::N_MOVES; ++m) { if (h->priority[m] < 0) return fail(EML_ERR_INVALID_ARGUMENT, "negative priority"); psum += h->priority[m]; }
+    if (!(psum > 0)) return fail(EML_ERR_INVALID_ARGUMENT, "all priorities are zero");
+    EML_CUDA(cudaSetDevice(plan->device));
+    EmlChains* ch = new (std::nothrow) EmlChains();
+    if (!ch) return fail(EML_ERR_CUDA, "out of host memory");
+    ch->plan = plan; ch->n = n_chains; ch->seed = seed;
+    const int P = h->n_params;
+    eml::ChainHyperDev& H = ch->H;
+    H.n_params = P; H.window = h->acceptance_window;
+    for (int m = 0; m < eml::N_MOVES; ++m) H.priority[m] = h->priority[m] / psum;
+    H.temperature = h->temperature; H.temperature_scale = h->temperature_scale; H.complexity_factor = h->complexity_factor;
+    for (int k = 0; k < 3; ++k) { H.lo[k] = h->bounds_lo[k]; H.hi[k] = h->bounds_hi[k]; H.jump_initial[k] = h->jump_initial[k]; H.jump_annealed[k] = h->jump_annealed[k]; }
+    H.jump_rescale = h->jump_rescale; H.acc_target = h->acceptance_target; H.acc_band = h->acceptance_band;
+    H.shock_anneal_at = h->shock_anneal_at;
+    int rc;
+#define CH_TRY(x) if ((rc = (x)) != EML_OK) { eml_chains_destroy(ch); return rc; }
+    int* d_cls = nullptr;
+    CH_TRY(dalloc(ch, &d_cls, (size_t)P));
+    if (cudaMemcpy(d_cls, h->col_class, sizeof(int) * P, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy col_class"); }
+    H.col_class = d_cls;
+    eml::ChainState& S = ch->S;
+    const size_t C = (size_t)n_chains;
+    CH_TRY(dalloc(ch, &S.cur, C * P)); CH_TRY(dalloc(ch, &S.prop, C * P)); CH_TRY(dalloc(ch, &S.best, C * P));
+    CH_TRY(dalloc(ch, &S.cur_loss, C)); CH_TRY(dalloc(ch, &S.prop_loss, C)); CH_TRY(dalloc(ch, &S.best_loss, C));
+    CH_TRY(dalloc(ch, &S.jump, C * 3)); CH_TRY(dalloc(ch, &S.log_ratio, C)); CH_TRY(dalloc(ch, &S.temp, C));
+    CH_TRY(dalloc(ch, &S.stats, C * EML_CHAIN_STATS)); CH_TRY(dalloc(ch, &S.rng_ctr, C)); CH_TRY(dalloc(ch, &S.window_bits, C));
+    CH_TRY(dalloc(ch, &S.step, C)); CH_TRY(dalloc(ch, &S.kwin, C)); CH_TRY(dalloc(ch, &S.move, C));
+    CH_TRY(dalloc(ch, &S.counters, C * 4)); CH_TRY(dalloc(ch, &S.annealed, C)); CH_TRY(dalloc(ch, &S.last_ratio, C));
+    CH_TRY(dalloc(ch, &ch->d_status, C));
+    if (target_set) {
+        for (int64_t i = 0; i < n_chains; ++i)
+            if (target_set[i] < 0 || target_set[i] >= plan->P.n_target_sets) { eml_chains_destroy(ch); return fail(EML_ERR_INVALID_ARGUMENT, "target_set entry out of range"); }
+        CH_TRY(dalloc(ch, &ch->d_target_set, C));
+        if (cudaMemcpy(ch->d_target_set, target_set, sizeof(int) * C, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy target_set"); }
+    }
+    if (cudaMemcpy(S.cur, initial_params, sizeof(double) * C * P, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy initial params"); }
+    // loss of the initial models (LearningChain.__init__, learning_chain.py:298)
+    CH_TRY(eml_eval_batch(plan, n_chains, S.cur, ch->d_target_set, nullptr, S.prop_loss, ch->d_status, nullptr));
+    const unsigned blocks = (unsigned)((n_chains + 127) / 128);
+    eml::chains_init_kernel<<<blocks, 128>>>(H, S, n_chains);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, std::string("chains init: ") + cudaGetErrorString(e)); }
+    *out = ch;
+    return EML_OK;
+}
+
+int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hist_aprob, int32_t* hist_code, void* stream) {
+    if (!ch) return fail(EML_ERR_INVALID_ARGUMENT, "chains is NULL");
+    if (n_steps < 0) return fail(EML_ERR_INVALID_ARGUMENT, "n_steps < 0");
+    EML_CUDA(cudaSetDevice(ch->plan->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((ch->n + 127) / 128);
+    for (int64_t i = 0; i < n_steps; ++i) {
+        eml::chains_propose_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed);
+        int rc = eml_eval_batch(ch->plan, ch->n, ch->S.prop, ch->d_target_set, nullptr, ch->S.prop_loss, ch->d_status, s);
+        if (rc != EML_OK) return rc;
+        eml::chains_accept_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed,
+                                                        hist_loss ? hist_loss + i * ch->n : nullptr,
+                                                        hist_aprob ? hist_aprob + i * ch->n : nullptr,
+                                                        hist_code ? hist_code + i * ch->n : nullptr);
+    }
+    EML_CUDA(cudaGetLastError());
+    return EML_OK;
+}
+
+int eml_chains_read(EmlChains* ch, double* current_params, double* current_loss, double* best_params, double* best_loss, double* stats) {
+    if (!ch) return fail(EML_ERR_INVALID_ARGUMENT, "chains is NULL");
+    EML_CUDA(cudaSetDevice(ch->plan->device));
+    EML_CUDA(cudaDeviceSynchronize());
+    const size_t C = (size_t)ch->n, P = (size_t)ch->H.n_params;
+    if (current_params) EML_CUDA(cudaMemcpy(current_params, ch->S.cur, sizeof(double) * C * P, cudaMemcpyDeviceToHost));
+    if (best_params) EML_CUDA(cudaMemcpy(best_params, ch->S.best, sizeof(double) * C * P, cudaMemcpyDeviceToHost));
+    if (current_loss) EML_CUDA(cudaMemcpy(current_loss, ch->S.cur_loss, sizeof(double) * C, cudaMemcpyDeviceToHost));
+    if (best_loss) EML_CUDA(cudaMemcpy(best_loss, ch->S.best_loss, sizeof(double) * C, cudaMemcpyDeviceToHost));
+    if (stats) EML_CUDA(cudaMemcpy(stats, ch->S.stats, sizeof(double) * C * EML_CHAIN_STATS, cudaMemcpyDeviceToHost));
+    return EML_OK;
+}
+
+const double* eml_chains_stats_device(EmlChains* ch) { return ch ? ch->S.stats : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// Internal definitions shared by the translation units behind the C ABI.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "eml_common.cuh"
+
+std::string& eml_last_error_ref();
+inline int fail(int code, const std::string& msg) {
+    eml_last_error_ref() = msg;
+    return code;
+}
+#define EML_CUDA(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess)                                                                                  \
+            return fail(EML_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+    } while (0)
+
+struct EmlPlan {
+    int device = 0;
+    eml::DevProblem P{};
+    int kernel = EML_KERNEL_GENERIC;
+    bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
+    bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs
+    std::vector<void*> owned; // device allocations
+    // staging for the host entry point
+    cudaStream_t stream = nullptr;
+    long long cap_models = 0;
+    double *d_params = nullptr, *d_expect = nullptr, *d_loss = nullptr;
+    int *d_tset = nullptr, *d_status = nullptr;
+    double *h_params = nullptr, *h_expect = nullptr, *h_loss = nullptr;  // pinned
+    int *h_tset = nullptr, *h_status = nullptr;
+    double* d_targets = nullptr;
+    size_t targets_bytes = 0;
+    unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
+    int* d_order = nullptr;             // LPT model order (capacity 2^18 models)
+};

@@ -132,6 +132,65 @@ const char* eml_plan_kernel_name(const EmlPlan* plan);
 /* FP64 microbenchmarks used to establish the roofline denominator (flops per second). */
 int eml_measure_fp64_peak(int device, int use_mma, double seconds, double* flops_per_s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched reversible-jump MCMC over device-resident parameter vectors ("next" row N1 of the scope table).
+ * One chain = one row of the plan's parameter layout; a step is  propose -> eml_eval_batch -> accept/reject,
+ * entirely on the device.  Per-chain semantics follow LearningChain.run (reference learning_chain.py:346-596):
+ * move choice with probability  priority x number-of-ways, tweak = Gaussian jitter with <= 10 redraws into the
+ * class bounds (learning_model.py:112-194), additions uniform in the bounds (process_handling.py:98-103),
+ * acceptance exp(-dLoss/T) x exp(-dComplexity/complexity_factor) x p_back/p_there (learning_chain.py:792-805),
+ * acceptance-window adaptation of the jump lengths (:374-388), shock annealing (:349-367).
+ * Random numbers: counter-based splitmix64 stream per chain (reproducible; NOT numpy's legacy stream --
+ * reference-trajectory parity is the job of the single-chain LearningChain class).
+ */
+typedef enum EmlColumnClass {
+    EML_COL_DEFECT_ENERGY = 0, /* always present, tweaked with the 'energies' jump length */
+    EML_COL_Q2D_COUPLING = 1,
+    EML_COL_D2D_COUPLING = 2,
+    EML_COL_QUBIT_L = 3,
+    EML_COL_DEFECT_L = 4,
+    EML_COL_FIXED = 5          /* e.g. qubit energies: never changed */
+} EmlColumnClass;
+
+typedef struct EmlChainHyper {
+    int32_t n_params;
+    int32_t acceptance_window;  /* <= 64 */
+    const int32_t* col_class;   /* [n_params] EmlColumnClass (host pointer, copied) */
+    double priority[9];         /* tweak, add qubit L, remove qubit L, add defect L, remove defect L,
+                                   add q-d coupling, remove q-d coupling, add d-d coupling, remove d-d coupling */
+    double temperature;         /* MH temperature, or gamma shape when temperature_scale > 0 */
+    double temperature_scale;   /* 0: fixed temperature */
+    double complexity_factor;
+    double bounds_lo[3];        /* parameter classes: 0 couplings, 1 energies, 2 Ls */
+    double bounds_hi[3];
+    double jump_initial[3];
+    double jump_annealed[3];
+    double jump_rescale;        /* jump_length_rescaling_factor */
+    double acceptance_target;
+    double acceptance_band;
+    int64_t shock_anneal_at;    /* <= 0: never */
+} EmlChainHyper;
+
+#define EML_CHAIN_STATS 8 /* current_loss, best_loss, acc_tweak, tot_tweak, acc_RJ, tot_RJ, last_window_acceptance, n_processes */
+
+typedef struct EmlChains EmlChains; /* opaque */
+
+/* initial_params: HOST [n_chains][P]; target_set: HOST [n_chains] or NULL.  Evaluates the initial models. */
+int eml_chains_create(EmlPlan* plan, const EmlChainHyper* hyper, int64_t n_chains, const double* initial_params,
+                      const int32_t* target_set, uint64_t seed, EmlChains** out);
+int eml_chains_destroy(EmlChains* chains);
+/* n_steps proposals per chain, asynchronous on `stream`.  Optional DEVICE history buffers [n_steps][n_chains]:
+ * proposal loss, acceptance probability, code = move << 1 | accepted. */
+int eml_chains_run(EmlChains* chains, int64_t n_steps, double* hist_loss, double* hist_aprob, int32_t* hist_code,
+                   void* stream);
+/* Synchronises and copies the chain state to HOST arrays (any may be NULL):
+ * current/best params [n_chains][P], current/best loss [n_chains], stats [n_chains][EML_CHAIN_STATS]. */
+int eml_chains_read(EmlChains* chains, double* current_params, double* current_loss, double* best_params,
+                    double* best_loss, double* stats);
+/* Device pointer of the per-chain statistics table [n_chains][EML_CHAIN_STATS] (refreshed by every run), for
+ * the checkpoint all_gather. */
+const double* eml_chains_stats_device(EmlChains* chains);
+
 #ifdef __cplusplus
 }
 #endif

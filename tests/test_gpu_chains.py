@@ -1,0 +1,90 @@
+"""GPU tests of the batched RJMCMC engine against the per-chain Python restatement (tests/chain_reference.py)."""
+import numpy as np
+import pytest
+import torch
+
+from effective_model_learning_b200 import BatchedChains, configs, engine
+from oracle import lindblad_oracle as lo
+from tests.chain_reference import ReferenceChain, MOVES
+from tests.helpers import OBS3
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(D, n_chains, steps_cfg=None):
+    cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    cfg['shock_anneal_at'] = 40
+    cfg['jump_length_rescaling_factor'] = 1.3
+    cfg['temperature_proposal'] = 0.002
+    if steps_cfg:
+        cfg['chain_step_options'] = steps_cfg
+    ts = np.linspace(0, 2.5, 60)
+    truth = lo.random_library_spec(np.random.default_rng(20260000 + 10 + D), 1, D)
+    targets = np.array([np.asarray(e) for e in lo.expect_exact(truth, ts, OBS3)])
+    targets = targets + np.random.default_rng(5).normal(0, 0.01, targets.shape)
+    eng = BatchedChains(ts, targets, OBS3, n_chains=n_chains, n_defects=D, seed=1234, **cfg)
+    return cfg, ts, targets, eng
+
+
+@pytest.mark.parametrize('D', [2, 3])
+def test_engine_matches_python_reference_step_by_step(D):
+    n_chains, steps = 6, 90
+    cfg, ts, targets, eng = _setup(D, n_chains, {m: (6 if m == MOVES[0] else 1) for m in MOVES})
+    state = eng.read()
+    hyper = eng.hyperparameters
+    refs = [ReferenceChain(eng.layout, hyper, cfg, state['current_params'][c], state['current_loss'][c], 1234, c)
+            for c in range(n_chains)]
+    hist = {'loss': torch.zeros((1, n_chains), dtype=torch.float64, device='cuda'),
+            'aprob': torch.zeros((1, n_chains), dtype=torch.float64, device='cuda'),
+            'code': torch.zeros((1, n_chains), dtype=torch.int32, device='cuda')}
+    seen = set()
+    for s in range(steps):
+        props = np.stack([r.propose() for r in refs])
+        _, ref_loss = eng.ctx.evaluate(props, want_expect=False, want_loss=True)
+        eng.run(1, history=hist)
+        state = eng.read()
+        code = hist['code'].cpu().numpy()[0]
+        np.testing.assert_allclose(hist['loss'].cpu().numpy()[0], ref_loss, rtol=1e-9, atol=1e-14,
+                                   err_msg=f'step {s}: the engine evaluated a different proposal')
+        for c, r in enumerate(refs):
+            a, accept = r.decide(float(ref_loss[c]))
+            assert code[c] >> 1 == r.mv, (s, c)
+            assert bool(code[c] & 1) == accept, (s, c, a)
+            assert hist['aprob'].cpu().numpy()[0][c] == pytest.approx(a, rel=1e-7, abs=1e-300)
+            np.testing.assert_allclose(state['current_params'][c], r.cur, rtol=1e-12, atol=1e-15)
+            seen.add(r.mv)
+        np.testing.assert_allclose(state['best_loss'], [r.best_loss for r in refs], rtol=1e-9)
+    assert len(seen) >= 6, 'the run should exercise most move types'
+    st = state['stats']
+    for c, r in enumerate(refs):
+        assert [st[c, 5], st[c, 4], st[c, 3], st[c, 2]] == r.counters
+        assert st[c, 0] == pytest.approx(r.cur_loss, rel=1e-9) and st[c, 7] == r.ways(r.cur)[1]
+    eng.close()
+
+
+def test_many_chains_reduce_the_loss_and_stay_in_bounds():
+    cfg, ts, targets, eng = _setup(2, 512)
+    start = eng.read()['current_loss'].copy()
+    eng.run(300)
+    state = eng.read()
+    assert np.median(state['best_loss']) < 0.25 * np.median(start)
+    assert np.all(state['best_loss'] <= state['current_loss'] + 1e-15)
+    lay = eng.layout
+    b = cfg['params_bounds']
+    for c, cls in enumerate(lay.classes):
+        col = state['current_params'][:, c]
+        if cls == 'qubit_energy':
+            assert np.all(col == 1.0)
+        elif cls == 'energies':
+            assert np.all((col >= b['energies'][0]) & (col <= b['energies'][1]))
+        else:
+            nz = col[col != 0]
+            assert np.all((nz >= b[cls][0]) & (nz <= b[cls][1]))
+    # the reported losses are the losses of the reported models
+    _, check = eng.ctx.evaluate(state['best_params'], want_expect=False, want_loss=True)
+    np.testing.assert_allclose(check, state['best_loss'], rtol=1e-9, atol=1e-14)
+    m = eng.best_models([0])[0]
+    assert m.final_loss == state['best_loss'][0]
+    table = eng.checkpoint()
+    assert table.shape == (512, 8) and np.array_equal(table[:, 1], state['best_loss'])
+    eng.close()
