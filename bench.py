@@ -35,7 +35,7 @@ CONFIG_INDEX = 11          # configs.py "EVERYTHING" library
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chains', type=int, default=4096, help='chains (models per step) per GPU')
@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--qubits', type=int, default=1)
     ap.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'warp_mma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-chains', action='store_true', help='skip the RJMCMC steps/s measurement')
     ap.add_argument('--cpu-sample', type=int, default=0, help='models in the CPU-baseline sample (0 = 8 per core)')
     return ap.parse_args()
 
@@ -337,6 +338,37 @@ def run_b200(args):
         'roofline': roofline,
         'clocks': clocks,
     }
+
+    # ---- second headline metric: RJMCMC steps/s of the batched chain engine (propose -> evaluate -> accept on device)
+    if not args.no_chains:
+        from effective_model_learning_b200 import BatchedChains, configs
+        cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[CONFIG_INDEX])
+        rj = {}
+        for label, init in (('from_initial_model', None), ('from_library_models', params_host)):
+            eng = BatchedChains(ts, targets, OBS3, n_chains=B, n_defects=args.defects, n_qubits=args.qubits,
+                                seed=1000 + rank, device=local, initial_params=init, **cfg)
+            eng.run(max(2, args.warmup), stream=stream)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            eng.run(args.steps, stream=stream)
+            c1.record()
+            barrier()
+            ms = c0.elapsed_time(c1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t[0])
+            table = eng.checkpoint(B * world) if world > 1 else eng.read()['stats']
+            rj[label] = {'steps_per_s': B * world * args.steps / (ms * 1e-3), 'ms_per_step': ms / args.steps,
+                         'mean_processes_per_model': float(np.mean(table[:, 7])),
+                         'acceptance_rate': float((table[:, 2].sum() + table[:, 4].sum()) / max(1.0, table[:, 3].sum() + table[:, 5].sum()))}
+            eng.close()
+        rj['note'] = ('one step = one proposal per chain: device-side move proposal, evaluation of the proposal, MH accept/reject; '
+                      'from_initial_model starts every chain at make_initial_model(1, D) (SURVEY 8d), from_library_models at the '
+                      'random library models of the evaluation batch (same model complexity as the headline metric); '
+                      'the reference spends 3 evaluations per step (SURVEY F6)')
+        line['rjmcmc'] = rj
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool = CpuPool()
