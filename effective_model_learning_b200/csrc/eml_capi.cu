@@ -179,7 +179,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         plan->d_counter = (unsigned int*)c;
         if (eml::warp_mma_supported(P, herm)) {
             void* o = nullptr;
-            ce = cudaMalloc(&o, sizeof(int) * (1 << 18));
+            ce = cudaMalloc(&o, sizeof(int) * 2 * (1 << 18));   // order + cost scratch
             if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(order)"); }
             plan->owned.push_back(o);
             plan->d_order = (int*)o;

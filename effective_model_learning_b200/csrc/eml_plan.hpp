@@ -34,5 +34,5 @@ struct EmlPlan {
     double* d_targets = nullptr;
     size_t targets_bytes = 0;
     unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
-    int* d_order = nullptr;             // LPT model order (capacity 2^18 models)
+    int* d_order = nullptr;             // LPT model order (capacity 2^18 models) followed by the float cost scratch
 };

@@ -66,13 +66,28 @@ bool jump_op_is_diag_flip_real(const double* op) {
 
 // Longest-processing-time-first ordering: the work of a model grows with the size of its generator, so the
 // persistent warps fetch models in order of decreasing  sum |energy| + sum strength^2 + sum rate  (a proxy for
-// the norm bound).  One CTA: cost, 256-bin histogram, scan, scatter.  Without it the last warps to finish
+// the norm bound): a cost kernel (one thread per model) and a one-CTA counting sort.  Without it the last warps to finish
 // determine the kernel time (3.5 models per warp at 4096 chains).
 constexpr int ORDER_BINS = 256;
 constexpr int ORDER_MAX_MODELS = 1 << 18;
 
-__global__ void __launch_bounds__(1024) order_models_kernel(const DevProblem P, const int n_models,
-                                                            const double* __restrict__ params, int* __restrict__ order) {
+// pass 1: one thread per model, cost proxy into scratch
+__global__ void __launch_bounds__(256) model_cost_kernel(const DevProblem P, const int n_models,
+                                                         const double* __restrict__ params, float* __restrict__ cost) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_models) return;
+    float c = 0.f;
+    for (int ti = 0; ti < P.n_terms; ++ti) {
+        const EmlTerm tm = P.terms[ti];
+        const float v = (float)params[(size_t)b * P.n_params + tm.param];
+        c += (tm.kind == EML_TERM_COUPLING) ? v * v : fabsf(v);
+    }
+    cost[b] = c;
+}
+
+// pass 2: one CTA, 256-bin counting sort of the costs, largest first
+__global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, const float* __restrict__ cost,
+                                                            int* __restrict__ order) {
     __shared__ unsigned int hist[ORDER_BINS];
     __shared__ unsigned int start[ORDER_BINS];
     __shared__ float smax;
@@ -80,21 +95,12 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const DevProblem P, 
     if (tid < ORDER_BINS) hist[tid] = 0;
     if (tid == 0) smax = 0.f;
     __syncthreads();
-    auto cost_of = [&](int b) {
-        float c = 0.f;
-        for (int ti = 0; ti < P.n_terms; ++ti) {
-            const EmlTerm tm = P.terms[ti];
-            const float v = (float)params[(size_t)b * P.n_params + tm.param];
-            c += (tm.kind == EML_TERM_COUPLING) ? v * v : fabsf(v);
-        }
-        return c;
-    };
     float mymax = 0.f;
-    for (int b = tid; b < n_models; b += blockDim.x) mymax = fmaxf(mymax, cost_of(b));
+    for (int b = tid; b < n_models; b += blockDim.x) mymax = fmaxf(mymax, cost[b]);
     atomicMax((int*)&smax, __float_as_int(mymax));      // non-negative floats order like ints
     __syncthreads();
     const float scale = (smax > 0.f) ? (ORDER_BINS - 1) / smax : 0.f;
-    for (int b = tid; b < n_models; b += blockDim.x) atomicAdd(&hist[ORDER_BINS - 1 - (int)(cost_of(b) * scale)], 1u);
+    for (int b = tid; b < n_models; b += blockDim.x) atomicAdd(&hist[ORDER_BINS - 1 - (int)(cost[b] * scale)], 1u);
     __syncthreads();
     if (tid == 0) {
         unsigned int run = 0;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const DevProblem P, 
     }
     __syncthreads();
     for (int b = tid; b < n_models; b += blockDim.x) {
-        const unsigned int slot = atomicAdd(&start[ORDER_BINS - 1 - (int)(cost_of(b) * scale)], 1u);
+        const unsigned int slot = atomicAdd(&start[ORDER_BINS - 1 - (int)(cost[b] * scale)], 1u);
         order[slot] = b;
     }
 }
@@ -545,7 +551,9 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {
-        order_models_kernel<<<1, 1024, 0, stream>>>(P, (int)n_models, params, order);
+        float* cost = reinterpret_cast<float*>(order + ORDER_MAX_MODELS);      // second half of the buffer
+        model_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>(P, (int)n_models, params, cost);
+        order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
         use_order = order;
     }
     long long warps_needed = n_models;
