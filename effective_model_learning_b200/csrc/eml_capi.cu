@@ -88,8 +88,8 @@ int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* tar
         plan->targets_bytes = bytes;
     }
     if (bytes) EML_CUDA(cudaMemcpy(plan->d_targets, targets, bytes, cudaMemcpyHostToDevice));
-    plan->P.targets = n_target_sets > 0 ? plan->d_targets : nullptr;
-    plan->P.n_target_sets = n_target_sets;
+    plan->P.targets = plan->Pw.targets = n_target_sets > 0 ? plan->d_targets : nullptr;
+    plan->P.n_target_sets = plan->Pw.n_target_sets = n_target_sets;
     return EML_OK;
 }
 
@@ -171,13 +171,28 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         }
     }
     plan->real_h = realh;
+    // Models with fewer than 3 sites are embedded for the warp kernel: spectator sites (identity dynamics,
+    // state |0><0|) are appended as the least significant factors, which changes neither the reduced dynamics of
+    // the real sites nor the observables.
+    plan->Pw = P;
+    if (d->n_tls < 3) {
+        const int pad = 3 - d->n_tls, D0 = 1 << d->n_tls, D1 = 8;
+        std::vector<double> big((size_t)D1 * D1 * 2, 0.0);
+        for (int r = 0; r < D0; ++r)
+            for (int c = 0; c < D0; ++c) {
+                big[2 * ((size_t)(r << pad) * D1 + (c << pad))] = d->rho0[2 * (r * D0 + c)];
+                big[2 * ((size_t)(r << pad) * D1 + (c << pad)) + 1] = d->rho0[2 * (r * D0 + c) + 1];
+            }
+        plan->Pw.n_tls = 3;
+        EML_TRY(upload(plan, big.data(), big.size(), &plan->Pw.rho0));
+    }
     {
         void* c = nullptr;
         cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int));
         if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
         plan->owned.push_back(c);
         plan->d_counter = (unsigned int*)c;
-        if (eml::warp_mma_supported(P, herm)) {
+        if (eml::warp_mma_supported(plan->Pw, herm)) {
             void* o = nullptr;
             ce = cudaMalloc(&o, sizeof(int) * 2 * (1 << 18));   // order + cost scratch
             if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(order)"); }
@@ -187,10 +202,10 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     }
 
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
-    if (want == EML_KERNEL_AUTO) want = eml::warp_mma_supported(P, herm) ? EML_KERNEL_WARP_MMA : EML_KERNEL_GENERIC;
-    if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(P, herm)) {
+    if (want == EML_KERNEL_AUTO) want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_MMA : EML_KERNEL_GENERIC;
+    if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(plan->Pw, herm)) {
         eml_plan_destroy(plan);
-        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls == 4 (d = 16), Hermitian H and rho0, diag/flip-real jump operators");
+        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls <= 4, Hermitian H and rho0, generalized-permutation jump operators");
     }
     if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA) {
         eml_plan_destroy(plan);
@@ -223,7 +238,7 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
-        e = eml::launch_warp_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
+        e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
                                  (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);

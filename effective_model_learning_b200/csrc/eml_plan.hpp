@@ -20,6 +20,7 @@ inline int fail(int code, const std::string& msg) {
 struct EmlPlan {
     int device = 0;
     eml::DevProblem P{};
+    eml::DevProblem Pw{};     // the same problem as the warp kernel sees it (n_tls < 3 embedded into 3 sites)
     int kernel = EML_KERNEL_GENERIC;
     bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
     bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs

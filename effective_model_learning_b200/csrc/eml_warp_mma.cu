@@ -1,4 +1,4 @@
-// d = 16 (n_tls = 4) evaluator: ONE WARP PER MODEL, density matrix and Taylor terms resident in
+// d = 8 and d = 16 (n_tls = 3, 4; smaller models are embedded) evaluator: ONE WARP PER MODEL, density matrix and Taylor terms resident in
 // registers in the FP64 mma.m8n8k4 accumulator layout, generator product on the DMMA pipe.
 //
 //   L rho = X + X^dag + J(rho),  X = G rho  (rho Hermitian => rho G^dag = X^dag),  G = -iH - 1/2 sum c^dag c
@@ -11,7 +11,10 @@
 // model with the same permutation.  X^dag needs 32 shuffles per application, the site stencils 32 per site
 // (none for the site mapped to the tile bits), the partial trace for the observables 12.
 //
-// Requirements (checked at plan creation, else the generic kernel runs): n_tls == 4, Hermitian H and rho0,
+// TL = d/8 tiles per side: d = 16 has 2x2 tiles per lane (the observed site on the tile bits), d = 8 a single
+// tile (all three site stencils go through shuffles).
+//
+// Requirements (checked at plan creation, else the generic kernel runs): n_tls == 3 or 4, Hermitian H and rho0,
 // every jump operator A has A (x) conj(A) real with only "diagonal" and "both bits flipped" entries
 // (sigmax/y/z/p/m, exc, gnd, id2, mm all qualify).
 //
@@ -113,21 +116,22 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     }
 }
 
-template <bool REAL_H>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+template <int TL, bool REAL_H>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 5 : CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
-    constexpr int N = 4, D = 16;
+    constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     __shared__ WarpScratch scratch_all[WARPS_PER_CTA];
     WarpScratch& S = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int T = P.n_times, K = P.n_obs;
 
-    // site -> bit position: the observable's site sits on bit 3 (tile bits I,J), the others follow in order
+    // site -> bit position: the observable's site sits on the top bit (for d = 16 the tile bits I,J), the
+    // others follow in order
     const int obs_site = P.obs_site;
-    auto pos = [&](int s) { return (s == obs_site) ? 3 : (s < obs_site ? 2 - s : 3 - s); };
+    auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
     // permuted index -> original (site 0 most significant) index, for reading rho0
     auto orig_index = [&](int x) {
         int o = 0;
@@ -140,7 +144,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     const int gp = g & 1;
     const int srcA = 4 * (2 * t + gp) + (g >> 1);
     const int srcB = 4 * (2 * t + 1 - gp) + (g >> 1);
-    const bool diag_lane = (t == (g >> 1));      // holds the partial-trace elements (rest_r == rest_c), e = g&1
+    // lanes holding partial-trace elements (row and column agree on every bit except the observed one), at e = g&1:
+    // d = 16: (g2,g1,g0) == (t1,t0,e); d = 8: (g1,g0) == (t0,e) and the observed bit is (g2 | t1)
+    const bool diag_lane = (TL == 2) ? (t == (g >> 1)) : (((g >> 1) & 1) == (t & 1));
 
     for (;;) {
         // ---- dynamic model fetch (one atomic per warp)
@@ -200,7 +206,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
             const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
             double w = 0.0;
-            for (int ti = 0; ti < P.n_terms; ++ti) {
+            for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
                 const EmlTerm tm = P.terms[ti];
                 if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
                 const double v = S.par[tm.param];
@@ -237,28 +243,29 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 
         // ---- A fragments of G with the permuted k index.  REAL_H: H is real, so G.re = -K/2 is diagonal and is
         //      folded into the diagonal stencil weight; only G.im = -H goes through the DMMA pipe.
-        double a_re[2][4], a_im[2][4];
+        double a_re[TL][KS], a_im[TL][KS];
 #pragma unroll
-        for (int I = 0; I < 2; ++I)
+        for (int I = 0; I < TL; ++I)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
                 const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
                 a_re[I][ks] = REAL_H ? 0.0 : S.G_re[8 * I + g][k];
                 a_im[I][ks] = S.G_im[8 * I + g][k];
             }
         // Stencil weights are stored HALVED: the DMMA accumulators start from J(v)/2, so that
         // X' + X'^dag = G v + v G^dag + J(v)  (J(v) is Hermitian).
-        double W0[2][2][2];
-        double F3[2][2];
+        double W0[TL][TL][2];
+        double F3[TL][TL];
 #pragma unroll
-        for (int I = 0; I < 2; ++I)
+        for (int I = 0; I < TL; ++I)
 #pragma unroll
-            for (int J = 0; J < 2; ++J) {
-                F3[I][J] = 0.5 * S.jw[3 * 8 + 4 + I * 2 + J];
+            for (int J = 0; J < TL; ++J) {
+                F3[I][J] = (TL == 2) ? 0.5 * S.jw[3 * 8 + 4 + I * 2 + J] : 0.0;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    double w = S.jw[3 * 8 + I * 2 + J] + S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] +
-                               S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] + S.jw[0 * 8 + (g & 1) * 2 + e];
+                    double w = S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] + S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] +
+                               S.jw[0 * 8 + (g & 1) * 2 + e];
+                    if (TL == 2) w += S.jw[3 * 8 + I * 2 + J];
                     if (REAL_H) w += S.G_re[8 * I + g][8 * I + g] + S.G_re[8 * J + 2 * t + e][8 * J + 2 * t + e];
                     W0[I][J][e] = 0.5 * w;
                 }
@@ -268,11 +275,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         const double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
 
         // ---- state: acc = rho(t_k) in C layout (rho0 permuted to the kernel's bit order)
-        double acc_re[2][2][2], acc_im[2][2][2];
+        double acc_re[TL][TL][2], acc_im[TL][TL][2];
 #pragma unroll
-        for (int I = 0; I < 2; ++I)
+        for (int I = 0; I < TL; ++I)
 #pragma unroll
-            for (int J = 0; J < 2; ++J)
+            for (int J = 0; J < TL; ++J)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int r = orig_index(8 * I + g), c = orig_index(8 * J + 2 * t + e);
@@ -289,11 +296,21 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // partial trace over the non-observed sites of a C-layout operand, reduce-scattered over the warp:
         // afterwards every lane holds the total of value index vi = lane >> 3 (0: rho00.re, 1: rho11.re,
         // 2: rho01.re, 3: rho01.im)
-        auto partial_trace = [&](const double (&xr)[2][2][2], const double (&xi)[2][2][2]) -> double {
-            double v0 = diag_lane ? (gp ? xr[0][0][1] : xr[0][0][0]) : 0.0;
-            double v1 = diag_lane ? (gp ? xr[1][1][1] : xr[1][1][0]) : 0.0;
-            double v2 = diag_lane ? (gp ? xr[0][1][1] : xr[0][1][0]) : 0.0;
-            double v3 = diag_lane ? (gp ? xi[0][1][1] : xi[0][1][0]) : 0.0;
+        auto partial_trace = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2]) -> double {
+            double v0, v1, v2, v3;
+            if (TL == 2) {
+                v0 = diag_lane ? (gp ? xr[0][0][1] : xr[0][0][0]) : 0.0;
+                v1 = diag_lane ? (gp ? xr[TL - 1][TL - 1][1] : xr[TL - 1][TL - 1][0]) : 0.0;
+                v2 = diag_lane ? (gp ? xr[0][TL - 1][1] : xr[0][TL - 1][0]) : 0.0;
+                v3 = diag_lane ? (gp ? xi[0][TL - 1][1] : xi[0][TL - 1][0]) : 0.0;
+            } else {
+                const double er = gp ? xr[0][0][1] : xr[0][0][0], ei = gp ? xi[0][0][1] : xi[0][0][0];
+                const int a = g >> 2, bb = t >> 1;      // observed bit of the row / of the column
+                v0 = (diag_lane && a == 0 && bb == 0) ? er : 0.0;
+                v1 = (diag_lane && a == 1 && bb == 1) ? er : 0.0;
+                v2 = (diag_lane && a == 0 && bb == 1) ? er : 0.0;
+                v3 = (diag_lane && a == 0 && bb == 1) ? ei : 0.0;
+            }
             const bool up16 = lane & 16;
             // lanes with bit4 = 0 keep (v0, v1), bit4 = 1 keep (v2, v3)
             double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;
@@ -371,11 +388,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 
             for (int sub = 0; UNI(sub < nsub); ++sub) {
                 const bool last = (sub == nsub - 1);
-                double v_re[2][2][2], v_im[2][2][2];
+                double v_re[TL][TL][2], v_im[TL][TL][2];
 #pragma unroll
-                for (int I = 0; I < 2; ++I)
+                for (int I = 0; I < TL; ++I)
 #pragma unroll
-                    for (int J = 0; J < 2; ++J)
+                    for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) { v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e]; }
                 double xp0 = 1.0, xp1 = 1.0;
@@ -392,11 +409,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         xp0 *= xs0; xp1 *= xs1;
                     }
                     // ---- accumulators start from J(v)/2: real-weighted site stencils (depend only on v)
-                    double x_re[2][2][2], x_im[2][2][2];
+                    double x_re[TL][TL][2], x_im[TL][TL][2];
 #pragma unroll
-                    for (int I = 0; I < 2; ++I)
+                    for (int I = 0; I < TL; ++I)
 #pragma unroll
-                        for (int J = 0; J < 2; ++J)
+                        for (int J = 0; J < TL; ++J)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 x_re[I][J][e] = W0[I][J][e] * v_re[I][J][e];
@@ -404,20 +421,22 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             }
                     {
 #pragma unroll
-                        for (int I = 0; I < 2; ++I)
+                        for (int I = 0; I < TL; ++I)
 #pragma unroll
-                            for (int J = 0; J < 2; ++J)
+                            for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
-                                    x_re[I][J][e] = fma(F3[I][J], v_re[I ^ 1][J ^ 1][e], x_re[I][J][e]);
-                                    x_im[I][J][e] = fma(F3[I][J], v_im[I ^ 1][J ^ 1][e], x_im[I][J][e]);
+                                    if (TL == 2) {
+                                        x_re[I][J][e] = fma(F3[I][J], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
+                                        x_im[I][J][e] = fma(F3[I][J], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
+                                    }
                                 }
                     }
                     {
 #pragma unroll
-                        for (int I = 0; I < 2; ++I)
+                        for (int I = 0; I < TL; ++I)
 #pragma unroll
-                            for (int J = 0; J < 2; ++J)
+                            for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), x_re[I][J][e]);
@@ -426,9 +445,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                     {
 #pragma unroll
-                        for (int I = 0; I < 2; ++I)
+                        for (int I = 0; I < TL; ++I)
 #pragma unroll
-                            for (int J = 0; J < 2; ++J)
+                            for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), x_re[I][J][e]);
@@ -437,9 +456,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                     {
 #pragma unroll
-                        for (int I = 0; I < 2; ++I)
+                        for (int I = 0; I < TL; ++I)
 #pragma unroll
-                            for (int J = 0; J < 2; ++J)
+                            for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), x_re[I][J][e]);
@@ -449,25 +468,25 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
                     //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
+                    for (int ks = 0; ks < KS; ++ks) {
                         if (!REAL_H) {
 #pragma unroll
-                            for (int J = 0; J < 2; ++J) {
+                            for (int J = 0; J < TL; ++J) {
                                 const double b_re = v_re[J][ks >> 1][ks & 1];
                                 const double nb_im = neg(v_im[J][ks >> 1][ks & 1]);
 #pragma unroll
-                                for (int I = 0; I < 2; ++I) {
+                                for (int I = 0; I < TL; ++I) {
                                     dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
                                     dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
                                 }
                             }
                         }
 #pragma unroll
-                        for (int J = 0; J < 2; ++J) {
+                        for (int J = 0; J < TL; ++J) {
                             const double b_re = v_re[J][ks >> 1][ks & 1];
                             const double b_im = v_im[J][ks >> 1][ks & 1];
 #pragma unroll
-                            for (int I = 0; I < 2; ++I) {
+                            for (int I = 0; I < TL; ++I) {
                                 dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
                                 dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
                             }
@@ -476,11 +495,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     // ---- next term = f (X' + X'^dag)
                     const double f = h / (double)(j + 1);
                     unsigned mx = 0;
-                    double w_re[2][2][2], w_im[2][2][2];
+                    double w_re[TL][TL][2], w_im[TL][TL][2];
 #pragma unroll
-                    for (int I = 0; I < 2; ++I)
+                    for (int I = 0; I < TL; ++I)
 #pragma unroll
-                        for (int J = 0; J < 2; ++J) {
+                        for (int J = 0; J < TL; ++J) {
                             // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I)
                             const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
                             const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
@@ -498,9 +517,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             }
                         }
 #pragma unroll
-                    for (int I = 0; I < 2; ++I)
+                    for (int I = 0; I < TL; ++I)
 #pragma unroll
-                        for (int J = 0; J < 2; ++J)
+                        for (int J = 0; J < TL; ++J)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
@@ -533,11 +552,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-template __global__ void eval_warp_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
-template __global__ void eval_warp_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+#define EML_WARP_INST(TL, RH) template __global__ void eval_warp_mma_kernel<TL, RH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+EML_WARP_INST(1, true) EML_WARP_INST(1, false) EML_WARP_INST(2, true) EML_WARP_INST(2, false)
 
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
-    return hermitian && P.n_tls == 4 && P.n_params <= MAXP;
+    return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
@@ -556,16 +575,18 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
         use_order = order;
     }
-    long long warps_needed = n_models;
-    long long ctas = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const long long max_ctas = (long long)sms * CTAS_PER_SM;   // persistent grid
+    using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
+                          unsigned int*, const int*);
+    const Kern kern = (P.n_tls == 4) ? (real_h ? (Kern)eval_warp_mma_kernel<2, true> : (Kern)eval_warp_mma_kernel<2, false>)
+                                     : (real_h ? (Kern)eval_warp_mma_kernel<1, true> : (Kern)eval_warp_mma_kernel<1, false>);
+    int per_sm = 1;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, 0)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
     if (ctas > max_ctas) ctas = max_ctas;
-    if (real_h)
-        eval_warp_mma_kernel<true><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
-                                                                                      expect, loss, status, counter, use_order);
-    else
-        eval_warp_mma_kernel<false><<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set,
-                                                                                       expect, loss, status, counter, use_order);
+    kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
+                                                           use_order);
     return cudaGetLastError();
 }
 

@@ -211,6 +211,44 @@ def test_warp_mma_loss_and_batch_equals_generic(use_kernel):
     np.testing.assert_allclose(out['warp_mma'][1][:8], want, rtol=1e-8, atol=1e-14)
 
 
+@pytest.mark.parametrize('kernel', ['warp_mma', 'generic'])
+@pytest.mark.parametrize('QD', [(1, 0), (1, 1), (1, 2)])
+def test_small_models_both_kernels(use_kernel, kernel, QD):
+    """d = 2, 4 (embedded into 3 sites by the warp kernel) and d = 8, incl. qubit-not-first and sigma-/+ jumps."""
+    from effective_model_learning_b200 import engine
+    use_kernel(kernel)
+    ts = np.linspace(0.0, 2.5, 200)
+    specs = [lo.random_library_spec(np.random.default_rng(3000 + b), *QD) for b in range(6)]
+    if QD == (1, 2):
+        specs.append({'tls': [
+            {'is_qubit': False, 'energy': 0.3, 'Ls': {'sigmam': 0.2, 'sigmax': 0.05}, 'initial_state': None, 'couplings': []},
+            {'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmaz': 0.07, 'sigmap': 0.13, 'gnd': 0.2},
+             'initial_state': lo.OPS['2e+1g'], 'couplings': [(0, 1.4, [('sigmax', 'sigmax')]), (2, 2.2, [('sigmay', 'sigmay')])]},
+            {'is_qubit': False, 'energy': 0.12, 'Ls': {'exc': 0.3, 'sigmay': 0.11}, 'initial_state': lo.OPS['mm'],
+             'couplings': [(0, 0.6, [('sigmaz', 'sigmax')])]},
+        ]})
+    for i, spec in enumerate(specs):
+        m = model_from_spec(spec)
+        obs = ['sigmax', 'sigmap', 'sigmaz']
+        got = m.calculate_dynamics(ts, obs)
+        assert engine.context_for(m, obs, ts).plan.kernel_name.startswith(kernel)
+        assert_close(got, lo.expect_exact(spec, ts, obs), TOL, f'{kernel} {QD} model {i}')
+
+
+def test_d8_batch_loss_equals_generic(use_kernel):
+    from effective_model_learning_b200 import engine
+    ts = np.sort(np.random.default_rng(0).uniform(0, 3.0, 150))
+    specs = [lo.random_library_spec(np.random.default_rng(4000 + b), 1, 2) for b in range(400)]
+    models = [model_from_spec(s) for s in specs]
+    targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
+    out = {}
+    for kernel in ('generic', 'warp_mma'):
+        use_kernel(kernel)
+        out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
+    assert np.abs(out['generic'][0] - out['warp_mma'][0]).max() < 1e-10
+    np.testing.assert_allclose(out['generic'][1], out['warp_mma'][1], rtol=1e-9, atol=1e-14)
+
+
 def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use_kernel):
     from effective_model_learning_b200 import engine
     use_kernel('auto')
