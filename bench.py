@@ -310,9 +310,18 @@ def run_b200(args):
     flops_launch = flops_per_app * applications
     achieved = flops_launch / (kernel_ms * 1e-3)
     canon = canonical_dense_flops(layout.n_tls, N_TIMES, 3)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            entry = json.load(f).get(f'{plan.kernel_name}:n_tls={layout.n_tls}:chains={B}')
+        if entry:
+            traffic = entry['bytes']
+    except (OSError, ValueError):
+        pass
     roofline = {
         'bound': 'tensor', 'pipe': 'fp64 (DFMA/DMMA)', 'kernel': plan.kernel_name,
-        'achieved': achieved / 1e12, 'peak': peak / 1e12, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+        'achieved': achieved / 1e12, 'peak': peak / 1e12, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+        'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu --set full capture of the same workload)',
         'peak_source': 'measured in this run: eml_measure_fp64_peak (register-resident DFMA / DMMA m8n8k4 chains); '
                        'MEASURED_PEAKS.json has no FP64 figure',
         'flops_per_launch': flops_launch, 'generator_applications_per_eval': applications / B,

@@ -24,7 +24,10 @@
 namespace eml {
 
 constexpr int WQ = 16;          // outputs per expansion (two per lane: p = lane&7 and (lane&7)+8)
-constexpr int WARPS_PER_CTA = 4;
+#ifndef EML_WARPS_PER_CTA
+#define EML_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = EML_WARPS_PER_CTA;
 #ifndef EML_CTAS_PER_SM
 #define EML_CTAS_PER_SM 2
 #endif
