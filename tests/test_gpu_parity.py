@@ -268,3 +268,28 @@ def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use
     got = m.calculate_dynamics(ts, OBS3)
     assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'generic'
     assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, 'fallback 2')
+
+
+def test_posterior_predictive_and_dense_grid_callers():
+    """Scope row N2: batched re-evaluation of sampled parameter vectors and the dense post-run grid."""
+    from effective_model_learning_b200 import configs, predictive, LearningModel, definitions
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    D = 2
+    ts = np.linspace(0.0, 2.5, 120)
+    vectors, specs = [], []
+    for b in range(40):
+        spec = lo.random_library_spec(np.random.default_rng(6000 + b), 1, D)
+        m = model_from_spec(spec, LearningModel)
+        vectors.append(m.vectorise_under_library(hyper)[0])
+        specs.append(spec)
+    means, stds, evaluated = predictive.posterior_predictive(vectors, hyper, ts, OBS3, D=D,
+                                                             qubit_initial_state=definitions.ops['plus'],
+                                                             defect_initial_state=definitions.ops['mm'])
+    want = np.array([[np.asarray(e) for e in lo.expect_exact(s, ts, OBS3)] for s in specs])
+    for m_, name in enumerate(OBS3):
+        assert np.abs(evaluated[name] - want[:, m_]).max() < TOL
+        np.testing.assert_allclose(means[name], want[:, m_].mean(axis=0), atol=1e-9)
+        np.testing.assert_allclose(stds[name], want[:, m_].std(axis=0), atol=1e-9)
+    grid, data = predictive.dense_grid_dynamics(model_from_spec(specs[0]), ts, OBS3)
+    assert len(grid) == 1200 and grid[0] == ts[0] and grid[-1] == ts[-1]
+    assert_close(data, lo.expect_exact(specs[0], grid, OBS3), TOL, 'dense grid')
