@@ -7,7 +7,7 @@ ProcessHandler, ParamsHandler, TwoLevelSystem, definitions.ops, configs); the dy
 the loss run in hand-written sm_100a CUDA kernels behind the C ABI of include/eml_b200.h.
 """
 from . import (definitions, two_level_system, engine, basic_model, learning_model, params_handling,  # noqa: F401
-               process_handling, learning_chain, configs, synthetic, dist, chains, predictive)
+               process_handling, learning_chain, configs, synthetic, dist, chains, predictive, output)
 from .basic_model import BasicModel  # noqa: F401
 from .learning_model import LearningModel  # noqa: F401
 from .learning_chain import LearningChain  # noqa: F401

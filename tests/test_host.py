@@ -182,3 +182,53 @@ def test_chain_replays_reference_trajectory(oracle_backend, D):
     assert set(chain.all_proposals) == {'proposals', 'loss', 'acceptance', 'log_posterior', 'log_likelihood_prior',
                                         'acceptance_probability', 'annealed', 'step_types'}
     assert len(chain.explored_proposals) == 1 + sum(g['acceptance'])
+
+
+def test_output_writes_the_reference_file_set(oracle_backend, tmp_path):
+    """Scope row N3: data files of reference output.py, loadable without qutip."""
+    import pickle
+    from effective_model_learning_b200 import output
+    g = json.load(open(os.path.join(GOLD, 'reference_chain_D1.json')))
+    config = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    config['iterations_till_progress_update'] = False
+    config['shock_anneal_at'] = 15
+    np.random.seed(3)
+    chain = eml.LearningChain(target_times=np.array(g['target_times'])[:30],
+                              target_datasets=[np.array(t)[:30] for t in g['targets']], target_observables=OBS3,
+                              initial=(1, 1), qubit_initial_state=definitions.ops['plus'],
+                              defect_initial_state=definitions.ops['mm'], max_chain_steps=30,
+                              store_all_proposals=True, **config)
+    with np.errstate(over='ignore'):
+        best = chain.run()
+
+    class Toggles:
+        comparison = False
+        loss = True
+        log_posterior = True
+        acceptance_probability = True
+        acceptance = True
+        graphs = False
+        pickle = True
+        text = True
+        all_proposals = True
+        hyperparams = True
+
+    base = str(tmp_path / 'run_D1_R1')
+    out = output.Output(toggles=Toggles, filename=base, loss=chain.explored_loss, best_loss=chain.best_loss,
+                        acceptance_probability=chain.explored_acceptance_probability,
+                        overall_acceptance={'parameters tweak': chain.acc_tweak_steps / max(chain.tot_tweak_steps, 1),
+                                            'reversible jump': chain.acc_RJ_steps / max(chain.tot_RJ_steps, 1)},
+                        acceptance=chain.chain_windows_acceptance_log, models_to_save=[best], model_names=['best'],
+                        chain_hyperparams=chain.get_init_hyperparams(), all_proposals=chain.all_proposals)
+    names = {os.path.basename(p)[len('run_D1_R1'):] for p in out.written}
+    assert {'_overall_acceptance.json', '_best.pickle', '_best.txt', '_proposals.pickle', '_hyperparameters.txt',
+            '_hyperparameters.pickle', '_loss.pickle', '_accepted_loss.pickle', '_unannealed_accepted_loss.pickle',
+            '_annealed_accepted_loss.pickle', '_accepted_log_posterior.pickle', '_AP.pickle',
+            '_accepted_AP.pickle'} <= names
+    loaded = pickle.load(open(base + '_best.pickle', 'rb'))
+    assert loaded.vectorise_under_library(config)[0] == best.vectorise_under_library(config)[0]
+    assert loaded.final_loss == chain.best_loss
+    props = pickle.load(open(base + '_proposals.pickle', 'rb'))
+    assert props['step_types'] == chain.run_step_type_tracker and 'jump to best' in props['step_types']
+    assert len(pickle.load(open(base + '_accepted_loss.pickle', 'rb'))) == sum(chain.run_acceptance_tracker)
+    assert pickle.load(open(base + '_loss.pickle', 'rb')) == chain.explored_loss
