@@ -17,6 +17,10 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
                             cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
+cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
+                           double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
+                           cudaStream_t stream);
+bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 }  // namespace eml
@@ -192,7 +196,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
         plan->owned.push_back(c);
         plan->d_counter = (unsigned int*)c;
-        if (eml::warp_mma_supported(plan->Pw, herm)) {
+        if (eml::warp_mma_supported(plan->Pw, herm) || eml::cta_mma_supported(P, herm)) {
             void* o = nullptr;
             ce = cudaMalloc(&o, sizeof(int) * 2 * (1 << 18));   // order + cost scratch
             if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(order)"); }
@@ -202,12 +206,18 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     }
 
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
-    if (want == EML_KERNEL_AUTO) want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_MMA : EML_KERNEL_GENERIC;
+    if (want == EML_KERNEL_AUTO)
+        want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_MMA
+               : eml::cta_mma_supported(P, herm) ? EML_KERNEL_CTA_MMA : EML_KERNEL_GENERIC;
+    if (want == EML_KERNEL_CTA_MMA && !eml::cta_mma_supported(P, herm)) {
+        eml_plan_destroy(plan);
+        return fail(EML_ERR_UNSUPPORTED, "cta_mma kernel needs n_tls == 5, Hermitian H and rho0, generalized-permutation jump operators");
+    }
     if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(plan->Pw, herm)) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls <= 4, Hermitian H and rho0, generalized-permutation jump operators");
     }
-    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA) {
+    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA && want != EML_KERNEL_CTA_MMA) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_INVALID_ARGUMENT, "unknown kernel id");
     }
@@ -223,6 +233,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
 const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (!plan) return "";
     if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
+    if (plan->kernel == EML_KERNEL_CTA_MMA) return plan->real_h ? "cta_mma_realH" : "cta_mma";
     return "generic";
 }
 
@@ -240,6 +251,9 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (plan->kernel == EML_KERNEL_WARP_MMA)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
                                  (cudaStream_t)stream);
+    else if (plan->kernel == EML_KERNEL_CTA_MMA)
+        e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order,
+                                plan->real_h, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)

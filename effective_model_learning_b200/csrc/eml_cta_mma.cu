@@ -1,0 +1,452 @@
+// d = 32 (n_tls = 5) evaluator: ONE CTA OF FOUR WARPS PER MODEL, FP64 DMMA.
+//
+// Same algorithm and register layout as eml_warp_mma.cu (Taylor action with dense output on the d x d density
+// matrix, Hermitian B-operand trick, real-weighted site stencils, accumulators started from J(v)/2), scaled up:
+// warp w owns the tile row I = w (rows 8w .. 8w+7) of rho, of the current Taylor term v and of X = G v, each as
+// 4 column tiles x 2 elements per lane -- the same 16 complex numbers per lane as the d = 16 kernel.  What a warp
+// needs from the other rows goes through shared memory, twice per generator application:
+//   Vs  (row-major, ld 40)  the whole current term: B fragments v[k][n] = conj(v[n][k]) and all five site stencils
+//                           are read from it with conflict-free LDS.128;
+//   Xs  (column-major, ld 34)  X' = J(v)/2 + G v, so that X'^dag is read back with LDS.128.
+// Two __syncthreads per application.  REAL_H as in the warp kernel (half the DMMAs when H is a real matrix).
+//
+// Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
+#include "eml_common.cuh"
+
+namespace eml {
+
+constexpr int CQ = 16;        // outputs per expansion
+constexpr int CMAXP = 96;
+constexpr int LDV = 40;       // row stride (doubles) of Vs: conflict-free LDS.128 over (g, t)
+constexpr int LDX = 34;       // column stride of Xs: conflict-free STS.64 over (g, t)
+
+struct CtaScratch {
+    double Vs_re[32 * LDV], Vs_im[32 * LDV];     // also hosts G during assembly: G_re = Vs_re (ld 40), G_im = Vs_im
+    double Xs_re[32 * LDX], Xs_im[32 * LDX];
+    double par[CMAXP];
+    double jw[40];            // [bitpos 0..4][type (0 diag, 1 flip)][ra][ca]
+    double colsum[32];
+    double trp[4][4];         // per-warp partial traces: b0.re, b0.im, b1.re, b1.im
+    double misc[4];
+    unsigned int mxs[4];
+    unsigned int fetch;
+};
+
+#define CUNI(c) (__all_sync(0xffffffffu, (c)) != 0)
+
+__device__ __forceinline__ void dmma_c(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double neg_c(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
+
+template <bool REAL_H>
+__global__ void __launch_bounds__(128, 2)
+eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
+                    const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
+                    int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
+    constexpr int N = 5, D = 32;
+    __shared__ __align__(16) CtaScratch S;
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int T = P.n_times, K = P.n_obs;
+    const int obs_site = P.obs_site;
+    auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
+    auto orig_index = [&](int x) {
+        int o = 0;
+#pragma unroll
+        for (int s = 0; s < N; ++s) o |= ((x >> pos(s)) & 1) << (N - 1 - s);
+        return o;
+    };
+    const int gp = g & 1;
+    const bool diag_lane = (t == (g >> 1));
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) S.fetch = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int bidx = S.fetch;
+        if ((long long)bidx >= n_models) break;
+        const long long b = (order != nullptr) ? order[bidx] : bidx;
+
+        // ---- parameters, clear G (G lives in the Vs planes with ld LDV during assembly)
+        for (int i = tid; i < P.n_params; i += 128) S.par[i] = params[b * P.n_params + i];
+        for (int i = tid; i < 32 * LDV; i += 128) { S.Vs_re[i] = 0.0; S.Vs_im[i] = 0.0; }
+        __syncthreads();
+        double* G_re = S.Vs_re;
+        double* G_im = S.Vs_im;
+
+        // ---- K1: thread r < 32 owns row r of G; threads < 40 own one jump weight each
+        if (tid < D) {
+            const int r = tid;
+            for (int ti = 0; ti < P.n_terms; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                const int sa = pos(tm.site_a);
+                const int ra = (r >> sa) & 1;
+                if (tm.kind == EML_TERM_ENERGY) {
+                    for (int a = 0; a < 2; ++a) {
+                        const cplx A = ld_op(P.op_table, tm.op_a, ra, a);
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        G_re[r * LDV + c] += v * A.im;
+                        G_im[r * LDV + c] -= v * A.re;
+                    }
+                } else if (tm.kind == EML_TERM_COUPLING) {
+                    const int sb = pos(tm.site_b);
+                    const int rb = (r >> sb) & 1;
+                    const double v2 = v * v;
+                    for (int a = 0; a < 2; ++a)
+                        for (int bb = 0; bb < 2; ++bb) {
+                            const cplx AB = cmul(ld_op(P.op_table, tm.op_a, ra, a), ld_op(P.op_table, tm.op_b, rb, bb));
+                            const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
+                            G_re[r * LDV + c] += v2 * AB.im;
+                            G_im[r * LDV + c] -= v2 * AB.re;
+                        }
+                } else {
+                    for (int a = 0; a < 2; ++a) {
+                        cplx M = {0.0, 0.0};
+                        for (int z = 0; z < 2; ++z) {
+                            const cplx m = cmul(cconj(ld_op(P.op_table, tm.op_a, z, ra)), ld_op(P.op_table, tm.op_a, z, a));
+                            M.re += m.re; M.im += m.im;
+                        }
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        G_re[r * LDV + c] -= 0.5 * v * M.re;
+                        G_im[r * LDV + c] -= 0.5 * v * M.im;
+                    }
+                }
+            }
+        }
+        if (tid >= 64 && tid < 64 + 40) {
+            const int e_ = tid - 64;
+            const int bp = e_ >> 3, type = (e_ >> 2) & 1, ra = (e_ >> 1) & 1, ca = e_ & 1;
+            const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
+            double wgt = 0.0;
+            for (int ti = 0; ti < P.n_terms; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                const cplx x = cmul(ld_op(P.op_table, tm.op_a, ra, a), cconj(ld_op(P.op_table, tm.op_a, ca, bb)));
+                wgt += v * x.re;
+            }
+            S.jw[e_] = wgt;
+        }
+        __syncthreads();
+        if (tid < D) {
+            double cs = 0.0;
+            for (int i = 0; i < D; ++i) cs += hypot(G_re[i * LDV + tid], G_im[i * LDV + tid]);
+            S.colsum[tid] = cs;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double mc = 0.0;
+            for (int i = 0; i < D; ++i) mc = fmax(mc, S.colsum[i]);
+            double nu = 2.0 * mc;
+            for (int bp = 0; bp < N; ++bp) {
+                double best = 0.0;
+                for (int a = 0; a < 2; ++a)
+                    for (int bb = 0; bb < 2; ++bb)
+                        best = fmax(best, fabs(S.jw[bp * 8 + a * 2 + bb]) + fabs(S.jw[bp * 8 + 4 + (1 - a) * 2 + (1 - bb)]));
+                nu += best;
+            }
+            S.misc[0] = nu;
+        }
+        __syncthreads();
+        const double nu = S.misc[0];
+
+        // ---- A fragments of this warp's rows (k index permuted: pi(ks,t) = 8(ks/2) + 2t + ks%2), stencil weights
+        double a_re[8], a_im[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+            a_re[ks] = REAL_H ? 0.0 : G_re[(8 * w + g) * LDV + k];
+            a_im[ks] = G_im[(8 * w + g) * LDV + k];
+        }
+        double W0[4][2];     // halved diagonal weights for (J, e)
+#pragma unroll
+        for (int J = 0; J < 4; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double x = S.jw[4 * 8 + (w >> 1) * 2 + (J >> 1)] + S.jw[3 * 8 + (w & 1) * 2 + (J & 1)] +
+                           S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] + S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] +
+                           S.jw[0 * 8 + (g & 1) * 2 + e];
+                if (REAL_H) x += G_re[(8 * w + g) * LDV + 8 * w + g] + G_re[(8 * J + 2 * t + e) * LDV + 8 * J + 2 * t + e];
+                W0[J][e] = 0.5 * x;
+            }
+        const double F4[2] = {0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 0], 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 1]};   // by J>>1
+        const double F3[2] = {0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 0], 0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 1]};     // by J&1
+        const double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
+        const double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
+        const double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        __syncthreads();     // G has been consumed: the Vs planes are free for the Taylor terms
+
+        // ---- state: this warp's rows of rho(t_k)
+        double acc_re[4][2], acc_im[4][2];
+#pragma unroll
+        for (int J = 0; J < 4; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = orig_index(8 * w + g), c = orig_index(8 * J + 2 * t + e);
+                acc_re[J][e] = P.rho0[2 * (r * D + c)];
+                acc_im[J][e] = P.rho0[2 * (r * D + c) + 1];
+            }
+        const int tset = (target_set != nullptr) ? target_set[b] : 0;
+        const double* tgt = (P.targets != nullptr) ? P.targets + (size_t)tset * K * T * 2 : nullptr;
+        double my_loss = 0.0;
+        int n_apply = 0;
+        bool capped = false;
+
+        // per-warp partial trace of a term into S.trp[w]: diag lanes, tiles J = (w&1) + 2b
+        auto partial_trace_store = [&](const double (&xr)[4][2], const double (&xi)[4][2]) {
+            const int J0 = w & 1, J1 = (w & 1) + 2;
+            double v0 = diag_lane ? (gp ? xr[J0][1] : xr[J0][0]) : 0.0;
+            double v1 = diag_lane ? (gp ? xi[J0][1] : xi[J0][0]) : 0.0;
+            double v2 = diag_lane ? (gp ? xr[J1][1] : xr[J1][0]) : 0.0;
+            double v3 = diag_lane ? (gp ? xi[J1][1] : xi[J1][0]) : 0.0;
+            const bool up16 = lane & 16;
+            double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;
+            s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+            double k0 = (up16 ? v2 : v0) + s0, k1 = (up16 ? v3 : v1) + s1;
+            const bool up8 = lane & 8;
+            double s = up8 ? k0 : k1;
+            s = __shfl_xor_sync(0xffffffffu, s, 8);
+            double k = (up8 ? k1 : k0) + s;
+            k += __shfl_xor_sync(0xffffffffu, k, 4);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            if ((lane & 7) == 0) S.trp[w][lane >> 3] = k;
+        };
+        // after a __syncthreads: the total of value index vi = lane >> 3 (rho00.re, rho11.re, rho01.re, rho01.im)
+        auto trace_total = [&]() -> double {
+            const int vi = lane >> 3;
+            // rho_red[a][b]: a = w>>1 of the contributing warps, b = tile half
+            if (vi == 0) return S.trp[0][0] + S.trp[1][0];
+            if (vi == 1) return S.trp[2][2] + S.trp[3][2];
+            if (vi == 2) return S.trp[0][2] + S.trp[1][2];
+            return S.trp[0][3] + S.trp[1][3];
+        };
+        auto emit = [&](int q, int kbase, double y0, double y1) {
+            const int p = lane;
+            const int srcl = p & 7;
+            double r[4];
+#pragma unroll
+            for (int vi = 0; vi < 4; ++vi) {
+                const double lo = __shfl_sync(0xffffffffu, y0, vi * 8 + srcl), hi = __shfl_sync(0xffffffffu, y1, vi * 8 + srcl);
+                r[vi] = (p & 8) ? hi : lo;
+            }
+            if (w == 0 && p < q) {
+                const int k = kbase + p;
+                for (int m = 0; m < K; ++m) {
+                    const double* O = P.obs + m * 8;
+                    const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
+                    const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
+                    if (expect != nullptr) {
+                        double* e = expect + (((size_t)b * K + m) * T + k) * 2;
+                        e[0] = ere; e[1] = eim;
+                    }
+                    if (tgt != nullptr) {
+                        const double dre = ere - tgt[((size_t)m * T + k) * 2], dim = eim - tgt[((size_t)m * T + k) * 2 + 1];
+                        my_loss += dre * dre + dim * dim;
+                    }
+                }
+            }
+        };
+
+        partial_trace_store(acc_re, acc_im);
+        __syncthreads();
+        emit(1, 0, trace_total(), 0.0);
+
+        const unsigned tol_hi = (unsigned)(__double2hiint(P.tol)) & 0x7fffffffu;
+        int kidx = 0;
+        while (CUNI(kidx < T - 1)) {
+            int q, nsub;
+            double htot;
+            {
+                const double t0 = P.times[kidx];
+                q = 1;
+                while (q < CQ && kidx + q < T - 1 && nu * (P.times[kidx + q + 1] - t0) <= P.theta_target) ++q;
+                htot = P.times[kidx + q] - t0;
+                nsub = 1;
+                if (q == 1) {
+                    const double th = nu * htot;
+                    if (th > P.theta_target) nsub = (int)ceil(th / P.theta_target);
+                }
+            }
+            const double h = htot / nsub;
+            const double t0 = P.times[kidx];
+            const int p0 = lane & 7, p1 = p0 + 8;
+            const double xs0 = (p0 < q) ? ((nsub == 1) ? (P.times[kidx + 1 + p0] - t0) / htot : 1.0) : 0.0;
+            const double xs1 = (p1 < q) ? (P.times[kidx + 1 + p1] - t0) / htot : 0.0;
+            double y0 = 0.0, y1 = 0.0;
+
+            for (int sub = 0; CUNI(sub < nsub); ++sub) {
+                __syncthreads();     // everybody is done reading S.trp / S.mxs of the previous expansion
+                const bool last = (sub == nsub - 1);
+                double v_re[4][2], v_im[4][2];
+#pragma unroll
+                for (int J = 0; J < 4; ++J)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { v_re[J][e] = acc_re[J][e]; v_im[J][e] = acc_im[J][e]; }
+                double xp0 = 1.0, xp1 = 1.0;
+                if (last) { y0 = 0.0; y1 = 0.0; }
+                int small = 0;
+                unsigned mx_term = 0x7fffffffu;     // size of the term about to be published (term 0: the state itself)
+                int j = 0;
+                for (;; ++j) {
+                    // ---- [A] publish term j: rows of this warp into Vs, partial trace, size
+#pragma unroll
+                    for (int J = 0; J < 4; ++J) {
+                        *reinterpret_cast<double2*>(&S.Vs_re[(8 * w + g) * LDV + 8 * J + 2 * t]) = make_double2(v_re[J][0], v_re[J][1]);
+                        *reinterpret_cast<double2*>(&S.Vs_im[(8 * w + g) * LDV + 8 * J + 2 * t]) = make_double2(v_im[J][0], v_im[J][1]);
+                    }
+                    partial_trace_store(v_re, v_im);
+                    if (lane == 0) S.mxs[w] = mx_term;
+                    __syncthreads();
+                    {
+                        const double tr = trace_total();
+                        y0 = fma(xp0, tr, y0);
+                        y1 = fma(xp1, tr, y1);
+                        xp0 *= xs0; xp1 *= xs1;
+                    }
+                    const unsigned mx = max(max(S.mxs[0], S.mxs[1]), max(S.mxs[2], S.mxs[3]));
+                    small = (mx <= tol_hi) ? small + 1 : 0;
+                    if (CUNI(small >= 2 || j >= MCAP)) break;   // uniform over the CTA (values read from shared memory)
+
+                    // ---- [B] accumulators = J(v)/2 (all five site stencils read from Vs), then += G v on the DMMA pipe
+                    double x_re[4][2], x_im[4][2];
+#pragma unroll
+                    for (int J = 0; J < 4; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[J][e] = W0[J][e] * v_re[J][e];
+                            x_im[J][e] = W0[J][e] * v_im[J][e];
+                        }
+#pragma unroll
+                    for (int J = 0; J < 4; ++J) {
+                        const int base = 8 * J + 2 * t;
+                        // bit 4: (I^2, J^2); bit 3: (I^1, J^1); bit 2: (g^4, t^2); bit 1: (g^2, t^1); bit 0: (g^1, e^1)
+                        const int o4 = (8 * (w ^ 2) + g) * LDV + 8 * (J ^ 2) + 2 * t;
+                        const int o3 = (8 * (w ^ 1) + g) * LDV + 8 * (J ^ 1) + 2 * t;
+                        const int o2 = (8 * w + (g ^ 4)) * LDV + 8 * J + 2 * (t ^ 2);
+                        const int o1 = (8 * w + (g ^ 2)) * LDV + 8 * J + 2 * (t ^ 1);
+                        const int o0 = (8 * w + (g ^ 1)) * LDV + base;
+                        const double2 r4 = *reinterpret_cast<const double2*>(&S.Vs_re[o4]), i4 = *reinterpret_cast<const double2*>(&S.Vs_im[o4]);
+                        const double2 r3 = *reinterpret_cast<const double2*>(&S.Vs_re[o3]), i3 = *reinterpret_cast<const double2*>(&S.Vs_im[o3]);
+                        const double2 r2 = *reinterpret_cast<const double2*>(&S.Vs_re[o2]), i2 = *reinterpret_cast<const double2*>(&S.Vs_im[o2]);
+                        const double2 r1 = *reinterpret_cast<const double2*>(&S.Vs_re[o1]), i1 = *reinterpret_cast<const double2*>(&S.Vs_im[o1]);
+                        const double2 r0 = *reinterpret_cast<const double2*>(&S.Vs_re[o0]), i0 = *reinterpret_cast<const double2*>(&S.Vs_im[o0]);
+                        const double w4 = F4[J >> 1], w3 = F3[J & 1];
+                        x_re[J][0] = fma(w4, r4.x, x_re[J][0]); x_re[J][1] = fma(w4, r4.y, x_re[J][1]);
+                        x_im[J][0] = fma(w4, i4.x, x_im[J][0]); x_im[J][1] = fma(w4, i4.y, x_im[J][1]);
+                        x_re[J][0] = fma(w3, r3.x, x_re[J][0]); x_re[J][1] = fma(w3, r3.y, x_re[J][1]);
+                        x_im[J][0] = fma(w3, i3.x, x_im[J][0]); x_im[J][1] = fma(w3, i3.y, x_im[J][1]);
+                        x_re[J][0] = fma(f2, r2.x, x_re[J][0]); x_re[J][1] = fma(f2, r2.y, x_re[J][1]);
+                        x_im[J][0] = fma(f2, i2.x, x_im[J][0]); x_im[J][1] = fma(f2, i2.y, x_im[J][1]);
+                        x_re[J][0] = fma(f1, r1.x, x_re[J][0]); x_re[J][1] = fma(f1, r1.y, x_re[J][1]);
+                        x_im[J][0] = fma(f1, i1.x, x_im[J][0]); x_im[J][1] = fma(f1, i1.y, x_im[J][1]);
+                        x_re[J][0] = fma(f0[0], r0.y, x_re[J][0]); x_re[J][1] = fma(f0[1], r0.x, x_re[J][1]);   // e^1
+                        x_im[J][0] = fma(f0[0], i0.y, x_im[J][0]); x_im[J][1] = fma(f0[1], i0.x, x_im[J][1]);
+                    }
+                    // B fragments: v[k][n] = conj(v[n][k]) with n = 8J+g (a row of warp J), k = pi(ks,t): read pairs
+                    // (ks even, ks odd) = columns (2t, 2t+1) of column tile ks/2 with one LDS.128
+#pragma unroll
+                    for (int J = 0; J < 4; ++J)
+#pragma unroll
+                        for (int kt = 0; kt < 4; ++kt) {
+                            const int o = (8 * J + g) * LDV + 8 * kt + 2 * t;
+                            const double2 br = *reinterpret_cast<const double2*>(&S.Vs_re[o]);
+                            const double2 bi = *reinterpret_cast<const double2*>(&S.Vs_im[o]);
+                            // X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
+                            if (!REAL_H) {
+                                dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt], br.x);
+                                dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt], neg_c(bi.x));
+                                dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt + 1], br.y);
+                                dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt + 1], neg_c(bi.y));
+                            }
+                            dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt], bi.x);
+                            dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt], br.x);
+                            dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt + 1], bi.y);
+                            dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt + 1], br.y);
+                        }
+                    // publish X' column-major so that the transpose is a vector load
+#pragma unroll
+                    for (int J = 0; J < 4; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            S.Xs_re[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_re[J][e];
+                            S.Xs_im[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_im[J][e];
+                        }
+                    __syncthreads();
+
+                    // ---- [C] next term = f (X' + X'^dag):  X'^dag[8w+g][8J+2t+e] = conj(X'[8J+2t+e][8w+g])
+                    const double f = h / (double)(j + 1);
+                    unsigned mxl = 0;
+#pragma unroll
+                    for (int J = 0; J < 4; ++J) {
+                        const int o = (8 * w + g) * LDX + 8 * J + 2 * t;
+                        const double2 tr_ = *reinterpret_cast<const double2*>(&S.Xs_re[o]);
+                        const double2 ti_ = *reinterpret_cast<const double2*>(&S.Xs_im[o]);
+                        const double wr0 = (x_re[J][0] + tr_.x) * f, wr1 = (x_re[J][1] + tr_.y) * f;
+                        const double wi0 = (x_im[J][0] - ti_.x) * f, wi1 = (x_im[J][1] - ti_.y) * f;
+                        v_re[J][0] = wr0; v_re[J][1] = wr1; v_im[J][0] = wi0; v_im[J][1] = wi1;
+                        acc_re[J][0] += wr0; acc_re[J][1] += wr1; acc_im[J][0] += wi0; acc_im[J][1] += wi1;
+                        mxl = max(mxl, (unsigned)__double2hiint(wr0) & 0x7fffffffu);
+                        mxl = max(mxl, (unsigned)__double2hiint(wr1) & 0x7fffffffu);
+                        mxl = max(mxl, (unsigned)__double2hiint(wi0) & 0x7fffffffu);
+                        mxl = max(mxl, (unsigned)__double2hiint(wi1) & 0x7fffffffu);
+                    }
+                    mx_term = __reduce_max_sync(0xffffffffu, mxl);
+                }
+                n_apply += j;
+                if (j >= MCAP && small < 2) capped = true;
+            }
+            emit(q, kidx + 1, y0, y1);
+            kidx += q;
+        }
+
+        if (w == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+            if (lane == 0) {
+                if (loss != nullptr) loss[b] = (tgt != nullptr) ? my_loss / ((double)T * (double)K) : 0.0;
+                if (status != nullptr) status[b] = capped ? -1 : n_apply;
+            }
+        }
+    }
+}
+
+template __global__ void eval_cta_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+template __global__ void eval_cta_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+
+bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian && P.n_tls == 5 && P.n_params <= CMAXP; }
+
+// declared in eml_warp_mma.cu
+void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, cudaStream_t stream);
+
+cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
+                           double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
+                           cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    const int* use_order = nullptr;
+    if (order != nullptr && n_models > 2LL * sms && n_models <= (1 << 18)) {
+        launch_model_order(P, n_models, params, order, stream);
+        use_order = order;
+    }
+    long long ctas = n_models;
+    if (ctas > 2LL * sms) ctas = 2LL * sms;
+    if (real_h)
+        eval_cta_mma_kernel<true><<<(unsigned)ctas, 128, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order);
+    else
+        eval_cta_mma_kernel<false><<<(unsigned)ctas, 128, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order);
+    return cudaGetLastError();
+}
+
+}  // namespace eml

@@ -558,6 +558,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #define EML_WARP_INST(TL, RH) template __global__ void eval_warp_mma_kernel<TL, RH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
 EML_WARP_INST(1, true) EML_WARP_INST(1, false) EML_WARP_INST(2, true) EML_WARP_INST(2, false)
 
+// longest-first model order into `order` (capacity 2 * ORDER_MAX_MODELS ints: order + float cost scratch)
+void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, cudaStream_t stream) {
+    float* cost = reinterpret_cast<float*>(order + ORDER_MAX_MODELS);
+    model_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>(P, (int)n_models, params, cost);
+    order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
+}
+
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }
@@ -573,9 +580,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {
-        float* cost = reinterpret_cast<float*>(order + ORDER_MAX_MODELS);      // second half of the buffer
-        model_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>(P, (int)n_models, params, cost);
-        order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
+        launch_model_order(P, n_models, params, order, stream);
         use_order = order;
     }
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,

@@ -146,7 +146,7 @@ def use_kernel():
 
     def select(name):
         engine.default_kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC,
-                                 'warp_mma': _native.KERNEL_WARP_MMA}[name]
+                                 'warp_mma': _native.KERNEL_WARP_MMA, 'cta_mma': _native.KERNEL_CTA_MMA}[name]
         engine.clear_contexts()
     yield select
     engine.default_kernel = saved
@@ -293,3 +293,54 @@ def test_posterior_predictive_and_dense_grid_callers():
     grid, data = predictive.dense_grid_dynamics(model_from_spec(specs[0]), ts, OBS3)
     assert len(grid) == 1200 and grid[0] == ts[0] and grid[-1] == ts[-1]
     assert_close(data, lo.expect_exact(specs[0], grid, OBS3), TOL, 'dense grid')
+
+
+# ---------------------------------------------------------------------------------------------
+# d = 32 kernel (four warps per model)
+def _d32_specs():
+    specs = [lo.random_library_spec(np.random.default_rng(7000 + b), 2, 3) for b in range(5)]
+    # first qubit NOT at site 0, sigma-/+ and projector jumps, a complex Hermitian coupling (sigmax (x) sigmay)
+    specs.append({'tls': [
+        {'is_qubit': False, 'energy': 0.3, 'Ls': {'sigmam': 0.2, 'sigmax': 0.05}, 'initial_state': None, 'couplings': []},
+        {'is_qubit': False, 'energy': 0.12, 'Ls': {'exc': 0.3, 'sigmap': 0.11}, 'initial_state': lo.OPS['mm'],
+         'couplings': [(0, 1.4, [('sigmax', 'sigmax')]), (2, 0.9, [('sigmay', 'sigmay'), ('sigmaz', 'sigmaz')])]},
+        {'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmaz': 0.07, 'sigmam': 0.13, 'gnd': 0.2},
+         'initial_state': lo.OPS['2e+1g'], 'couplings': [(3, 2.2, [('sigmax', 'sigmax')]), (4, 0.7, [('sigmax', 'sigmay')])]},
+        {'is_qubit': True, 'energy': 0.8, 'Ls': {'sigmay': 0.3}, 'initial_state': None,
+         'couplings': [(0, 0.6, [('sigmaz', 'sigmax')])]},
+        {'is_qubit': False, 'energy': 0.21, 'Ls': {'sigmaz': 0.15, 'sigmay': 0.02}, 'initial_state': lo.OPS['mm'],
+         'couplings': [(1, 1.1, [('sigmaz', 'sigmaz')])]},
+    ]})
+    return specs
+
+
+@pytest.mark.parametrize('kernel', ['cta_mma', 'generic'])
+def test_d32_kernels_match_oracle(use_kernel, kernel):
+    from effective_model_learning_b200 import engine
+    use_kernel(kernel)
+    rng = np.random.default_rng(8)
+    ts = np.sort(np.concatenate([np.linspace(0.0, 2.5, 70), [2.5 + 9.0], rng.uniform(0, 2.5, 10)]))
+    worst = 0.0
+    for i, spec in enumerate(_d32_specs()):
+        m = model_from_spec(spec)
+        obs = ['sigmax', 'sigmap', 'sigmaz']
+        got = m.calculate_dynamics(ts, obs)
+        assert engine.context_for(m, obs, ts).plan.kernel_name.startswith(kernel)
+        want = lo.expect_exact(spec, ts, obs)
+        assert_close(got, want, TOL, f'{kernel} d=32 model {i}')
+        worst = max(worst, max_err(got, want))
+    print(f'{kernel} d=32: worst abs err {worst:.2e}')
+
+
+def test_d32_batch_loss_equals_generic(use_kernel):
+    from effective_model_learning_b200 import engine
+    ts = np.linspace(0.0, 2.5, 40)
+    specs = [lo.random_library_spec(np.random.default_rng(9000 + b), 2, 3) for b in range(330)]
+    models = [model_from_spec(s) for s in specs]
+    targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
+    out = {}
+    for kernel in ('generic', 'cta_mma'):
+        use_kernel(kernel)
+        out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
+    assert np.abs(out['generic'][0] - out['cta_mma'][0]).max() < 1e-10
+    np.testing.assert_allclose(out['generic'][1], out['cta_mma'][1], rtol=1e-9, atol=1e-14)
