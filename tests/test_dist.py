@@ -63,3 +63,14 @@ def test_single_process_gather_is_identity():
     assert np.array_equal(edist.gather_chain_stats(x), x)
     with pytest.raises(RuntimeError):
         edist.gather_chain_stats(np.zeros((3, 2)))
+
+
+def test_enumerate_chains_follows_launcher_loop_order():
+    from effective_model_learning_b200.multiset import enumerate_chains
+    ch = enumerate_chains(2, [11, 0], [1, 2, 3], [2])
+    assert len(ch) == 2 * 2 * 3 * 2
+    assert [(c.dataset, c.config, c.defects, c.repetition) for c in ch[:5]] == \
+        [(0, 11, 1, 1), (0, 11, 1, 2), (0, 11, 2, 1), (0, 11, 2, 2), (0, 11, 3, 1)]
+    ch = enumerate_chains(1, [11], [1, 2], [3, 1])
+    assert [(c.defects, c.repetition) for c in ch] == [(1, 1), (1, 2), (1, 3), (2, 1)]
+    assert len(enumerate_chains(1, [11], [1, 2], [5, 5, 5])) == 6      # malformed repetitions -> default 3 each
