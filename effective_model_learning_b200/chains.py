@@ -42,11 +42,12 @@ class BatchedChains:
 
     target_datasets: [K][T] (shared by all chains) or [S][K][T] with `target_set[n_chains]` choosing one per chain.
     Hyperparameters take the names and meaning of LearningChain's (configs.py dictionaries can be passed as **config).
+    Chain c uses the random stream of global chain number first_chain + c.
     """
 
     def __init__(self, target_times, target_datasets, target_observables, *, n_chains: int, n_defects: int,
                  n_qubits: int = 1, qubit_energy: float = 1.0, qubit_initial_state=None, defect_initial_state=None,
-                 target_set=None, seed: int = 0, device: int = 0, initial_params=None,
+                 target_set=None, seed: int = 0, first_chain: int = 0, device: int = 0, initial_params=None,
                  chain_step_options=None, temperature_proposal=0.0005, shock_anneal_at=False, complexity_factor=1,
                  jump_length_rescaling_factor=1.0, acceptance_window=10, acceptance_target=0.4, acceptance_band=0.2,
                  params_handler_hyperparams=None, qubit_Ls_library=None, defect_Ls_library=None,
@@ -112,7 +113,7 @@ class BatchedChains:
         _native.check(lib.eml_chains_create(plan.handle, C.byref(h), self.n_chains,
                                             initial_params.ctypes.data_as(C.POINTER(C.c_double)),
                                             ts.ctypes.data_as(C.POINTER(C.c_int32)) if ts is not None else None,
-                                            C.c_uint64(seed & (2 ** 64 - 1)), C.byref(handle)), 'eml_chains_create')
+                                            C.c_uint64(seed & (2 ** 64 - 1)), int(first_chain), C.byref(handle)), 'eml_chains_create')
         self._h = handle
         self.steps_done = 0
 

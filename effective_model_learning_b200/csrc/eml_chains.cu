@@ -127,14 +127,14 @@ __device__ inline double xi_product(const ChainHyperDev& H, const double* row, c
 }
 
 __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
-                                      const unsigned long long seed) {
+                                      const unsigned long long seed, const long long first_chain) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chains) return;
     const int P = H.n_params;
     double* cur = S.cur + c * P;
     double* prop = S.prop + c * P;
     double* jump = S.jump + c * 3;
-    Rng rng{chain_key(seed, c), S.rng_ctr[c]};
+    Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
 
     // shock annealing: switch to the annealed jump lengths and restart from the best model (learning_chain.py:349-367)
     if (H.shock_anneal_at > 0 && S.step[c] == H.shock_anneal_at) {
@@ -231,11 +231,12 @@ __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S,
 }
 
 __global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
-                                     const unsigned long long seed, double* hist_loss, double* hist_aprob, int* hist_code) {
+                                     const unsigned long long seed, const long long first_chain, double* hist_loss,
+                                     double* hist_aprob, int* hist_code) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chains) return;
     const int P = H.n_params;
-    Rng rng{chain_key(seed, c), S.rng_ctr[c]};
+    Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
     const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
     const double a = exp(-1.0 / S.temp[c] * (Lp - Lc)) * S.log_ratio[c];     // learning_chain.py:802-805
     const bool accept = rng.uniform() < a;
@@ -296,6 +297,7 @@ struct EmlChains {
     EmlPlan* plan = nullptr;
     long long n = 0;
     unsigned long long seed = 0;
+    long long first_chain = 0;
     eml::ChainHyperDev H{};
     eml::ChainState S{};
     std::vector<void*> owned;
@@ -324,7 +326,7 @@ int eml_chains_destroy(EmlChains* ch) {
 }
 
 int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, const double* initial_params,
-                      const int32_t* target_set, uint64_t seed, EmlChains** out) {
+                      const int32_t* target_set, uint64_t seed, int64_t first_chain, EmlChains** out) {
     if (!out) return fail(EML_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
     if (!plan || !h || !initial_params) return fail(EML_ERR_INVALID_ARGUMENT, "plan/hyper/initial_params is NULL");
@@ -341,7 +343,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     EML_CUDA(cudaSetDevice(plan->device));
     EmlChains* ch = new (std::nothrow) EmlChains();
     if (!ch) return fail(EML_ERR_CUDA, "out of host memory");
-    ch->plan = plan; ch->n = n_chains; ch->seed = seed;
+    ch->plan = plan; ch->n = n_chains; ch->seed = seed; ch->first_chain = first_chain;
     const int P = h->n_params;
     eml::ChainHyperDev& H = ch->H;
     H.n_params = P; H.window = h->acceptance_window;
@@ -389,10 +391,10 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((ch->n + 127) / 128);
     for (int64_t i = 0; i < n_steps; ++i) {
-        eml::chains_propose_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed);
+        eml::chains_propose_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain);
         int rc = eml_eval_batch(ch->plan, ch->n, ch->S.prop, ch->d_target_set, nullptr, ch->S.prop_loss, ch->d_status, s);
         if (rc != EML_OK) return rc;
-        eml::chains_accept_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed,
+        eml::chains_accept_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain,
                                                         hist_loss ? hist_loss + i * ch->n : nullptr,
                                                         hist_aprob ? hist_aprob + i * ch->n : nullptr,
                                                         hist_code ? hist_code + i * ch->n : nullptr);

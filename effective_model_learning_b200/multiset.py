@@ -69,7 +69,7 @@ class MultisetSweep:
             ts, data, obs = datasets[ds]
             eng = BatchedChains(ts, data, obs, n_chains=len(members), n_defects=D,
                                 qubit_initial_state=qubit_initial_state, defect_initial_state=defect_initial_state,
-                                seed=seed + 7919 * members[0], device=device, **cfg)
+                                seed=seed, first_chain=members[0], device=device, **cfg)
             self.engines.append((key, members, eng, torch.cuda.Stream(device=device)))
 
     def run(self, steps: int):

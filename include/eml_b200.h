@@ -176,9 +176,11 @@ typedef struct EmlChainHyper {
 
 typedef struct EmlChains EmlChains; /* opaque */
 
-/* initial_params: HOST [n_chains][P]; target_set: HOST [n_chains] or NULL.  Evaluates the initial models. */
+/* initial_params: HOST [n_chains][P]; target_set: HOST [n_chains] or NULL.  Evaluates the initial models.
+ * Chain c draws from the random stream of global chain number first_chain + c, so a sweep gives the same
+ * results however its chains are partitioned over engines and GPUs. */
 int eml_chains_create(EmlPlan* plan, const EmlChainHyper* hyper, int64_t n_chains, const double* initial_params,
-                      const int32_t* target_set, uint64_t seed, EmlChains** out);
+                      const int32_t* target_set, uint64_t seed, int64_t first_chain, EmlChains** out);
 int eml_chains_destroy(EmlChains* chains);
 /* n_steps proposals per chain, asynchronous on `stream`.  Optional DEVICE history buffers [n_steps][n_chains]:
  * proposal loss, acceptance probability, code = move << 1 | accepted. */

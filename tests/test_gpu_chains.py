@@ -88,3 +88,19 @@ def test_many_chains_reduce_the_loss_and_stay_in_bounds():
     table = eng.checkpoint()
     assert table.shape == (512, 8) and np.array_equal(table[:, 1], state['best_loss'])
     eng.close()
+
+
+def test_results_do_not_depend_on_how_chains_are_split_over_engines():
+    """first_chain makes chain c of a sweep use the same random stream whichever engine / GPU owns it."""
+    cfg, ts, targets, whole = _setup(2, 64)
+    whole.run(25)
+    a = whole.read()
+    whole.close()
+    parts = []
+    for lo_, hi_ in ((0, 24), (24, 64)):
+        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=2, seed=1234, first_chain=lo_, **cfg)
+        eng.run(25)
+        parts.append(eng.read())
+        eng.close()
+    for key in ('current_params', 'best_loss', 'stats'):
+        assert np.array_equal(a[key], np.concatenate([p[key] for p in parts]))
