@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libeml_b200.so')
+LIB_PATH = os.environ.get('EML_B200_LIB', os.path.join(_HERE, 'libeml_b200.so'))   # override: kernel-variant experiments
 
 EML_OK = 0
 EML_ERR_NOT_CONVERGED = -4

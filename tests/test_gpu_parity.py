@@ -344,3 +344,42 @@ def test_d32_batch_loss_equals_generic(use_kernel):
         out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
     assert np.abs(out['generic'][0] - out['cta_mma'][0]).max() < 1e-10
     np.testing.assert_allclose(out['generic'][1], out['cta_mma'][1], rtol=1e-9, atol=1e-14)
+
+
+def test_c_abi_edge_cases_and_error_codes():
+    """Empty batch, eight observables, a single time, bad descriptors -> RuntimeError with the library's message."""
+    from effective_model_learning_b200 import _native, definitions, engine
+    ops = definitions.ops
+    op_table = np.stack([ops['sigmaz'], ops['sigmax']])
+    rho0 = np.kron(ops['plus'], ops['mm'])
+    terms = [(0, _native.TERM_ENERGY, 0, -1, 0, -1), (1, _native.TERM_COUPLING, 0, 1, 1, 1), (2, _native.TERM_LINDBLAD, 1, -1, 0, -1)]
+    ts = np.linspace(0, 1, 9)
+    names = ['sigmax', 'sigmay', 'sigmaz', 'sigmap', 'sigmam', 'exc', 'gnd', 'id2']
+    obs = np.stack([ops[n] for n in names])
+    plan = _native.Plan(2, 3, terms, op_table, rho0, 0, obs, ts)
+    ex, loss = plan.eval_host(np.zeros((0, 3)), want_expect=True, want_loss=False)
+    assert ex.shape == (0, 8, 9)
+    ex, _ = plan.eval_host(np.array([[1.0, 0.9, 0.2]]), want_expect=True, want_loss=False)
+    spec = {'tls': [{'is_qubit': True, 'energy': 1.0, 'Ls': {}, 'initial_state': lo.OPS['plus'],
+                     'couplings': [(1, 0.9, [('sigmax', 'sigmax')])]},
+                    {'is_qubit': False, 'energy': 0.0, 'Ls': {'sigmaz': 0.2}, 'initial_state': lo.OPS['mm'], 'couplings': []}]}
+    want = lo.expect_exact(spec, ts, names)
+    for m in range(8):
+        assert np.abs(ex[0, m] - want[m]).max() < TOL
+    assert abs(ex[0, 7] - 1).max() < 1e-12                    # Tr(rho) stays 1
+    # loss requested without targets is defined as 0; targets of the wrong shape are refused
+    _, loss = plan.eval_host(np.array([[1.0, 0.9, 0.2]]), want_expect=False, want_loss=True)
+    assert loss[0] == 0.0
+    with pytest.raises(RuntimeError):
+        plan.set_targets(np.zeros((3, 9)))
+    plan.close()
+    with pytest.raises(RuntimeError, match='non-decreasing'):
+        _native.Plan(2, 3, terms, op_table, rho0, 0, obs, ts[::-1].copy())
+    with pytest.raises(RuntimeError, match='malformed'):
+        _native.Plan(2, 3, [(5, 0, 0, -1, 0, -1)], op_table, rho0, 0, obs, ts)
+    with pytest.raises(RuntimeError, match='n_tls'):
+        _native.Plan(6, 0, [], op_table, np.eye(64), 0, obs, ts)
+    with pytest.raises(RuntimeError, match='n_obs'):
+        _native.Plan(2, 3, terms, op_table, rho0, 0, np.stack([ops['id2']] * 9), ts)
+    with pytest.raises(RuntimeError, match='warp_mma'):
+        _native.Plan(5, 0, [], op_table, np.eye(32) / 32, 0, obs, ts, kernel=_native.KERNEL_WARP_MMA)
