@@ -276,6 +276,15 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                     if (th > P.theta_target) nsub = (int)ceil(th / P.theta_target);
                 }
             }
+            if (CUNI(htot == 0.0)) {     // repeated time points: the state does not move
+                __syncthreads();
+                partial_trace_store(acc_re, acc_im);
+                __syncthreads();
+                const double tr = trace_total();
+                emit(q, kidx + 1, tr, tr);
+                kidx += q;
+                continue;
+            }
             const double h = htot / nsub;
             const double t0 = P.times[kidx];
             const int p0 = lane & 7, p1 = p0 + 8;

@@ -229,6 +229,13 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
         int q, nsub;
         double htot;
         choose_step(P.times, T, k, nu, P.theta_target, q, nsub, htot);
+        if (htot == 0.0) {               // repeated time points: the state does not move
+#pragma unroll
+            for (int p = 0; p < QMAX; ++p) { y_re[p] = acc_re; y_im[p] = acc_im; }
+            emit(q, k + 1);
+            k += q;
+            continue;
+        }
         const double h = htot / nsub;
         const double t0 = P.times[k];
 #pragma unroll

@@ -48,6 +48,9 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+// 1/(j+1) for the Taylor recurrences
+__constant__ double INV_TABLE[MCAP + 2];
+
 // warp-uniform predicate the compiler can SEE is uniform (vote result): keeps shuffles free of divergence guards
 #define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
@@ -273,9 +276,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     W0[I][J][e] = 0.5 * w;
                 }
             }
-        const double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
-        const double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
-        const double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
+        double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
+        double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        // The generator is kept PRE-MULTIPLIED by the current step length h (rescaled in place when h changes), so
+        // that u_{j+1} = (h L) u_j needs no per-element scaling; the Taylor term is u_j / j!.
+        double h_cur = 1.0;
 
         // ---- state: acc = rho(t_k) in C layout (rho0 permuted to the kernel's bit order)
         double acc_re[TL][TL][2], acc_im[TL][TL][2];
@@ -365,7 +371,6 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             emit(1, 0, v, 0.0);
         }
 
-        const unsigned tol_hi = (unsigned)(__double2hiint(P.tol)) & 0x7fffffffu;
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
             int q, nsub;
@@ -381,6 +386,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     const double th = nu * htot;
                     if (th > P.theta_target) nsub = (int)ceil(th / P.theta_target);
                 }
+            }
+            if (UNI(htot == 0.0)) {      // repeated time points: the state does not move
+                const double tr = partial_trace(acc_re, acc_im);
+                emit(q, kidx + 1, tr, tr);
+                kidx += q;
+                continue;
             }
             const double h = htot / nsub;
             const double t0 = P.times[kidx];
@@ -398,7 +409,24 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) { v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e]; }
-                double xp0 = 1.0, xp1 = 1.0;
+                if (UNI(h != h_cur)) {
+                    const double rs = h / h_cur;
+                    h_cur = h;
+#pragma unroll
+                    for (int I = 0; I < TL; ++I) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) { a_re[I][ks] *= rs; a_im[I][ks] *= rs; }
+#pragma unroll
+                        for (int J = 0; J < TL; ++J) {
+                            F3[I][J] *= rs;
+                            W0[I][J][0] *= rs; W0[I][J][1] *= rs;
+                        }
+                    }
+                    f2 *= rs; f1 *= rs; f0[0] *= rs; f0[1] *= rs;
+                }
+                double xp0 = 1.0, xp1 = 1.0;      // x^j / j! for this lane's two outputs
+                double cfac = 1.0;                // 1 / j!
+                double thr = P.tol;               // tol * j!: |u_j| <= thr  <=>  |term_j| <= tol
                 if (last) { y0 = 0.0; y1 = 0.0; }
                 int small = 0;
                 int j = 0;
@@ -409,7 +437,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         const double tr = partial_trace(v_re, v_im);
                         y0 = fma(xp0, tr, y0);
                         y1 = fma(xp1, tr, y1);
-                        xp0 *= xs0; xp1 *= xs1;
+                        const double inv = INV_TABLE[j];
+                        xp0 *= xs0 * inv; xp1 *= xs1 * inv;
                     }
                     // ---- accumulators start from J(v)/2: real-weighted site stencils (depend only on v)
                     double x_re[TL][TL][2], x_im[TL][TL][2];
@@ -495,8 +524,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             }
                         }
                     }
-                    // ---- next term = f (X' + X'^dag)
-                    const double f = h / (double)(j + 1);
+                    // ---- u_{j+1} = X' + X'^dag;  term_{j+1} = u_{j+1} / (j+1)!
+                    cfac *= INV_TABLE[j];
+                    thr *= (double)(j + 1);
                     unsigned mx = 0;
                     double w_re[TL][TL][2], w_im[TL][TL][2];
 #pragma unroll
@@ -512,8 +542,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             const double t_im[2] = {gp ? rBi : rAi, gp ? rAi : rBi};
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                const double wr = (x_re[I][J][e] + t_re[e]) * f;
-                                const double wi = (x_im[I][J][e] - t_im[e]) * f;
+                                const double wr = x_re[I][J][e] + t_re[e];
+                                const double wi = x_im[I][J][e] - t_im[e];
                                 w_re[I][J][e] = wr; w_im[I][J][e] = wi;
                                 mx = max(mx, (unsigned)__double2hiint(wr) & 0x7fffffffu);
                                 mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
@@ -526,10 +556,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
-                                acc_re[I][J][e] += w_re[I][J][e]; acc_im[I][J][e] += w_im[I][J][e];
+                                acc_re[I][J][e] = fma(cfac, w_re[I][J][e], acc_re[I][J][e]);
+                                acc_im[I][J][e] = fma(cfac, w_im[I][J][e], acc_im[I][J][e]);
                             }
                     mx = __reduce_max_sync(0xffffffffu, mx);
-                    small = (mx <= tol_hi) ? small + 1 : 0;      // mx is warp-uniform (REDUX result)
+                    small = (mx <= ((unsigned)__double2hiint(thr) & 0x7fffffffu)) ? small + 1 : 0;   // mx is warp-uniform (REDUX)
                     if (UNI(small >= 2)) { ++j; break; }
                 }
                 {   // the final term computed above has not been traced yet
@@ -569,6 +600,19 @@ bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }
 
+static cudaError_t init_inv_table() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && done[dev]) return cudaSuccess;
+    double h[MCAP + 2];
+    for (int j = 0; j < MCAP + 2; ++j) h[j] = 1.0 / (double)(j + 1);
+    e = cudaMemcpyToSymbol(INV_TABLE, h, sizeof(h));
+    if (e == cudaSuccess && dev < 64) done[dev] = true;
+    return e;
+}
+
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
                             bool real_h, cudaStream_t stream) {
@@ -576,6 +620,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = init_inv_table()) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
     const int* use_order = nullptr;

@@ -383,3 +383,13 @@ def test_c_abi_edge_cases_and_error_codes():
         _native.Plan(2, 3, terms, op_table, rho0, 0, np.stack([ops['id2']] * 9), ts)
     with pytest.raises(RuntimeError, match='warp_mma'):
         _native.Plan(5, 0, [], op_table, np.eye(32) / 32, 0, obs, ts, kernel=_native.KERNEL_WARP_MMA)
+
+
+@pytest.mark.parametrize('QD', [(1, 1), (1, 2), (1, 3), (2, 3)])
+def test_trailing_and_isolated_repeated_times(QD):
+    """Zero-length macro steps (the last times equal; a repeat followed by a long interval) must not produce NaNs."""
+    ts = np.array([0.0, 0.0, 0.4, 0.4, 0.4, 30.0, 30.0, 30.5, 30.5])
+    spec = lo.random_library_spec(np.random.default_rng(77), *QD)
+    got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
+    assert all(np.all(np.isfinite(g)) for g in got)
+    assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, f'repeated times {QD}')
