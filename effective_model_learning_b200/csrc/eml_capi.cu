@@ -15,11 +15,11 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                            cudaStream_t stream);
+                            const int* cost_hint, cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           cudaStream_t stream);
+                           const int* cost_hint, cudaStream_t stream);
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
@@ -237,8 +237,11 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
     return "generic";
 }
 
-int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
-                   double* loss, int32_t* status, void* stream) {
+}  // extern "C"
+
+// internal entry point: eml_eval_batch plus an optional measured cost per model for the longest-first ordering
+int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
+                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint) {
     if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
     if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
     if (n_models == 0) return EML_OK;
@@ -250,10 +253,10 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
-                                 (cudaStream_t)stream);
+                                 cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order,
-                                plan->real_h, (cudaStream_t)stream);
+                                plan->real_h, cost_hint, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)
@@ -261,6 +264,15 @@ int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const 
     if (e != cudaSuccess) return fail(EML_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return EML_OK;
 }
+
+extern "C" {
+
+int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
+                   double* loss, int32_t* status, void* stream) {
+    return eml_eval_batch_hinted(plan, n_models, params, target_set, expect, loss, status, stream, nullptr);
+}
+
+}  // extern "C"
 
 static int ensure_staging(EmlPlan* plan, long long n) {
     if (!plan->stream) EML_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
@@ -288,6 +300,8 @@ static int ensure_staging(EmlPlan* plan, long long n) {
     plan->cap_models = cap;
     return EML_OK;
 }
+
+extern "C" {
 
 int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
                         double* expect, double* loss) {

@@ -392,7 +392,9 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
     const unsigned blocks = (unsigned)((ch->n + 127) / 128);
     for (int64_t i = 0; i < n_steps; ++i) {
         eml::chains_propose_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain);
-        int rc = eml_eval_batch(ch->plan, ch->n, ch->S.prop, ch->d_target_set, nullptr, ch->S.prop_loss, ch->d_status, s);
+        // the generator applications each chain's previous proposal needed order this step's models (longest first)
+        int rc = eml_eval_batch_hinted(ch->plan, ch->n, ch->S.prop, ch->d_target_set, nullptr, ch->S.prop_loss, ch->d_status, s,
+                                       ch->d_status);
         if (rc != EML_OK) return rc;
         eml::chains_accept_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain,
                                                         hist_loss ? hist_loss + i * ch->n : nullptr,

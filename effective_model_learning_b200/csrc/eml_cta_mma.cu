@@ -434,11 +434,12 @@ template __global__ void eval_cta_mma_kernel<false>(const DevProblem, const long
 bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian && P.n_tls == 5 && P.n_params <= CMAXP; }
 
 // declared in eml_warp_mma.cu
-void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, cudaStream_t stream);
+void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, const int* cost_hint,
+                        cudaStream_t stream);
 
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           cudaStream_t stream) {
+                           const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -446,7 +447,7 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 2LL * sms && n_models <= (1 << 18)) {
-        launch_model_order(P, n_models, params, order, stream);
+        launch_model_order(P, n_models, params, order, cost_hint, stream);
         use_order = order;
     }
     long long ctas = n_models;

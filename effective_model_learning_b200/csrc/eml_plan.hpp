@@ -37,3 +37,6 @@ struct EmlPlan {
     unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
     int* d_order = nullptr;             // LPT model order (capacity 2^18 models) followed by the float cost scratch
 };
+
+int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
+                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint);

@@ -589,10 +589,21 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #define EML_WARP_INST(TL, RH) template __global__ void eval_warp_mma_kernel<TL, RH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
 EML_WARP_INST(1, true) EML_WARP_INST(1, false) EML_WARP_INST(2, true) EML_WARP_INST(2, false)
 
-// longest-first model order into `order` (capacity 2 * ORDER_MAX_MODELS ints: order + float cost scratch)
-void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, cudaStream_t stream) {
+__global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_models) cost[b] = (float)max(hint[b], 0);
+}
+
+// longest-first model order into `order` (capacity 2 * ORDER_MAX_MODELS ints: order + float cost scratch).
+// cost_hint (device, optional): a measured cost per model, e.g. the generator applications the same chain's previous
+// proposal needed; without it a proxy computed from the parameters is used.
+void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, const int* cost_hint,
+                        cudaStream_t stream) {
     float* cost = reinterpret_cast<float*>(order + ORDER_MAX_MODELS);
-    model_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>(P, (int)n_models, params, cost);
+    if (cost_hint != nullptr)
+        hint_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>((int)n_models, cost_hint, cost);
+    else
+        model_cost_kernel<<<(unsigned)((n_models + 255) / 256), 256, 0, stream>>>(P, (int)n_models, params, cost);
     order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
 }
 
@@ -615,7 +626,7 @@ static cudaError_t init_inv_table() {
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
-                            bool real_h, cudaStream_t stream) {
+                            bool real_h, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -625,7 +636,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {
-        launch_model_order(P, n_models, params, order, stream);
+        launch_model_order(P, n_models, params, order, cost_hint, stream);
         use_order = order;
     }
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
