@@ -143,8 +143,9 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         __syncthreads();
         if (tid == 0) {
             double mc = 0.0;
-            for (int i = 0; i < D; ++i) mc = fmax(mc, S.colsum[i]);
-            double nu = 2.0 * mc;
+            double poison = 0.0;     // fmax drops NaNs: carry them into nu explicitly
+            for (int i = 0; i < D; ++i) { mc = fmax(mc, S.colsum[i]); poison += S.colsum[i]; }
+            double nu = 2.0 * mc + 0.0 * poison;
             for (int bp = 0; bp < N; ++bp) {
                 double best = 0.0;
                 for (int a = 0; a < 2; ++a)
@@ -156,6 +157,13 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         }
         __syncthreads();
         const double nu = S.misc[0];
+        if (!(nu * (P.times[T - 1] - P.times[0]) < 1e7)) {     // non-finite generator or absurd step count: do not hang
+            if (tid == 0) {
+                if (loss != nullptr) loss[b] = nan("");
+                if (status != nullptr) status[b] = -1;
+            }
+            continue;
+        }
 
         // ---- A fragments of this warp's rows (k index permuted: pi(ks,t) = 8(ks/2) + 2t + ks%2), stencil weights
         double a_re[8], a_im[8];

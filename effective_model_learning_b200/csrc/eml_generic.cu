@@ -142,8 +142,9 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
     __syncthreads();
     if (tid == 0) {
         double mc = 0.0, mr = 0.0;
-        for (int i = 0; i < D; ++i) { mc = fmax(mc, misc[i]); mr = fmax(mr, misc[D + i]); }
-        double nu = mc + mr;
+        double poison = 0.0;     // fmax drops NaNs: carry them into nu explicitly
+        for (int i = 0; i < D; ++i) { mc = fmax(mc, misc[i]); mr = fmax(mr, misc[D + i]); poison += misc[i] + misc[D + i]; }
+        double nu = mc + mr + 0.0 * poison;
         for (int s = 0; s < N; ++s) {
             double best = 0.0;
             for (int col = 0; col < 4; ++col) {
@@ -157,6 +158,13 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
     }
     __syncthreads();
     const double nu = misc[2 * D];
+    if (!(nu * (P.times[T - 1] - P.times[0]) < 1e7)) {         // non-finite generator or absurd step count: do not hang
+        if (tid == 0) {
+            if (loss != nullptr) loss[b] = nan("");
+            if (status != nullptr) status[b] = -1;
+        }
+        return;
+    }
     double* lossbuf = misc + 2 * D + 8;   // [QMAX*MAX_OBS] per-thread loss partials
 
     // ---- per-thread element

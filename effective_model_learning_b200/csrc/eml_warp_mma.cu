@@ -233,8 +233,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         __syncwarp();
         if (lane == 0) {
             double mc = 0.0;
-            for (int i = 0; i < D; ++i) mc = fmax(mc, S.colsum[i]);
-            double nu = 2.0 * mc;
+            double poison = 0.0;     // fmax drops NaNs: carry them into nu explicitly
+            for (int i = 0; i < D; ++i) { mc = fmax(mc, S.colsum[i]); poison += S.colsum[i]; }
+            double nu = 2.0 * mc + 0.0 * poison;
             for (int bp = 0; bp < N; ++bp) {
                 double best = 0.0;
                 for (int a = 0; a < 2; ++a)
@@ -246,6 +247,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         }
         __syncwarp();
         const double nu = S.misc[0];
+        // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
+        if (UNI(!(nu * (P.times[T - 1] - P.times[0]) < 1e7))) {
+            if (lane == 0) {
+                if (loss != nullptr) loss[b] = nan("");
+                if (status != nullptr) status[b] = -1;
+            }
+            __syncwarp();
+            continue;
+        }
 
         // ---- A fragments of G with the permuted k index.  REAL_H: H is real, so G.re = -K/2 is diagonal and is
         //      folded into the diagonal stencil weight; only G.im = -H goes through the DMMA pipe.

@@ -393,3 +393,23 @@ def test_trailing_and_isolated_repeated_times(QD):
     got = model_from_spec(spec).calculate_dynamics(ts, OBS3)
     assert all(np.all(np.isfinite(g)) for g in got)
     assert_close(got, lo.expect_exact(spec, ts, OBS3), TOL, f'repeated times {QD}')
+
+
+@pytest.mark.parametrize('kernel,QD', [('auto', (1, 2)), ('auto', (1, 3)), ('generic', (1, 3)), ('auto', (2, 3))])
+def test_non_finite_parameters_fail_loudly_instead_of_hanging(use_kernel, kernel, QD):
+    from effective_model_learning_b200 import configs, synthetic
+    use_kernel(kernel)
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    lay = synthetic.LibraryLayout(*QD, hyper)
+    ctx = lay.context(np.linspace(0, 2.5, 30), OBS3)
+    good = lay.batch_params(1000 + np.arange(3))
+    bad = good.copy()
+    bad[1, 2] = np.nan
+    with pytest.raises(RuntimeError, match='Taylor cap|not converged|hit'):
+        ctx.evaluate(bad, want_expect=True)
+    huge = good.copy()
+    huge[0, lay.n_library - 1] = 1e9          # a rate of 1e9: nu * span far beyond anything sensible
+    with pytest.raises(RuntimeError):
+        ctx.evaluate(huge, want_expect=True)
+    ex, _ = ctx.evaluate(good, want_expect=True)      # the plan is still usable afterwards
+    assert np.all(np.isfinite(ex))
