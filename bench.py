@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'warp_mma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-chains', action='store_true', help='skip the RJMCMC steps/s measurement')
-    ap.add_argument('--cpu-sample', type=int, default=0, help='models in the CPU-baseline sample (0 = 8 per core)')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='models in the CPU-baseline sample (0 = 64 per core; 16 per core per step in the reference arm)')
     return ap.parse_args()
 
 
@@ -119,7 +119,7 @@ def run_reference(args):
     layout, _ = make_layout(args)
     targets = cpu_targets(args, layout)
     pool = CpuPool()
-    per_step = args.cpu_sample or 8 * pool.cores
+    per_step = args.cpu_sample or 16 * pool.cores      # ~0.3 s of wall clock (5 core-seconds) per step
     per_step = min(per_step, args.chains)
     rows = layout.batch_params(1000 + np.arange(per_step))
     for _ in range(max(1, min(args.warmup, 1))):
@@ -381,7 +381,7 @@ def run_b200(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool = CpuPool()
-        n = args.cpu_sample or 8 * pool.cores
+        n = args.cpu_sample or 64 * pool.cores         # ~20 core-seconds of CPU work
         n = min(n, B)
         rows = params_host[:n]
         tg = [targets[m] for m in range(3)]

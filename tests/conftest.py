@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # the C-ABI library is a build artefact (git-ignored): build it once if this checkout has none yet
+    lib = os.path.join(ROOT, 'effective_model_learning_b200', 'libeml_b200.so')
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu() -> bool:
