@@ -207,6 +207,10 @@ def evaluate_models(models, evaluation_times, obs_names, targets=None, want_expe
     if len(models) == 0:
         raise RuntimeError('no models to evaluate')
     ctx = context_for(models[0], obs_names, evaluation_times, device)
+    for m in models[1:]:
+        if (len(m.TLSs) != ctx.n_tls or first_qubit_site(m) != first_qubit_site(models[0])
+                or any(not np.array_equal(_initial_state_array(t), s) for t, s in zip(m.TLSs, ctx.site_states))):
+            raise RuntimeError('models of one batch must share the number of TLSs, the first qubit and the initial states')
     params = ctx.params_of([model_processes(m) for m in models])
     if targets is not None:
         ctx.set_targets(np.asarray(targets))
