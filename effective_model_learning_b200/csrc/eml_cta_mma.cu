@@ -34,6 +34,8 @@ struct CtaScratch {
 
 #define CUNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
+__constant__ double CTA_INV_TABLE[MCAP + 2];     // 1/(j+1)
+
 __device__ __forceinline__ void dmma_c(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
         : "+d"(d0), "+d"(d1)
@@ -184,11 +186,13 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                 if (REAL_H) x += G_re[(8 * w + g) * LDV + 8 * w + g] + G_re[(8 * J + 2 * t + e) * LDV + 8 * J + 2 * t + e];
                 W0[J][e] = 0.5 * x;
             }
-        const double F4[2] = {0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 0], 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 1]};   // by J>>1
-        const double F3[2] = {0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 0], 0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 1]};     // by J&1
-        const double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
-        const double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
-        const double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        double F4[2] = {0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 0], 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 1]};   // by J>>1
+        double F3[2] = {0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 0], 0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 1]};     // by J&1
+        double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
+        double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
+        double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
+        // the generator is kept pre-multiplied by the current step length (see eml_warp_mma.cu): u_{j+1} = (h L) u_j
+        double h_cur = 1.0;
         __syncthreads();     // G has been consumed: the Vs planes are free for the Taylor terms
 
         // ---- state: this warp's rows of rho(t_k)
@@ -209,11 +213,16 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
 
         // per-warp partial trace of a term into S.trp[w]: diag lanes, tiles J = (w&1) + 2b
         auto partial_trace_store = [&](const double (&xr)[4][2], const double (&xi)[4][2]) {
-            const int J0 = w & 1, J1 = (w & 1) + 2;
-            double v0 = diag_lane ? (gp ? xr[J0][1] : xr[J0][0]) : 0.0;
-            double v1 = diag_lane ? (gp ? xi[J0][1] : xi[J0][0]) : 0.0;
-            double v2 = diag_lane ? (gp ? xr[J1][1] : xr[J1][0]) : 0.0;
-            double v3 = diag_lane ? (gp ? xi[J1][1] : xi[J1][0]) : 0.0;
+            // tiles J = (w&1) and (w&1)+2, selected with predicates (a runtime index would put the arrays in local memory)
+            const bool odd = w & 1;
+            const double ar0 = odd ? xr[1][0] : xr[0][0], ar1 = odd ? xr[1][1] : xr[0][1];
+            const double ai0 = odd ? xi[1][0] : xi[0][0], ai1 = odd ? xi[1][1] : xi[0][1];
+            const double br0 = odd ? xr[3][0] : xr[2][0], br1 = odd ? xr[3][1] : xr[2][1];
+            const double bi0 = odd ? xi[3][0] : xi[2][0], bi1 = odd ? xi[3][1] : xi[2][1];
+            double v0 = diag_lane ? (gp ? ar1 : ar0) : 0.0;
+            double v1 = diag_lane ? (gp ? ai1 : ai0) : 0.0;
+            double v2 = diag_lane ? (gp ? br1 : br0) : 0.0;
+            double v3 = diag_lane ? (gp ? bi1 : bi0) : 0.0;
             const bool up16 = lane & 16;
             double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;
             s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
@@ -268,7 +277,6 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         __syncthreads();
         emit(1, 0, trace_total(), 0.0);
 
-        const unsigned tol_hi = (unsigned)(__double2hiint(P.tol)) & 0x7fffffffu;
         int kidx = 0;
         while (CUNI(kidx < T - 1)) {
             int q, nsub;
@@ -308,10 +316,23 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                 for (int J = 0; J < 4; ++J)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) { v_re[J][e] = acc_re[J][e]; v_im[J][e] = acc_im[J][e]; }
-                double xp0 = 1.0, xp1 = 1.0;
+                if (CUNI(h != h_cur)) {
+                    const double rs = h / h_cur;
+                    h_cur = h;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) { a_re[ks] *= rs; a_im[ks] *= rs; }
+#pragma unroll
+                    for (int J = 0; J < 4; ++J) { W0[J][0] *= rs; W0[J][1] *= rs; }
+                    F4[0] *= rs; F4[1] *= rs; F3[0] *= rs; F3[1] *= rs;
+                    f2 *= rs; f1 *= rs; f0[0] *= rs; f0[1] *= rs;
+                }
+                double xp0 = 1.0, xp1 = 1.0;      // x^j / j!
+                double cfac = 1.0;                // 1 / j!
+                double thr = P.tol;               // tol * j!
                 if (last) { y0 = 0.0; y1 = 0.0; }
                 int small = 0;
                 unsigned mx_term = 0x7fffffffu;     // size of the term about to be published (term 0: the state itself)
+                unsigned thr_term = 0;
                 int j = 0;
                 for (;; ++j) {
                     // ---- [A] publish term j: rows of this warp into Vs, partial trace, size
@@ -327,10 +348,11 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                         const double tr = trace_total();
                         y0 = fma(xp0, tr, y0);
                         y1 = fma(xp1, tr, y1);
-                        xp0 *= xs0; xp1 *= xs1;
+                        const double inv = CTA_INV_TABLE[j];
+                        xp0 *= xs0 * inv; xp1 *= xs1 * inv;
                     }
                     const unsigned mx = max(max(S.mxs[0], S.mxs[1]), max(S.mxs[2], S.mxs[3]));
-                    small = (mx <= tol_hi) ? small + 1 : 0;
+                    small = (mx <= thr_term) ? small + 1 : 0;
                     if (CUNI(small >= 2 || j >= MCAP)) break;   // uniform over the CTA (values read from shared memory)
 
                     // ---- [B] accumulators = J(v)/2 (all five site stencils read from Vs), then += G v on the DMMA pipe
@@ -400,17 +422,20 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                     __syncthreads();
 
                     // ---- [C] next term = f (X' + X'^dag):  X'^dag[8w+g][8J+2t+e] = conj(X'[8J+2t+e][8w+g])
-                    const double f = h / (double)(j + 1);
+                    cfac *= CTA_INV_TABLE[j];
+                    thr *= (double)(j + 1);
+                    thr_term = (unsigned)__double2hiint(thr) & 0x7fffffffu;
                     unsigned mxl = 0;
 #pragma unroll
                     for (int J = 0; J < 4; ++J) {
                         const int o = (8 * w + g) * LDX + 8 * J + 2 * t;
                         const double2 tr_ = *reinterpret_cast<const double2*>(&S.Xs_re[o]);
                         const double2 ti_ = *reinterpret_cast<const double2*>(&S.Xs_im[o]);
-                        const double wr0 = (x_re[J][0] + tr_.x) * f, wr1 = (x_re[J][1] + tr_.y) * f;
-                        const double wi0 = (x_im[J][0] - ti_.x) * f, wi1 = (x_im[J][1] - ti_.y) * f;
+                        const double wr0 = x_re[J][0] + tr_.x, wr1 = x_re[J][1] + tr_.y;
+                        const double wi0 = x_im[J][0] - ti_.x, wi1 = x_im[J][1] - ti_.y;
                         v_re[J][0] = wr0; v_re[J][1] = wr1; v_im[J][0] = wi0; v_im[J][1] = wi1;
-                        acc_re[J][0] += wr0; acc_re[J][1] += wr1; acc_im[J][0] += wi0; acc_im[J][1] += wi1;
+                        acc_re[J][0] = fma(cfac, wr0, acc_re[J][0]); acc_re[J][1] = fma(cfac, wr1, acc_re[J][1]);
+                        acc_im[J][0] = fma(cfac, wi0, acc_im[J][0]); acc_im[J][1] = fma(cfac, wi1, acc_im[J][1]);
                         mxl = max(mxl, (unsigned)__double2hiint(wr0) & 0x7fffffffu);
                         mxl = max(mxl, (unsigned)__double2hiint(wr1) & 0x7fffffffu);
                         mxl = max(mxl, (unsigned)__double2hiint(wi0) & 0x7fffffffu);
@@ -452,6 +477,15 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    {
+        static bool done[64] = {false};
+        if (dev >= 64 || !done[dev]) {
+            double hinv[MCAP + 2];
+            for (int j = 0; j < MCAP + 2; ++j) hinv[j] = 1.0 / (double)(j + 1);
+            if ((e = cudaMemcpyToSymbol(CTA_INV_TABLE, hinv, sizeof(hinv))) != cudaSuccess) return e;
+            if (dev < 64) done[dev] = true;
+        }
+    }
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 2LL * sms && n_models <= (1 << 18)) {
