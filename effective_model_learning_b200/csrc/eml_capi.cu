@@ -241,7 +241,12 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
 
 // internal entry point: eml_eval_batch plus an optional measured cost per model for the longest-first ordering
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
-                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint) {
+                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,
+                          int* order_ws) {
+    // counter_ws / order_ws: caller-owned work-fetch counter and ordering buffer (2 * 2^18 ints), so that several
+    // evaluations of one plan can be in flight on different streams; NULL = the plan's own
+    unsigned int* const counter = counter_ws ? counter_ws : plan->d_counter;
+    int* const order = counter_ws ? order_ws : plan->d_order;
     if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
     if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
     if (n_models == 0) return EML_OK;
@@ -252,10 +257,10 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA)
-        e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order, plan->real_h,
+        e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
                                  cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA)
-        e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, plan->d_counter, plan->d_order,
+        e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
                                 plan->real_h, cost_hint, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
@@ -269,7 +274,7 @@ extern "C" {
 
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                    double* loss, int32_t* status, void* stream) {
-    return eml_eval_batch_hinted(plan, n_models, params, target_set, expect, loss, status, stream, nullptr);
+    return eml_eval_batch_hinted(plan, n_models, params, target_set, expect, loss, status, stream, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"

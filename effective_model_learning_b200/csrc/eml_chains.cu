@@ -126,10 +126,10 @@ __device__ inline double xi_product(const ChainHyperDev& H, const double* row, c
     return out;
 }
 
-__global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
+__global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo, const long long c_hi,
                                       const unsigned long long seed, const long long first_chain) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chains) return;
+    const long long c = c_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_hi) return;
     const int P = H.n_params;
     double* cur = S.cur + c * P;
     double* prop = S.prop + c * P;
@@ -230,11 +230,11 @@ __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S,
     S.rng_ctr[c] = rng.ctr;
 }
 
-__global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains,
+__global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo, const long long c_hi,
                                      const unsigned long long seed, const long long first_chain, double* hist_loss,
                                      double* hist_aprob, int* hist_code) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chains) return;
+    const long long c = c_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_hi) return;
     const int P = H.n_params;
     Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
     const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
@@ -303,6 +303,14 @@ struct EmlChains {
     std::vector<void*> owned;
     int* d_target_set = nullptr;
     int* d_status = nullptr;
+    // Large batches advance as two independent groups of chains on two streams: while the last (shortest) models
+    // of one group's evaluation finish, the other group's next evaluation already fills the idle SMs.
+    int n_groups = 1;
+    long long group_lo[2] = {0, 0}, group_hi[2] = {0, 0};
+    cudaStream_t gstream[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    unsigned int* g_counter[2] = {nullptr, nullptr};
+    int* g_order[2] = {nullptr, nullptr};
 };
 
 template <typename T>
@@ -321,6 +329,11 @@ int eml_chains_destroy(EmlChains* ch) {
     cudaSetDevice(ch->plan->device);
     cudaDeviceSynchronize();
     for (void* p : ch->owned) cudaFree(p);
+    for (int g = 0; g < 2; ++g) {
+        if (ch->gstream[g]) cudaStreamDestroy(ch->gstream[g]);
+        if (ch->join[g]) cudaEventDestroy(ch->join[g]);
+    }
+    if (ch->fork) cudaEventDestroy(ch->fork);
     delete ch;
     return EML_OK;
 }
@@ -376,6 +389,20 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     if (cudaMemcpy(S.cur, initial_params, sizeof(double) * C * P, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy initial params"); }
     // loss of the initial models (LearningChain.__init__, learning_chain.py:298)
     CH_TRY(eml_eval_batch(plan, n_chains, S.cur, ch->d_target_set, nullptr, S.prop_loss, ch->d_status, nullptr));
+    // groups: two halves when every half still has several models per resident warp
+    ch->n_groups = (n_chains >= 2048) ? 2 : 1;
+    for (int g = 0; g < ch->n_groups; ++g) {
+        ch->group_lo[g] = g * n_chains / ch->n_groups;
+        ch->group_hi[g] = (g + 1) * n_chains / ch->n_groups;
+        CH_TRY(dalloc(ch, &ch->g_counter[g], 1));
+        CH_TRY(dalloc(ch, &ch->g_order[g], (size_t)2 * (1 << 18)));
+        if (cudaStreamCreateWithFlags(&ch->gstream[g], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ch->join[g], cudaEventDisableTiming) != cudaSuccess) {
+            eml_chains_destroy(ch);
+            return fail(EML_ERR_CUDA, "chains: stream/event creation failed");
+        }
+    }
+    if (cudaEventCreateWithFlags(&ch->fork, cudaEventDisableTiming) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "chains: event creation failed"); }
     const unsigned blocks = (unsigned)((n_chains + 127) / 128);
     eml::chains_init_kernel<<<blocks, 128>>>(H, S, n_chains);
     cudaError_t e = cudaDeviceSynchronize();
@@ -389,17 +416,32 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
     if (n_steps < 0) return fail(EML_ERR_INVALID_ARGUMENT, "n_steps < 0");
     EML_CUDA(cudaSetDevice(ch->plan->device));
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned blocks = (unsigned)((ch->n + 127) / 128);
+    // fork: the group streams start after everything already queued on the caller's stream
+    EML_CUDA(cudaEventRecord(ch->fork, s));
+    for (int g = 0; g < ch->n_groups; ++g) EML_CUDA(cudaStreamWaitEvent(ch->gstream[g], ch->fork, 0));
     for (int64_t i = 0; i < n_steps; ++i) {
-        eml::chains_propose_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain);
-        // the generator applications each chain's previous proposal needed order this step's models (longest first)
-        int rc = eml_eval_batch_hinted(ch->plan, ch->n, ch->S.prop, ch->d_target_set, nullptr, ch->S.prop_loss, ch->d_status, s,
-                                       ch->d_status);
-        if (rc != EML_OK) return rc;
-        eml::chains_accept_kernel<<<blocks, 128, 0, s>>>(ch->H, ch->S, ch->n, ch->seed, ch->first_chain,
-                                                        hist_loss ? hist_loss + i * ch->n : nullptr,
-                                                        hist_aprob ? hist_aprob + i * ch->n : nullptr,
-                                                        hist_code ? hist_code + i * ch->n : nullptr);
+        for (int g = 0; g < ch->n_groups; ++g) {
+            const long long lo = ch->group_lo[g], hi = ch->group_hi[g], cnt = hi - lo;
+            if (cnt <= 0) continue;
+            cudaStream_t gs = ch->gstream[g];
+            const unsigned blocks = (unsigned)((cnt + 127) / 128);
+            const int P = ch->H.n_params;
+            eml::chains_propose_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            // the generator applications each chain's previous proposal needed order this step's models (longest first)
+            int rc = eml_eval_batch_hinted(ch->plan, cnt, ch->S.prop + lo * P, ch->d_target_set ? ch->d_target_set + lo : nullptr,
+                                           nullptr, ch->S.prop_loss + lo, ch->d_status + lo, gs, ch->d_status + lo,
+                                           ch->g_counter[g], ch->g_order[g]);
+            if (rc != EML_OK) return rc;
+            eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain,
+                                                             hist_loss ? hist_loss + i * ch->n : nullptr,
+                                                             hist_aprob ? hist_aprob + i * ch->n : nullptr,
+                                                             hist_code ? hist_code + i * ch->n : nullptr);
+        }
+    }
+    // join: the caller's stream continues after both groups are done
+    for (int g = 0; g < ch->n_groups; ++g) {
+        EML_CUDA(cudaEventRecord(ch->join[g], ch->gstream[g]));
+        EML_CUDA(cudaStreamWaitEvent(s, ch->join[g], 0));
     }
     EML_CUDA(cudaGetLastError());
     return EML_OK;

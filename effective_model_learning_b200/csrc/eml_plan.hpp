@@ -39,4 +39,5 @@ struct EmlPlan {
 };
 
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
-                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint);
+                          double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,
+                          int* order_ws);

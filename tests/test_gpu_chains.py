@@ -104,3 +104,19 @@ def test_results_do_not_depend_on_how_chains_are_split_over_engines():
         eng.close()
     for key in ('current_params', 'best_loss', 'stats'):
         assert np.array_equal(a[key], np.concatenate([p[key] for p in parts]))
+
+
+def test_two_group_pipelining_gives_the_same_chains():
+    """>= 2048 chains advance as two groups on two streams; the result must equal two single-group engines."""
+    cfg, ts, targets, whole = _setup(1, 2304)
+    whole.run(12)
+    a = whole.read()
+    whole.close()
+    parts = []
+    for lo_, hi_ in ((0, 1000), (1000, 2304)):
+        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=1, seed=1234, first_chain=lo_, **cfg)
+        eng.run(12)
+        parts.append(eng.read())
+        eng.close()
+    for key in ('current_params', 'current_loss', 'best_loss', 'stats'):
+        assert np.array_equal(a[key], np.concatenate([p[key] for p in parts])), key
