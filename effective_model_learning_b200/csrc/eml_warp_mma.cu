@@ -41,6 +41,7 @@ struct WarpScratch {
     double jw[32];      // [bitpos][type(0 diag,1 flip)][ra][ca]
     double colsum[16];
     double misc[4];
+    double xt_re[256], xt_im[256];   // X' staged column-major (swizzled) for the conjugate transpose
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -128,7 +129,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
-    __shared__ WarpScratch scratch_all[WARPS_PER_CTA];
+    __shared__ __align__(16) WarpScratch scratch_all[WARPS_PER_CTA];
     WarpScratch& S = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -539,11 +540,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     thr *= (double)(j + 1);
                     unsigned mx = 0;
                     double w_re[TL][TL][2], w_im[TL][TL][2];
+                    if constexpr (TL == 2) {     // d = 16: shuffles (measured 1 % faster than the shared-memory route)
 #pragma unroll
                     for (int I = 0; I < TL; ++I)
 #pragma unroll
                         for (int J = 0; J < TL; ++J) {
-                            // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I)
+                            // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I) with shuffles
                             const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
                             const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
                             const double rAr = shfl(sAr, srcA), rBr = shfl(sBr, srcB);
@@ -559,6 +561,40 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                 mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
                             }
                         }
+                    } else {                     // d = 8: issue-bound, the shared-memory route saves ~90 instructions (+5 %)
+                    // X'^dag through shared memory: element (R, C) of X' is stored at C*16 + (R ^ m(C)) with the swizzle
+                    // m(C) = 4*bit1(C) + 8*(bit2(C) ^ bit0(C)), which makes both the STS.64 of the accumulator
+                    // fragments and the LDS.128 of the transposed pairs bank-conflict free.
+#pragma unroll
+                    for (int I = 0; I < TL; ++I)
+#pragma unroll
+                        for (int J = 0; J < TL; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int Cc = 8 * J + 2 * t + e;
+                                const int m = 4 * (t & 1) + 8 * (((t >> 1) & 1) ^ e);
+                                S.xt_re[Cc * 16 + ((8 * I + g) ^ m)] = x_re[I][J][e];
+                                S.xt_im[Cc * 16 + ((8 * I + g) ^ m)] = x_im[I][J][e];
+                            }
+                    __syncwarp();
+#pragma unroll
+                    for (int I = 0; I < TL; ++I)
+#pragma unroll
+                        for (int J = 0; J < TL; ++J) {
+                            const int m = 4 * ((g >> 1) & 1) + 8 * (((g >> 2) & 1) ^ (g & 1));
+                            const int o = (8 * I + g) * 16 + ((8 * J + 2 * t) ^ m);
+                            const double2 tr_ = *reinterpret_cast<const double2*>(&S.xt_re[o]);
+                            const double2 ti_ = *reinterpret_cast<const double2*>(&S.xt_im[o]);
+                            const double wr0 = x_re[I][J][0] + tr_.x, wr1 = x_re[I][J][1] + tr_.y;
+                            const double wi0 = x_im[I][J][0] - ti_.x, wi1 = x_im[I][J][1] - ti_.y;
+                            w_re[I][J][0] = wr0; w_re[I][J][1] = wr1; w_im[I][J][0] = wi0; w_im[I][J][1] = wi1;
+                            mx = max(mx, (unsigned)__double2hiint(wr0) & 0x7fffffffu);
+                            mx = max(mx, (unsigned)__double2hiint(wr1) & 0x7fffffffu);
+                            mx = max(mx, (unsigned)__double2hiint(wi0) & 0x7fffffffu);
+                            mx = max(mx, (unsigned)__double2hiint(wi1) & 0x7fffffffu);
+                        }
+                    __syncwarp();
+                    }
 #pragma unroll
                     for (int I = 0; I < TL; ++I)
 #pragma unroll
