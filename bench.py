@@ -135,7 +135,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'model evaluations/sec (4-TLS, d=16)' if (args.qubits, args.defects) == (1, 3)
         else 'model evaluations/sec', 'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t_total / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (complex128)', 'data': 'synthetic',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'algorithm': 'emulated qutip 4.7.5 mesolve: CSR Liouvillian + '
                    'scipy ZVODE adams/12 atol 1e-8 rtol 1e-6, one OS process per core (qutip itself is not installable)'},
         'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': pool.cores, 'kind': 'port', 'sample': sample},
@@ -335,7 +335,7 @@ def run_b200(args):
         'metric': 'model evaluations/sec (4-TLS, d=16)' if (args.qubits, args.defects) == (1, 3) else 'model evaluations/sec',
         'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 (complex128)', 'data': 'synthetic',
+        'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'kernel': plan.kernel_name,
                    'algorithm': 'Taylor action on the d x d density matrix with dense output (DESIGN.md section 4)',
                    'l2': 'flushed between iterations (256 MB memset); inputs are 1.1 MB per step',
