@@ -7,7 +7,7 @@
 namespace eml {
 
 constexpr int QMAX = 16;   // output times covered by one Taylor expansion (dense output)
-constexpr int MCAP = 64;   // hard cap on Taylor terms per expansion (theta <= 12 converges to 1e-15 by 57)
+constexpr int MCAP = 80;   // hard cap on Taylor terms per expansion (theta <= 16 with a tight norm bound needs ~66)
 constexpr int MAX_OBS = 8;
 
 // Device-resident constants of a plan; passed to kernels by value.
