@@ -130,7 +130,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     P.n_tls = d->n_tls; P.n_params = d->n_params; P.n_terms = d->n_terms; P.n_obs = d->n_obs;
     P.n_times = d->n_times; P.n_target_sets = 0; P.obs_site = d->obs_site;
     P.theta_target = (opts && opts->theta_target > 0) ? opts->theta_target : 16.0;
-    P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-12;
+    P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-11;
     if (P.theta_target > 16.0) P.theta_target = 16.0;  // MCAP = 80 terms converge below 1e-15 for theta <= 16
     const int dd = 1 << (2 * d->n_tls);
     int rc;

@@ -90,7 +90,7 @@ typedef struct EmlPlan EmlPlan; /* opaque */
 /* Tunables of the evaluator (0 / negative = keep default). */
 typedef struct EmlOptions {
     double theta_target; /* norm-bound * step targeted per Taylor expansion (default and maximum 16) */
-    double tol;          /* absolute per-element stopping tolerance (default 1e-12) */
+    double tol;          /* absolute per-element stopping tolerance (default 1e-11) */
     int32_t kernel;      /* EML_KERNEL_AUTO or a specific kernel, for tests/benchmarks */
     int32_t reserved;
 } EmlOptions;

@@ -38,7 +38,7 @@ def norm_bound(G, Gt, c_ops):
     return nb
 
 
-def evaluate(H, c_ops, rho0, obs, times, theta_target=16.0, m_cap=80, tol=1e-12, q_max=16):
+def evaluate(H, c_ops, rho0, obs, times, theta_target=16.0, m_cap=80, tol=1e-11, q_max=16):
     """Returns expect (K,T complex), number of L applications."""
     times = np.asarray(times, float)
     T = len(times)
