@@ -23,7 +23,8 @@
 
 namespace eml {
 
-constexpr int WQ = 16;          // outputs per expansion (two per lane: p = lane&7 and (lane&7)+8)
+// outputs per expansion: NY per lane (p = (lane&7) + 8n); d = 16 has registers for 2 (16 outputs), d = 8 for 4
+// (32 outputs -- small models have small nu * dt, so long expansions need many outputs to reach theta)
 #ifndef EML_WARPS_PER_CTA
 #define EML_WARPS_PER_CTA 4
 #endif
@@ -124,11 +125,12 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
 }
 
 template <int TL, bool REAL_H>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 5 : CTAS_PER_SM)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
+    constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
     __shared__ __align__(16) WarpScratch scratch_all[WARPS_PER_CTA];
     WarpScratch& S = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -347,16 +349,25 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             return k;   // value index = 2*bit4 + bit3 = lane >> 3
         };
 
-        // emit q outputs starting at time index kbase; y0/y1 are this lane's accumulators for outputs
-        // p = lane&7 and (lane&7)+8 of value index lane>>3
-        auto emit = [&](int q, int kbase, double y0, double y1) {
-            const int p = lane;   // lane p < q finalises output p
+        // emit q outputs starting at time index kbase; y[n] is this lane's accumulator for output
+        // p = (lane&7) + 8n of value index lane>>3.  Lane l finalises outputs l, l + 32, ...
+        auto emit = [&](int q, int kbase, const double (&y)[NY]) {
+          for (int pbase = 0; UNI(pbase < q); pbase += 32) {
+            const int p = pbase + lane;
             const int srcl = p & 7;
             double r[4];
 #pragma unroll
             for (int vi = 0; vi < 4; ++vi) {
-                const double lo = shfl(y0, vi * 8 + srcl), hi = shfl(y1, vi * 8 + srcl);
-                r[vi] = (p & 8) ? hi : lo;
+                double val = 0.0;
+#pragma unroll
+                for (int n = 0; n < NY; ++n) {
+                    // the source lane vi*8 + srcl holds output 8n + srcl in y[n]; this lane wants n == p >> 3
+                    if ((n >> 2) == (pbase >> 5)) {      // outputs of this 32-block live in y[4*(pbase/32) .. +3]
+                        const double got = shfl(y[n], vi * 8 + srcl);
+                        if (n == (p >> 3)) val = got;
+                    }
+                }
+                r[vi] = val;
             }
             if (p < q) {
                 const int k = kbase + p;
@@ -375,11 +386,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                 }
             }
+          }
         };
 
         {
             const double v = partial_trace(acc_re, acc_im);
-            emit(1, 0, v, 0.0);
+            double y1st[NY];
+#pragma unroll
+            for (int n = 0; n < NY; ++n) y1st[n] = v;
+            emit(1, 0, y1st);
         }
 
         int kidx = 0;
@@ -400,16 +415,22 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             }
             if (UNI(htot == 0.0)) {      // repeated time points: the state does not move
                 const double tr = partial_trace(acc_re, acc_im);
-                emit(q, kidx + 1, tr, tr);
+                double yz[NY];
+#pragma unroll
+                for (int n = 0; n < NY; ++n) yz[n] = tr;
+                emit(q, kidx + 1, yz);
                 kidx += q;
                 continue;
             }
             const double h = htot / nsub;
             const double t0 = P.times[kidx];
-            const int p0 = lane & 7, p1 = p0 + 8;
-            const double xs0 = (p0 < q) ? ((nsub == 1) ? (P.times[kidx + 1 + p0] - t0) / htot : 1.0) : 0.0;
-            const double xs1 = (p1 < q) ? (P.times[kidx + 1 + p1] - t0) / htot : 0.0;
-            double y0 = 0.0, y1 = 0.0;
+            double xs[NY], y[NY];
+#pragma unroll
+            for (int n = 0; n < NY; ++n) {
+                const int p = (lane & 7) + 8 * n;
+                xs[n] = (p < q) ? ((nsub == 1) ? (P.times[kidx + 1 + p] - t0) / htot : 1.0) : 0.0;
+                y[n] = 0.0;
+            }
 
             for (int sub = 0; UNI(sub < nsub); ++sub) {
                 const bool last = (sub == nsub - 1);
@@ -435,10 +456,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                     f2 *= rs; f1 *= rs; f0[0] *= rs; f0[1] *= rs;
                 }
-                double xp0 = 1.0, xp1 = 1.0;      // x^j / j! for this lane's two outputs
+                double xp[NY];                    // x^j / j! for this lane's outputs
+#pragma unroll
+                for (int n = 0; n < NY; ++n) xp[n] = 1.0;
                 double cfac = 1.0;                // 1 / j!
                 double thr = P.tol;               // tol * j!: |u_j| <= thr  <=>  |term_j| <= tol
-                if (last) { y0 = 0.0; y1 = 0.0; }
+                if (last) {
+#pragma unroll
+                    for (int n = 0; n < NY; ++n) y[n] = 0.0;
+                }
                 int small = 0;
                 int j = 0;
                 for (; UNI(j < MCAP); ++j) {
@@ -446,10 +472,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     //      (independent of the DMMAs below, so the shuffles overlap with them)
                     {
                         const double tr = partial_trace(v_re, v_im);
-                        y0 = fma(xp0, tr, y0);
-                        y1 = fma(xp1, tr, y1);
                         const double inv = INV_TABLE[j];
-                        xp0 *= xs0 * inv; xp1 *= xs1 * inv;
+#pragma unroll
+                        for (int n = 0; n < NY; ++n) {
+                            y[n] = fma(xp[n], tr, y[n]);
+                            xp[n] *= xs[n] * inv;
+                        }
                     }
                     // ---- accumulators start from J(v)/2: real-weighted site stencils (depend only on v)
                     double x_re[TL][TL][2], x_im[TL][TL][2];
@@ -611,13 +639,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 }
                 {   // the final term computed above has not been traced yet
                     const double tr = partial_trace(v_re, v_im);
-                    y0 = fma(xp0, tr, y0);
-                    y1 = fma(xp1, tr, y1);
+#pragma unroll
+                    for (int n = 0; n < NY; ++n) y[n] = fma(xp[n], tr, y[n]);
                 }
                 n_apply += j;
                 if (j >= MCAP && small < 2) capped = true;
             }
-            emit(q, kidx + 1, y0, y1);
+            emit(q, kidx + 1, y);
             kidx += q;
         }
 
