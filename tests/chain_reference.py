@@ -51,6 +51,26 @@ class Rng:
         return math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * u2)
 
 
+def rng_gamma(rng, shape, scale):
+    """Marsaglia-Tsang, the same draw order as Rng::gamma in csrc/eml_chains.cu."""
+    boost = 1.0
+    if shape < 1.0:
+        boost = rng.uniform() ** (1.0 / shape)
+        shape += 1.0
+    d = shape - 1.0 / 3.0
+    c = 1.0 / math.sqrt(9.0 * d)
+    for _ in range(64):
+        x = rng.normal()
+        v = 1.0 + c * x
+        if v <= 0.0:
+            continue
+        v = v * v * v
+        u = rng.uniform()
+        if math.log(u) < 0.5 * x * x + d - d * v + d * math.log(v):
+            return boost * d * v * scale
+    return boost * d * scale
+
+
 def Phi(y):
     return 0.5 * (1.0 + math.erf(y / math.sqrt(2.0)))
 
@@ -109,7 +129,8 @@ class ReferenceChain:
             self.step_i += 1
             self.cur, self.cur_loss = self.best.copy(), self.best_loss
             self.tracker.append(True)
-        self.T = cfg['temperature_proposal']
+        tp = cfg['temperature_proposal']
+        self.T = rng_gamma(rng, tp[0], tp[1]) if isinstance(tp, (tuple, list)) else tp
         w = cfg['acceptance_window']
         if self.k >= w:
             self.k = 0

@@ -11,11 +11,11 @@ from tests.helpers import OBS3
 pytestmark = pytest.mark.gpu
 
 
-def _setup(D, n_chains, steps_cfg=None):
+def _setup(D, n_chains, steps_cfg=None, temperature=0.002):
     cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
     cfg['shock_anneal_at'] = 40
     cfg['jump_length_rescaling_factor'] = 1.3
-    cfg['temperature_proposal'] = 0.002
+    cfg['temperature_proposal'] = temperature
     if steps_cfg:
         cfg['chain_step_options'] = steps_cfg
     ts = np.linspace(0, 2.5, 60)
@@ -26,10 +26,11 @@ def _setup(D, n_chains, steps_cfg=None):
     return cfg, ts, targets, eng
 
 
-@pytest.mark.parametrize('D', [2, 3])
-def test_engine_matches_python_reference_step_by_step(D):
+@pytest.mark.parametrize('D,temperature', [(2, 0.002), (3, 0.002), (1, (2.0, 0.001)), (2, (0.7, 0.004))])
+def test_engine_matches_python_reference_step_by_step(D, temperature):
+    """Fixed temperature and gamma-sampled temperature (shape >= 1 and the shape < 1 boost branch)."""
     n_chains, steps = 6, 90
-    cfg, ts, targets, eng = _setup(D, n_chains, {m: (6 if m == MOVES[0] else 1) for m in MOVES})
+    cfg, ts, targets, eng = _setup(D, n_chains, {m: (6 if m == MOVES[0] else 1) for m in MOVES}, temperature)
     state = eng.read()
     hyper = eng.hyperparameters
     refs = [ReferenceChain(eng.layout, hyper, cfg, state['current_params'][c], state['current_loss'][c], 1234, c)
