@@ -87,7 +87,7 @@ def load():
         lib.eml_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, dp]
         lib.eml_chains_create.argtypes = [vp, C.POINTER(EmlChainHyper), C.c_int64, dp, ip, C.c_uint64, C.c_int64, C.POINTER(vp)]
         lib.eml_chains_destroy.argtypes = [vp]
-        lib.eml_chains_run.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+        lib.eml_chains_run.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
         lib.eml_chains_read.argtypes = [vp, dp, dp, dp, dp, dp]
         lib.eml_chains_stats_device.argtypes = [vp]
         lib.eml_chains_stats_device.restype = vp

@@ -118,11 +118,18 @@ class BatchedChains:
         self.steps_done = 0
 
     def run(self, steps: int, history=None, stream: int = 0):
-        """`steps` proposals per chain (asynchronous).  history: dict of torch CUDA tensors 'loss','aprob' [steps][C] f64, 'code' int32."""
-        hl = ha = hc = None
+        """
+        `steps` proposals per chain (asynchronous).  history: dict of torch CUDA tensors, any of
+        'loss', 'aprob' [steps][C] float64, 'code' [steps][C] int32 (move << 1 | accepted),
+        'params' [steps][C][P] float64 (current model after each step; accepted models = rows with code & 1).
+        """
+        ptr = {k: None for k in ('loss', 'aprob', 'code', 'params')}
         if history is not None:
-            hl, ha, hc = (history[k].data_ptr() for k in ('loss', 'aprob', 'code'))
-        _native.check(self._lib.eml_chains_run(self._h, int(steps), C.c_void_p(hl), C.c_void_p(ha), C.c_void_p(hc),
+            for k in ptr:
+                if k in history:
+                    ptr[k] = history[k].data_ptr()
+        _native.check(self._lib.eml_chains_run(self._h, int(steps), C.c_void_p(ptr['loss']), C.c_void_p(ptr['aprob']),
+                                               C.c_void_p(ptr['code']), C.c_void_p(ptr['params']),
                                                C.c_void_p(stream or None)), 'eml_chains_run')
         self.steps_done += int(steps)
 

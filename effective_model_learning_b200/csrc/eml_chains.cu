@@ -232,7 +232,7 @@ __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S,
 
 __global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo, const long long c_hi,
                                      const unsigned long long seed, const long long first_chain, double* hist_loss,
-                                     double* hist_aprob, int* hist_code) {
+                                     double* hist_aprob, int* hist_code, double* hist_params) {
     const long long c = c_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_hi) return;
     const int P = H.n_params;
@@ -256,6 +256,8 @@ __global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, 
     if (hist_loss) hist_loss[c] = Lp;
     if (hist_aprob) hist_aprob[c] = a;
     if (hist_code) hist_code[c] = (mv << 1) | (accept ? 1 : 0);
+    if (hist_params)
+        for (int p = 0; p < P; ++p) hist_params[c * P + p] = S.cur[c * P + p];
     // statistics record for the checkpoint all_gather
     int n_proc = 0;
     for (int p = 0; p < P; ++p) {
@@ -411,7 +413,8 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     return EML_OK;
 }
 
-int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hist_aprob, int32_t* hist_code, void* stream) {
+int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hist_aprob, int32_t* hist_code,
+                   double* hist_params, void* stream) {
     if (!ch) return fail(EML_ERR_INVALID_ARGUMENT, "chains is NULL");
     if (n_steps < 0) return fail(EML_ERR_INVALID_ARGUMENT, "n_steps < 0");
     EML_CUDA(cudaSetDevice(ch->plan->device));
@@ -435,7 +438,8 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
             eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain,
                                                              hist_loss ? hist_loss + i * ch->n : nullptr,
                                                              hist_aprob ? hist_aprob + i * ch->n : nullptr,
-                                                             hist_code ? hist_code + i * ch->n : nullptr);
+                                                             hist_code ? hist_code + i * ch->n : nullptr,
+                                                             hist_params ? hist_params + i * ch->n * P : nullptr);
         }
     }
     // join: the caller's stream continues after both groups are done

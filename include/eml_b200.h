@@ -183,9 +183,11 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* hyper, int64_t n_chain
                       const int32_t* target_set, uint64_t seed, int64_t first_chain, EmlChains** out);
 int eml_chains_destroy(EmlChains* chains);
 /* n_steps proposals per chain, asynchronous on `stream`.  Optional DEVICE history buffers [n_steps][n_chains]:
- * proposal loss, acceptance probability, code = move << 1 | accepted. */
+ * proposal loss, acceptance probability, code = move << 1 | accepted; and hist_params [n_steps][n_chains][P]:
+ * the chain's current parameter vector after the step (the accepted models the reference keeps in
+ * explored_proposals, learning_chain.py:585-586, are the rows whose code has bit 0 set). */
 int eml_chains_run(EmlChains* chains, int64_t n_steps, double* hist_loss, double* hist_aprob, int32_t* hist_code,
-                   void* stream);
+                   double* hist_params, void* stream);
 /* Synchronises and copies the chain state to HOST arrays (any may be NULL):
  * current/best params [n_chains][P], current/best loss [n_chains], stats [n_chains][EML_CHAIN_STATS]. */
 int eml_chains_read(EmlChains* chains, double* current_params, double* current_loss, double* best_params,

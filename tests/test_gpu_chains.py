@@ -37,7 +37,8 @@ def test_engine_matches_python_reference_step_by_step(D, temperature):
             for c in range(n_chains)]
     hist = {'loss': torch.zeros((1, n_chains), dtype=torch.float64, device='cuda'),
             'aprob': torch.zeros((1, n_chains), dtype=torch.float64, device='cuda'),
-            'code': torch.zeros((1, n_chains), dtype=torch.int32, device='cuda')}
+            'code': torch.zeros((1, n_chains), dtype=torch.int32, device='cuda'),
+            'params': torch.zeros((1, n_chains, eng.layout.n_params), dtype=torch.float64, device='cuda')}
     seen = set()
     for s in range(steps):
         props = np.stack([r.propose() for r in refs])
@@ -45,6 +46,7 @@ def test_engine_matches_python_reference_step_by_step(D, temperature):
         eng.run(1, history=hist)
         state = eng.read()
         code = hist['code'].cpu().numpy()[0]
+        assert np.array_equal(hist['params'].cpu().numpy()[0], state['current_params'])
         np.testing.assert_allclose(hist['loss'].cpu().numpy()[0], ref_loss, rtol=1e-9, atol=1e-14,
                                    err_msg=f'step {s}: the engine evaluated a different proposal')
         for c, r in enumerate(refs):
