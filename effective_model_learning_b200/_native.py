@@ -24,7 +24,8 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA, KERNEL_CTA_MMA = 0, 1, 2, 3
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
            'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count',
            'eml_plan_kernel_name', 'eml_measure_fp64_peak', 'eml_chains_create', 'eml_chains_destroy',
-           'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device')
+           'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device', 'eml_chains_state_bytes',
+           'eml_chains_export', 'eml_chains_import')
 CHAIN_STATS = 8
 COL_DEFECT_ENERGY, COL_Q2D_COUPLING, COL_D2D_COUPLING, COL_QUBIT_L, COL_DEFECT_L, COL_FIXED = range(6)
 
@@ -91,6 +92,10 @@ def load():
         lib.eml_chains_read.argtypes = [vp, dp, dp, dp, dp, dp]
         lib.eml_chains_stats_device.argtypes = [vp]
         lib.eml_chains_stats_device.restype = vp
+        lib.eml_chains_state_bytes.argtypes = [vp]
+        lib.eml_chains_state_bytes.restype = C.c_size_t
+        lib.eml_chains_export.argtypes = [vp, vp]
+        lib.eml_chains_import.argtypes = [vp, vp]
         _lib = lib
     return _lib
 

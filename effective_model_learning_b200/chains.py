@@ -150,6 +150,19 @@ class BatchedChains:
         stats = self.read()['stats']
         return dist.gather_chain_stats(stats, n_chains_global if n_chains_global is not None else self.n_chains)
 
+    def export_state(self) -> bytes:
+        """Complete chain state as an opaque blob (checkpoint); see import_state."""
+        n = self._lib.eml_chains_state_bytes(self._h)
+        buf = C.create_string_buffer(n)
+        _native.check(self._lib.eml_chains_export(self._h, buf), 'eml_chains_export')
+        return buf.raw
+
+    def import_state(self, blob: bytes):
+        """Resume from a blob exported by an engine with the same layout, hyperparameters, n_chains and first_chain."""
+        if len(blob) != self._lib.eml_chains_state_bytes(self._h):
+            raise RuntimeError('checkpoint size does not match this engine')
+        _native.check(self._lib.eml_chains_import(self._h, C.c_char_p(blob)), 'eml_chains_import')
+
     def best_models(self, which=None):
         """LearningModel objects of the best model of each chain (or of the chains listed in `which`)."""
         state = self.read()

@@ -466,4 +466,52 @@ int eml_chains_read(EmlChains* ch, double* current_params, double* current_loss,
 
 const double* eml_chains_stats_device(EmlChains* ch) { return ch ? ch->S.stats : nullptr; }
 
+// ---- checkpoint / resume: every per-chain array, in a fixed order
+struct Segment { void* ptr; size_t bytes; };
+static std::vector<Segment> state_segments(const EmlChains* ch) {
+    const size_t C = (size_t)ch->n, P = (size_t)ch->H.n_params;
+    const eml::ChainState& S = ch->S;
+    return {{S.cur, C * P * 8}, {S.best, C * P * 8}, {S.cur_loss, C * 8}, {S.best_loss, C * 8}, {S.jump, C * 3 * 8},
+            {S.stats, C * EML_CHAIN_STATS * 8}, {S.rng_ctr, C * 8}, {S.window_bits, C * 8}, {S.step, C * 8},
+            {S.last_ratio, C * 8}, {S.kwin, C * 4}, {S.counters, C * 4 * 4}, {S.annealed, C * 4}, {ch->d_status, C * 4}};
+}
+static const unsigned long long kBlobMagic = 0x454d4c4348413031ull;   // "EMLCHA01"
+
+size_t eml_chains_state_bytes(const EmlChains* ch) {
+    if (!ch) return 0;
+    size_t total = 4 * sizeof(unsigned long long);
+    for (const Segment& s : state_segments(ch)) total += s.bytes;
+    return total;
+}
+
+int eml_chains_export(EmlChains* ch, void* blob) {
+    if (!ch || !blob) return fail(EML_ERR_INVALID_ARGUMENT, "chains/blob is NULL");
+    EML_CUDA(cudaSetDevice(ch->plan->device));
+    EML_CUDA(cudaDeviceSynchronize());
+    unsigned long long* head = (unsigned long long*)blob;
+    head[0] = kBlobMagic; head[1] = (unsigned long long)ch->n; head[2] = (unsigned long long)ch->H.n_params; head[3] = ch->seed;
+    char* out = (char*)(head + 4);
+    for (const Segment& s : state_segments(ch)) {
+        EML_CUDA(cudaMemcpy(out, s.ptr, s.bytes, cudaMemcpyDeviceToHost));
+        out += s.bytes;
+    }
+    return EML_OK;
+}
+
+int eml_chains_import(EmlChains* ch, const void* blob) {
+    if (!ch || !blob) return fail(EML_ERR_INVALID_ARGUMENT, "chains/blob is NULL");
+    const unsigned long long* head = (const unsigned long long*)blob;
+    if (head[0] != kBlobMagic || head[1] != (unsigned long long)ch->n || head[2] != (unsigned long long)ch->H.n_params)
+        return fail(EML_ERR_INVALID_ARGUMENT, "checkpoint does not match this engine (magic / n_chains / n_params)");
+    EML_CUDA(cudaSetDevice(ch->plan->device));
+    EML_CUDA(cudaDeviceSynchronize());
+    ch->seed = head[3];
+    const char* in = (const char*)(head + 4);
+    for (const Segment& s : state_segments(ch)) {
+        EML_CUDA(cudaMemcpy(s.ptr, in, s.bytes, cudaMemcpyHostToDevice));
+        in += s.bytes;
+    }
+    return EML_OK;
+}
+
 }  // extern "C"

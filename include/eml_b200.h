@@ -195,6 +195,12 @@ int eml_chains_read(EmlChains* chains, double* current_params, double* current_l
 /* Device pointer of the per-chain statistics table [n_chains][EML_CHAIN_STATS] (refreshed by every run), for
  * the checkpoint all_gather. */
 const double* eml_chains_stats_device(EmlChains* chains);
+/* Checkpoint / resume: the complete chain state (models, losses, jump lengths, acceptance windows, counters,
+ * random-stream positions) as one opaque host blob.  Importing it into an engine created with the same plan layout,
+ * hyperparameters, n_chains, seed and first_chain continues the chains exactly where they were. */
+size_t eml_chains_state_bytes(const EmlChains* chains);
+int eml_chains_export(EmlChains* chains, void* host_blob);
+int eml_chains_import(EmlChains* chains, const void* host_blob);
 
 #ifdef __cplusplus
 }

@@ -123,3 +123,22 @@ def test_two_group_pipelining_gives_the_same_chains():
         eng.close()
     for key in ('current_params', 'current_loss', 'best_loss', 'stats'):
         assert np.array_equal(a[key], np.concatenate([p[key] for p in parts])), key
+
+
+def test_checkpoint_resume_continues_exactly():
+    cfg, ts, targets, a = _setup(2, 40)
+    a.run(30)
+    blob = a.export_state()
+    a.run(30)
+    want = a.read()
+    a.close()
+    b = BatchedChains(ts, targets, OBS3, n_chains=40, n_defects=2, seed=1234, **cfg)
+    b.import_state(blob)
+    b.run(30)
+    got = b.read()
+    b.close()
+    for key in want:
+        assert np.array_equal(want[key], got[key]), key
+    with pytest.raises(RuntimeError):
+        c = BatchedChains(ts, targets, OBS3, n_chains=41, n_defects=2, seed=1234, **cfg)
+        c.import_state(blob)
