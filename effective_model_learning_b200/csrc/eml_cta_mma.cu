@@ -16,7 +16,7 @@
 namespace eml {
 
 constexpr int CQ = 16;        // outputs per expansion
-constexpr int CMAXP = 96;
+constexpr int CMAXP = 192;
 constexpr int LDV = 40;       // row stride (doubles) of Vs: conflict-free LDS.128 over (g, t)
 constexpr int LDX = 34;       // column stride of Xs: conflict-free STS.64 over (g, t)
 

@@ -41,7 +41,7 @@ constexpr int WARPS_PER_CTA = EML_WARPS_PER_CTA;
 #define EML_CTAS_PER_SM 2
 #endif
 constexpr int CTAS_PER_SM = EML_CTAS_PER_SM;   // 2 -> 8 warps per SM (<= 255 regs); 3 -> 12 warps (<= 168 regs)
-constexpr int MAXP = 64;        // parameter-vector cap for this kernel
+constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 
 struct WarpScratch {
     double G_re[16][17];
