@@ -232,3 +232,28 @@ def test_output_writes_the_reference_file_set(oracle_backend, tmp_path):
     assert props['step_types'] == chain.run_step_type_tracker and 'jump to best' in props['step_types']
     assert len(pickle.load(open(base + '_accepted_loss.pickle', 'rb'))) == sum(chain.run_acceptance_tracker)
     assert pickle.load(open(base + '_loss.pickle', 'rb')) == chain.explored_loss
+
+
+def test_total_dev_paths_agree_and_wrap_single_dataset(oracle_backend):
+    """Fused device loss vs the host path taken when custom_function_on_dynamics_return is set; str/ndarray wrapping."""
+    ts = np.linspace(0, 2.0, 25)
+    spec = lo.random_library_spec(np.random.default_rng(12), 1, 2)
+    truth = model_from_spec(spec, eml.LearningModel)
+    data = [np.asarray(d) + 0.01 for d in lo.expect_exact(spec, ts, OBS3)]
+    config = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    config['iterations_till_progress_update'] = False
+    kw = dict(initial=(1, 2), qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'])
+    fused = eml.LearningChain(ts, data, OBS3, **kw, **config)
+    config2 = dict(config, custom_function_on_dynamics_return=lambda r: r)
+    hosted = eml.LearningChain(ts, data, OBS3, **kw, **config2)
+    assert fused.total_dev(truth) == pytest.approx(hosted.total_dev(truth), rel=1e-12)
+    assert fused.total_dev(truth) == pytest.approx(1e-4, rel=1e-9)          # every point is off by exactly 0.01
+    single = eml.LearningChain(ts, data[0], 'sigmax', **kw, **config)
+    assert isinstance(single.target_datasets, list) and single.target_observables == ['sigmax']
+    assert single.total_dev(truth) == pytest.approx(1e-4, rel=1e-9)
+    with pytest.raises(RuntimeWarning):
+        eml.LearningChain(ts, data, OBS3, initial='nonsense', **config)
+    with pytest.raises(RuntimeError):
+        fused.step(truth, 'no such move')
+    assert fused.complementary_step('add qubit L') == 'remove qubit L'
+    assert fused.acceptance_probability((truth, 0.2), (truth, 0.1), 1.0, 1.0) > 1.0
