@@ -159,7 +159,7 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         }
         __syncthreads();
         const double nu = S.misc[0];
-        if (!(nu * (P.times[T - 1] - P.times[0]) < 1e7)) {     // non-finite generator or absurd step count: do not hang
+        if (!(nu * (P.times[T - 1] - P.times[0]) < 1e5)) {     // non-finite generator or absurd step count: do not hang
             if (tid == 0) {
                 if (loss != nullptr) loss[b] = nan("");
                 if (status != nullptr) status[b] = -1;

@@ -259,7 +259,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         __syncwarp();
         const double nu = S.misc[0];
         // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
-        if (UNI(!(nu * (P.times[T - 1] - P.times[0]) < 1e7))) {
+        if (UNI(!(nu * (P.times[T - 1] - P.times[0]) < 1e5))) {
             if (lane == 0) {
                 if (loss != nullptr) loss[b] = nan("");
                 if (status != nullptr) status[b] = -1;
