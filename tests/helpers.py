@@ -72,3 +72,27 @@ def oracle_evaluate(ctx, params, target_set=None, want_expect=True, want_loss=Fa
         sets = np.zeros(B, dtype=int) if target_set is None else np.asarray(target_set)
         loss = np.array([np.sum(np.abs(expect[b] - tg[sets[b]]) ** 2) / (T * K) for b in range(B)])
     return (expect if want_expect else None), loss
+
+
+def random_general_spec(rng, n, p_coupling=0.5):
+    """
+    Random model exercising everything the DMMA kernels support beyond the config libraries: any qubit position,
+    all initial states, generalized-permutation jump operators, Hermitian couplings with mixed Pauli pairs
+    (sigmax (x) sigmay makes H complex), repeated couplings on a pair.
+    """
+    paulis = ['sigmax', 'sigmay', 'sigmaz']
+    jumps = ['sigmax', 'sigmay', 'sigmaz', 'sigmap', 'sigmam', 'exc', 'gnd']
+    states = [None, lo.OPS['plus'], lo.OPS['mm'], lo.OPS['2e+1g'], lo.OPS['gnd'], lo.OPS['exc']]
+    qubit_at = int(rng.integers(0, n))
+    tls = []
+    for k in range(n):
+        init = states[int(rng.integers(0, len(states)))]
+        Ls = {str(op): float(rng.uniform(0.01, 0.4)) for op in rng.permutation(jumps)[:int(rng.integers(0, 4))]}
+        tls.append({'is_qubit': k == qubit_at or bool(rng.uniform() < 0.2), 'energy': float(rng.uniform(0.05, 1.2)),
+                    'Ls': Ls, 'initial_state': None if init is None else init.copy(), 'couplings': []})
+    for i in range(n):
+        for j in range(n):
+            if i != j and rng.uniform() < p_coupling / max(1, n - 2):
+                pairs = [(str(rng.choice(paulis)), str(rng.choice(paulis))) for _ in range(int(rng.integers(1, 3)))]
+                tls[i]['couplings'].append((j, float(rng.uniform(0.1, 2.5)), pairs))
+    return {'tls': tls}

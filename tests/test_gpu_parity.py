@@ -413,3 +413,30 @@ def test_non_finite_parameters_fail_loudly_instead_of_hanging(use_kernel, kernel
         ctx.evaluate(huge, want_expect=True)
     ex, _ = ctx.evaluate(good, want_expect=True)      # the plan is still usable afterwards
     assert np.all(np.isfinite(ex))
+
+
+@pytest.mark.parametrize('n', [2, 3, 4, 5])
+def test_randomised_general_models_dmma_vs_generic_vs_oracle(use_kernel, n):
+    """Stress: 40 random general models per size; DMMA kernels == generic kernel (1e-10), a few also vs the oracle."""
+    from effective_model_learning_b200 import engine
+    from tests.helpers import random_general_spec
+    rng = np.random.default_rng(100 + n)
+    ts = np.sort(np.concatenate([[0.0], rng.uniform(0, 3.0, 45), [3.0, 3.0, 9.0]]))
+    obs = ['sigmax', 'sigmam', 'exc']
+    specs = [random_general_spec(np.random.default_rng(31000 + 97 * n + i), n) for i in range(40)]
+    results = {}
+    names = set()
+    for kernel in ('auto', 'generic'):
+        use_kernel(kernel)
+        out = []
+        for spec in specs:
+            m = model_from_spec(spec)
+            out.append(m.calculate_dynamics(ts, obs))
+            names.add((kernel, engine.context_for(m, obs, ts).plan.kernel_name))
+        results[kernel] = out
+    assert any(k == 'auto' and name != 'generic' for k, name in names), names
+    for a, b in zip(results['auto'], results['generic']):
+        for x, y in zip(a, b):
+            assert np.abs(np.asarray(x) - np.asarray(y)).max() < 1e-10
+    for i in (0, 7, 19):
+        assert_close(results['auto'][i], lo.expect_exact(specs[i], ts, obs), TOL, f'n={n} model {i}')
