@@ -141,58 +141,86 @@ def run_reference(args):
         'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': pool.cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'rjmcmc_equivalent_steps_per_s': value / 3.0,   # the reference spends 3 evaluations per RJMCMC step
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """
+    SM clock, power and clock-event reasons sampled DURING the timed region: NVML in a background thread every
+    20 ms (pynvml), falling back to an `nvidia-smi -lms 100` subprocess when NVML cannot be loaded.
+    """
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
 
     def __init__(self, device):
-        self.rows = []
+        self.rows = []          # (t, sm_mhz, sm_max_mhz, power_w, [reasons])
         self.proc = None
+        self.stop_flag = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = int(visible.split(',')[device]) if visible and visible.split(',')[device].isdigit() else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = 'nvml'
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
                                           '-lms', '100', '-i', str(device)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = 'nvidia-smi'
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for (t, line) in self.rows:
-            if not (t0 - 0.05 <= t <= t1 + 0.05):
-                continue
-            parts = [p.strip() for p in line.split(',')]
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = ((n.nvmlClocksEventReasonHwSlowdown, 'hw_slowdown'), (n.nvmlClocksEventReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+                (n.nvmlClocksEventReasonSwThermalSlowdown, 'sw_thermal_slowdown'), (n.nvmlClocksEventReasonSwPowerCap, 'sw_power_cap'))
+        while not self.stop_flag:
             try:
-                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append((time.perf_counter(), sm, self.smax, pw, [name for bit, name in bits if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(',')]
+            try:
+                self.rows.append((time.perf_counter(), float(parts[0]), float(parts[1]), float(parts[2]),
+                                  [n for n, p in zip(self.NAMES, parts[3:7]) if p.lower().startswith('active')]))
             except (ValueError, IndexError):
                 continue
-            for n, p in zip(names, parts[3:7]):
-                if p.lower().startswith('active'):
-                    reasons.add(n)
-        if not sm:   # region shorter than the sampling period: use the nearest samples
-            for (t, line) in self.rows[-3:]:
-                parts = [p.strip() for p in line.split(',')]
-                try:
-                    sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
-                except (ValueError, IndexError):
-                    pass
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+    def stop(self, t0, t1):
+        if self.source is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi available']}
+        time.sleep(0.05 if self.source == 'nvml' else 0.15)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + 0.02] or self.rows[-3:]
+        sm = [r[1] for r in inside]
+        reasons = sorted({name for r in inside for name in r[4]})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max((r[2] for r in inside), default=None),
+                'power_w_max': max((r[3] for r in inside), default=None), 'samples': len(sm), 'reasons': reasons,
+                'source': self.source}
 
 
 def canonical_dense_flops(n_tls, T, K):
@@ -256,7 +284,7 @@ def run_b200(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        time.sleep(0.25)
+        time.sleep(0.1)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launch_count()
