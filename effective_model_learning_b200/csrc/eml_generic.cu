@@ -28,7 +28,7 @@ __host__ __device__ inline GenericSmem generic_layout(int n, int n_params) {
     L.red = o; o += QMAX * 4 * D;   // [p][ab][rest][2], rest < D/2
     L.rr = o; o += QMAX * 8;        // [p][ab][2]
     L.par = o; o += n_params;
-    L.misc = o; o += 2 * D + 8 + QMAX * MAX_OBS;
+    L.misc = o; o += 2 * D + 8 + QMAX * MAX_OBS + 3 * QMAX;   // + xs[QMAX], xp[2][QMAX] (dense-output weights)
     L.total = o;
     return L;
 }
@@ -178,23 +178,20 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
 
     double acc_re = 0.0, acc_im = 0.0;
     if (active) { acc_re = P.rho0[2 * tid]; acc_im = P.rho0[2 * tid + 1]; }
-    double y_re[QMAX], y_im[QMAX], xs[QMAX], xp[QMAX];
+    // dense-output accumulators live in shared memory (`red`, owned by the diag threads) and the weights x^j in
+    // xs_s / xp_s (double-buffered by term parity), which keeps the kernel at ~100 registers
+    double* xs_s = misc + 2 * D + 8 + QMAX * MAX_OBS;
+    double* xp_s = xs_s + QMAX;
+    const int ybase = (ab * (D / 2) + rest) * 2;       // this diag thread's slot within red[p][...]
+    const int ystride = 4 * (D / 2) * 2;
     double my_loss = 0.0;
     int n_apply = 0;
     bool capped = false;
     const int tset = (target_set != nullptr) ? target_set[b] : 0;
     const double* tgt = (P.targets != nullptr) ? P.targets + (size_t)tset * K * T * 2 : nullptr;
 
-    // emits q outputs starting at time index kbase from y_re/y_im of the diag threads
+    // emits q outputs starting at time index kbase from the accumulators the diag threads keep in red[p][ab][rest]
     auto emit = [&](int q, int kbase) {
-        if (diag) {
-#pragma unroll
-            for (int p = 0; p < QMAX; ++p)
-                if (p < q) {
-                    red[((p * 4 + ab) * (D / 2) + rest) * 2] = y_re[p];
-                    red[((p * 4 + ab) * (D / 2) + rest) * 2 + 1] = y_im[p];
-                }
-        }
         __syncthreads();
         if (tid < q * 4) {
             double sre = 0.0, sim = 0.0;
@@ -228,7 +225,7 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
         __syncthreads();
     };
 
-    y_re[0] = acc_re; y_im[0] = acc_im;
+    if (diag) { red[ybase] = acc_re; red[ybase + 1] = acc_im; }
     emit(1, 0);
 
     int cur = 0;
@@ -238,21 +235,23 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
         double htot;
         choose_step(P.times, T, k, nu, P.theta_target, q, nsub, htot);
         if (htot == 0.0) {               // repeated time points: the state does not move
-#pragma unroll
-            for (int p = 0; p < QMAX; ++p) { y_re[p] = acc_re; y_im[p] = acc_im; }
+            if (diag)
+                for (int p = 0; p < q; ++p) { red[p * ystride + ybase] = acc_re; red[p * ystride + ybase + 1] = acc_im; }
             emit(q, k + 1);
             k += q;
             continue;
         }
         const double h = htot / nsub;
         const double t0 = P.times[k];
-#pragma unroll
-        for (int p = 0; p < QMAX; ++p) xs[p] = (p < q) ? ((nsub == 1) ? (P.times[k + 1 + p] - t0) / htot : 1.0) : 0.0;
+        __syncthreads();      // the previous emit is done reading red / rr
+        if (tid < QMAX) xs_s[tid] = (tid < q) ? ((nsub == 1) ? (P.times[k + 1 + tid] - t0) / htot : 1.0) : 0.0;
         for (int sub = 0; sub < nsub; ++sub) {
             double* vr = vbuf + cur * 2 * DD;
             if (active) { vr[tid] = acc_re; vr[DD + tid] = acc_im; }
-#pragma unroll
-            for (int p = 0; p < QMAX; ++p) { y_re[p] = acc_re; y_im[p] = acc_im; xp[p] = 1.0; }
+            if (diag && sub == nsub - 1)
+                for (int p = 0; p < q; ++p) { red[p * ystride + ybase] = acc_re; red[p * ystride + ybase + 1] = acc_im; }
+            __syncthreads();      // xs_s visible
+            if (tid < QMAX) xp_s[tid] = xs_s[tid];          // buffer 0 = x^1, the weight of term 1
             __syncthreads();
             int small = 0;
             int j = 0;
@@ -295,15 +294,14 @@ eval_generic_kernel(const DevProblem P, const long long n_models, const double* 
                     w_re[tid] = ore; w_im[tid] = oim;
                     acc_re += ore; acc_im += oim;
                     if (diag && sub == nsub - 1) {
-#pragma unroll
-                        for (int p = 0; p < QMAX; ++p)
-                            if (p < q) {
-                                xp[p] *= xs[p];
-                                y_re[p] += xp[p] * ore;
-                                y_im[p] += xp[p] * oim;
-                            }
+                        const double* xw = xp_s + (j & 1) * QMAX;      // x^(j+1), prepared before the last barrier
+                        for (int p = 0; p < q; ++p) {
+                            red[p * ystride + ybase] += xw[p] * ore;
+                            red[p * ystride + ybase + 1] += xw[p] * oim;
+                        }
                     }
                 }
+                if (tid < QMAX) xp_s[((j + 1) & 1) * QMAX + tid] = xp_s[(j & 1) * QMAX + tid] * xs_s[tid];   // x^(j+2) for the next term
                 const int big = (fabs(ore) > P.tol) || (fabs(oim) > P.tol);
                 const int anybig = __syncthreads_or(big);
                 cur ^= 1;
