@@ -17,20 +17,6 @@ def pytest_configure(config):
         __graft_entry__.build()
 
 
-def _have_gpu() -> bool:
-    try:
-        from effective_model_learning_b200 import _native
-        return _native.device_count() > 0
-    except Exception:
-        return False
-
-
-def pytest_collection_modifyitems(config, items):
-    # GPU tests are selected with -m gpu; when selected on a box without a device they must
-    # fail loudly rather than skip, so nothing is done here beyond registering the marker.
-    return
-
-
 @pytest.fixture
 def oracle_backend(monkeypatch):
     """Route EvalContext.evaluate to the CPU oracle (host-logic tests on a box without a GPU)."""
