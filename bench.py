@@ -333,6 +333,7 @@ def run_b200(args):
     # ---- roofline of the (single) kernel: FP64 FLOPs it executes / CUDA-event time, vs measured FP64 peak
     fp64_fma = _native.measure_fp64_peak(local, False, 0.3)
     fp64_mma = _native.measure_fp64_peak(local, True, 0.3)
+    fp64_mixed = _native.measure_fp64_peak(local, 2, 0.3)      # DMMA and DFMA interleaved in every warp
     peak = max(fp64_fma, fp64_mma)
     flops_per_app = engine.flops_per_application(plan.kernel_name, layout.n_tls)
     flops_launch = flops_per_app * applications
@@ -352,6 +353,8 @@ def run_b200(args):
         'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu --set full capture of the same workload)',
         'peak_source': 'measured in this run: eml_measure_fp64_peak (register-resident DFMA / DMMA m8n8k4 chains); '
                        'MEASURED_PEAKS.json has no FP64 figure',
+        'peak_dfma_tflops': fp64_fma / 1e12, 'peak_dmma_tflops': fp64_mma / 1e12,
+        'peak_mixed_dmma_dfma_tflops': fp64_mixed / 1e12,
         'flops_per_launch': flops_launch, 'generator_applications_per_eval': applications / B,
         'flops_per_application': flops_per_app, 'kernel_ms': kernel_ms,
         'canonical_dense_gflop_per_eval': canon / 1e9,

@@ -119,7 +119,8 @@ def launch_count() -> int:
     return int(load().eml_launch_count())
 
 
-def measure_fp64_peak(device: int = 0, use_mma: bool = False, seconds: float = 0.5) -> float:
+def measure_fp64_peak(device: int = 0, use_mma=False, seconds: float = 0.5) -> float:
+    """use_mma: False = DFMA chains, True = DMMA m8n8k4 chains, 2 = both interleaved in every warp."""
     out = C.c_double(0.0)
     check(load().eml_measure_fp64_peak(device, int(use_mma), seconds, C.byref(out)), 'eml_measure_fp64_peak')
     return out.value

@@ -37,6 +37,26 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mixed: every warp alternates independent DMMA and DFMA chains -- tells whether the two share one pipe
+__global__ void __launch_bounds__(256) mixed_peak_kernel(double* out, int iters, double a, double b) {
+    double c[4][2];
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c[u][0] = threadIdx.x + u; c[u][1] = u; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dmma884(c[u][0], c[u][1], a, b);
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += c[u][0] + c[u][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s) {
     int dev = 0, sms = 0;
     cudaError_t e;
@@ -49,13 +69,16 @@ cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 4096;
     // flops per launch
-    const double fl = use_mma ? (double)blocks * (threads / 32) * iters * 8.0 * (2.0 * 8 * 8 * 4)
-                              : (double)blocks * threads * iters * 64.0 * 2.0;
+    // mixed (use_mma == 2): per iteration and warp 4 DMMAs (512 flops each) + 32 warp-wide DFMAs (64 flops each)
+    const double fl = use_mma == 2 ? (double)blocks * (threads / 32) * iters * (4.0 * 512.0 + 32.0 * 64.0)
+                      : use_mma    ? (double)blocks * (threads / 32) * iters * 8.0 * (2.0 * 8 * 8 * 4)
+                                   : (double)blocks * threads * iters * 64.0 * 2.0;
     double best = 0.0, elapsed = 0.0;
     int reps = 0;
     while ((elapsed < seconds * 1e3 || reps < 3) && reps < 10000) {
         cudaEventRecord(e0);
-        if (use_mma) dmma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        if (use_mma == 2) mixed_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        else if (use_mma) dmma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
         else dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
         cudaEventRecord(e1);
         if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
