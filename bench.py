@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument('--chains', type=int, default=4096, help='chains (models per step) per GPU')
     ap.add_argument('--defects', type=int, default=3)
     ap.add_argument('--qubits', type=int, default=1)
-    ap.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'warp_mma'])
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'warp_mma', 'warp_cheb'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-chains', action='store_true', help='skip the RJMCMC steps/s measurement')
     ap.add_argument('--cpu-sample', type=int, default=0, help='models in the CPU-baseline sample (0 = 64 per core; 16 per core per step in the reference arm)')
@@ -243,7 +243,8 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC, 'warp_mma': _native.KERNEL_WARP_MMA}[args.kernel]
+    kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC, 'warp_mma': _native.KERNEL_WARP_MMA,
+              'warp_cheb': _native.KERNEL_WARP_CHEB}[args.kernel]
 
     layout, _ = make_layout(args)
     ts = np.linspace(*T_SPAN, N_TIMES)

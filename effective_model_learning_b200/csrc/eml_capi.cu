@@ -14,7 +14,7 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
                            double* expect, double* loss, int* status, cudaStream_t stream);
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
-                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
+                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h, bool chebyshev,
                             const int* cost_hint, cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
@@ -207,17 +207,17 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
 
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
     if (want == EML_KERNEL_AUTO)
-        want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_MMA
+        want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_CHEB
                : eml::cta_mma_supported(P, herm) ? EML_KERNEL_CTA_MMA : EML_KERNEL_GENERIC;
     if (want == EML_KERNEL_CTA_MMA && !eml::cta_mma_supported(P, herm)) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_UNSUPPORTED, "cta_mma kernel needs n_tls == 5, Hermitian H and rho0, generalized-permutation jump operators");
     }
-    if (want == EML_KERNEL_WARP_MMA && !eml::warp_mma_supported(plan->Pw, herm)) {
+    if ((want == EML_KERNEL_WARP_MMA || want == EML_KERNEL_WARP_CHEB) && !eml::warp_mma_supported(plan->Pw, herm)) {
         eml_plan_destroy(plan);
-        return fail(EML_ERR_UNSUPPORTED, "warp_mma kernel needs n_tls <= 4, Hermitian H and rho0, generalized-permutation jump operators");
+        return fail(EML_ERR_UNSUPPORTED, "warp kernels need n_tls <= 4, Hermitian H and rho0, generalized-permutation jump operators");
     }
-    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA && want != EML_KERNEL_CTA_MMA) {
+    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA && want != EML_KERNEL_CTA_MMA && want != EML_KERNEL_WARP_CHEB) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_INVALID_ARGUMENT, "unknown kernel id");
     }
@@ -233,6 +233,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
 const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (!plan) return "";
     if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
+    if (plan->kernel == EML_KERNEL_WARP_CHEB) return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
     if (plan->kernel == EML_KERNEL_CTA_MMA) return plan->real_h ? "cta_mma_realH" : "cta_mma";
     return "generic";
 }
@@ -256,8 +257,9 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     EML_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
     cudaError_t e;
-    if (plan->kernel == EML_KERNEL_WARP_MMA)
+    if (plan->kernel == EML_KERNEL_WARP_MMA || plan->kernel == EML_KERNEL_WARP_CHEB)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
+                                 plan->kernel == EML_KERNEL_WARP_CHEB,
                                  cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,

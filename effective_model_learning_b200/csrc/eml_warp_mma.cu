@@ -27,6 +27,7 @@
 // (sigmax/y/z/p/m, exc, gnd, id2, mm all qualify).
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
+#include <cmath>
 #include "eml_common.cuh"
 
 namespace eml {
@@ -43,15 +44,29 @@ constexpr int WARPS_PER_CTA = EML_WARPS_PER_CTA;
 constexpr int CTAS_PER_SM = EML_CTAS_PER_SM;   // 2 -> 8 warps per SM (<= 255 regs); 3 -> 12 warps (<= 168 regs)
 constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 
-struct WarpScratch {
-    double G_re[16][17];
-    double G_im[16][17];
+// Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26 KB at d = 16,
+// 16 warps x 13 KB at d <= 8), and the largest  tau * (A + B)  whose series fits (cheb_terms(z) <= cap)
+constexpr int CHEB_KCAP_TL2 = 640, CHEB_KCAP_TL1 = 256;
+constexpr double CHEB_C1 = 9.25, CHEB_C0 = 5.0;        // |J_k(z)| < 1e-14 for k >= z + C1 z^(1/3) + C0 (z <= 2000)
+constexpr double CHEB_HUMP = 14.0;                     // cap on tau * B: partial sums stay below e^14 (as theta = 16 did)
+
+template <int TL, bool CHEB>
+struct alignas(16) WarpScratch {
+    static constexpr int D = 8 * TL;
+    static constexpr int KCAP = CHEB ? (TL == 2 ? CHEB_KCAP_TL2 : CHEB_KCAP_TL1) : 0;
+    // G_re, G_im, par are contiguous: dead once the A fragments are in registers, the Chebyshev path reuses them
+    // for the coefficient table of the step end (KCAP + 1 <= 2 D (D + 1) + MAXP doubles)
+    double G_re[D][D + 1];
+    double G_im[D][D + 1];
     double par[MAXP];
     double jw[32];      // [bitpos][type(0 diag,1 flip)][ra][ca]
+    double kd[8];       // [bitpos][ra]: diagonal of sum rate * A^dag A per site
     double colsum[16];
     double misc[4];
-    double xt_re[256], xt_im[256];   // X' staged column-major (swizzled) for the conjugate transpose
+    double xt_re[TL == 1 ? 128 : 2], xt_im[TL == 1 ? 128 : 2];   // d = 8: X' staged column-major (swizzled) for the conjugate transpose
+    alignas(16) double tr[(KCAP + 1) * 4];                        // partial traces of the Chebyshev terms
 };
+static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -132,15 +147,17 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     }
 }
 
-template <int TL, bool REAL_H>
+template <int TL, bool REAL_H, bool CHEB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
-                     int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
+                     int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
+                     const double cheb_zcap) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
-    __shared__ __align__(16) WarpScratch scratch_all[WARPS_PER_CTA];
-    WarpScratch& S = scratch_all[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Scratch = WarpScratch<TL, CHEB>;
+    Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int T = P.n_times, K = P.n_obs;
@@ -175,7 +192,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 
         // ---- parameters, clear G
         for (int i = lane; i < P.n_params; i += 32) S.par[i] = params[b * P.n_params + i];
-        for (int i = lane; i < 16 * 17; i += 32) { (&S.G_re[0][0])[i] = 0.0; (&S.G_im[0][0])[i] = 0.0; }
+        for (int i = lane; i < D * (D + 1); i += 32) { (&S.G_re[0][0])[i] = 0.0; (&S.G_im[0][0])[i] = 0.0; }
         __syncwarp();
 
         // ---- K1: assemble G (lane r < 16 owns row r) and the real jump weights (one entry per lane)
@@ -232,6 +249,21 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 w += v * x.re;
             }
             S.jw[lane] = w;
+        }
+        if (CHEB && lane < 8) {     // diagonal of sum rate * A^dag A per site (the anticommutator part of the site generator)
+            const int bp = lane >> 1, ra = lane & 1;
+            double kdv = 0.0;
+            for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                for (int z = 0; z < 2; ++z) {
+                    const cplx m = ld_op(P.op_table, tm.op_a, z, ra);
+                    kdv += v * (m.re * m.re + m.im * m.im);
+                }
+            }
+            S.kd[lane] = kdv;
         }
         __syncwarp();
 
@@ -357,6 +389,24 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             return k;   // value index = 2*bit4 + bit3 = lane >> 3
         };
 
+        // observables and loss of one output time from the reduced density matrix r = (rho00, rho11, Re rho01, Im rho01)
+        auto finish_output = [&](const int k, const double (&r)[4]) {
+            for (int m = 0; m < K; ++m) {
+                const double* O = P.obs + m * 8;
+                // Tr(O rho_red) = O00 r00 + O11 r11 + O01 r10 + O10 r01,  r10 = conj(r01)
+                const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
+                const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
+                if (expect != nullptr) {
+                    double* e = expect + (((size_t)b * K + m) * T + k) * 2;
+                    e[0] = ere; e[1] = eim;
+                }
+                if (tgt != nullptr) {
+                    const double dre = ere - tgt[((size_t)m * T + k) * 2], dim = eim - tgt[((size_t)m * T + k) * 2 + 1];
+                    my_loss += dre * dre + dim * dim;
+                }
+            }
+        };
+
         // emit q outputs starting at time index kbase; y[n] is this lane's accumulator for output
         // p = (lane&7) + 8n of value index lane>>3.  Lane l finalises outputs l, l + 32, ...
         auto emit = [&](int q, int kbase, const double (&y)[NY]) {
@@ -377,23 +427,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 }
                 r[vi] = val;
             }
-            if (p < q) {
-                const int k = kbase + p;
-                for (int m = 0; m < K; ++m) {
-                    const double* O = P.obs + m * 8;
-                    // Tr(O rho_red) = O00 r00 + O11 r11 + O01 r10 + O10 r01,  r10 = conj(r01)
-                    const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
-                    const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
-                    if (expect != nullptr) {
-                        double* e = expect + (((size_t)b * K + m) * T + k) * 2;
-                        e[0] = ere; e[1] = eim;
-                    }
-                    if (tgt != nullptr) {
-                        const double dre = ere - tgt[((size_t)m * T + k) * 2], dim = eim - tgt[((size_t)m * T + k) * 2 + 1];
-                        my_loss += dre * dre + dim * dim;
-                    }
-                }
-            }
+            if (p < q) finish_output(kbase + p, r);
           }
         };
 
@@ -405,6 +439,380 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             emit(1, 0, y1st);
         }
 
+        // ---- generator application core, shared by both series: given x = (diagonal stencil weight) * v (+ anything
+        //      Hermitian / 2), add the remaining site stencils (J(v)/2) and G v on the DMMA pipe -> X'
+        auto apply_rest = [&](const double (&v_re)[TL][TL][2], const double (&v_im)[TL][TL][2], double (&x_re)[TL][TL][2], double (&x_im)[TL][TL][2]) {
+            {
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            if (TL == 2) {
+                                x_re[I][J][e] = fma(F3[I][J], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
+                                x_im[I][J][e] = fma(F3[I][J], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
+                            }
+                        }
+            }
+            {
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), x_im[I][J][e]);
+                        }
+            }
+            {
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), x_im[I][J][e]);
+                        }
+            }
+            {
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), x_im[I][J][e]);
+                        }
+            }
+            // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
+            //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                if (!REAL_H) {
+#pragma unroll
+                    for (int J = 0; J < TL; ++J) {
+                        const double b_re = v_re[J][ks >> 1][ks & 1];
+                        const double nb_im = neg(v_im[J][ks >> 1][ks & 1]);
+#pragma unroll
+                        for (int I = 0; I < TL; ++I) {
+                            dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
+                            dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int J = 0; J < TL; ++J) {
+                    const double b_re = v_re[J][ks >> 1][ks & 1];
+                    const double b_im = v_im[J][ks >> 1][ks & 1];
+#pragma unroll
+                    for (int I = 0; I < TL; ++I) {
+                        dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
+                        dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
+                    }
+                }
+            }
+        };
+        // w = X' + X'^dag (the conjugate transpose gathered with shuffles, d = 8: through shared memory)
+        auto symmetrise = [&](const double (&x_re)[TL][TL][2], const double (&x_im)[TL][TL][2], double (&w_re)[TL][TL][2], double (&w_im)[TL][TL][2]) {
+            if constexpr (TL == 2) {     // d = 16: shuffles (measured 1 % faster than the shared-memory route)
+#pragma unroll
+            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                for (int J = 0; J < TL; ++J) {
+                    // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I) with shuffles
+                    const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
+                    const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
+                    const double rAr = shfl(sAr, srcA), rBr = shfl(sBr, srcB);
+                    const double rAi = shfl(sAi, srcA), rBi = shfl(sBi, srcB);
+                    const double t_re[2] = {gp ? rBr : rAr, gp ? rAr : rBr};
+                    const double t_im[2] = {gp ? rBi : rAi, gp ? rAi : rBi};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double wr = x_re[I][J][e] + t_re[e];
+                        const double wi = x_im[I][J][e] - t_im[e];
+                        w_re[I][J][e] = wr; w_im[I][J][e] = wi;
+                    }
+                }
+            } else {                     // d = 8: issue-bound, the shared-memory route saves ~90 instructions (+5 %)
+            // X'^dag through shared memory: element (R, C) of X' is stored at C*16 + (R ^ m(C)) with the swizzle
+            // m(C) = 4*bit1(C) + 8*(bit2(C) ^ bit0(C)), which makes both the STS.64 of the accumulator
+            // fragments and the LDS.128 of the transposed pairs bank-conflict free.
+#pragma unroll
+            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                for (int J = 0; J < TL; ++J)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int Cc = 8 * J + 2 * t + e;
+                        const int m = 4 * (t & 1) + 8 * (((t >> 1) & 1) ^ e);
+                        S.xt_re[Cc * 16 + ((8 * I + g) ^ m)] = x_re[I][J][e];
+                        S.xt_im[Cc * 16 + ((8 * I + g) ^ m)] = x_im[I][J][e];
+                    }
+            __syncwarp();
+#pragma unroll
+            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                for (int J = 0; J < TL; ++J) {
+                    const int m = 4 * ((g >> 1) & 1) + 8 * (((g >> 2) & 1) ^ (g & 1));
+                    const int o = (8 * I + g) * 16 + ((8 * J + 2 * t) ^ m);
+                    const double2 tr_ = *reinterpret_cast<const double2*>(&S.xt_re[o]);
+                    const double2 ti_ = *reinterpret_cast<const double2*>(&S.xt_im[o]);
+                    const double wr0 = x_re[I][J][0] + tr_.x, wr1 = x_re[I][J][1] + tr_.y;
+                    const double wi0 = x_im[I][J][0] - ti_.x, wi1 = x_im[I][J][1] - ti_.y;
+                    w_re[I][J][0] = wr0; w_re[I][J][1] = wr1; w_im[I][J][0] = wi0; w_im[I][J][1] = wi1;
+                }
+            __syncwarp();
+            }
+        };
+
+        if constexpr (CHEB) {
+        // =====================================================================================================
+        // Chebyshev series of the propagator (Jacobi-Anger):  with  L = L_s - ac  and  At = L_s / R,
+        //     exp(tau L) rho = e^{-ac tau} [ J_0(tau R) phi_0 + 2 sum_{k>=1} J_k(tau R) phi_k ],
+        //     phi_0 = rho,  phi_1 = At rho,  phi_{k+1} = 2 At phi_k + phi_{k-1}
+        // (phi_k = i^k T_k(At / i): a REAL three-term recurrence).  The phi_k do not depend on tau, so ONE recurrence
+        // serves every output time of a macro step; only the 2x2 partial trace of each phi_k is kept (shared
+        // memory) and each output is a Bessel-weighted sum of them, the weights generated per output by Miller's
+        // backward recurrence.  There is no e^theta cancellation hump as in the Taylor series, so a macro step can
+        // span hundreds of output times: about  tau (A + B) + 9.25 (tau (A + B))^(1/3) + 5  generator applications
+        // instead of ~4 per unit of the norm bound.  [-iR, iR] must enclose the imaginary extent of the numerical
+        // range: Gershgorin on H for the commutator, per-site Gershgorin for the dissipator (real range [dlo, dhi],
+        // centred by the shift ac; antisymmetric part added to the imaginary extent); the series is truncated for
+        // the confocal ellipse (semi-axes A along the imaginary axis, B real) through the corner of that rectangle.
+        double spread, ac, ah, dasym = 0.0;
+        {
+            double hi = -1e300, lo = 1e300;
+            if (lane < D) {
+                double rad = 0.0;
+                for (int c = 0; c < D; ++c)
+                    if (c != lane) rad += REAL_H ? fabs(S.G_im[lane][c]) : hypot(S.G_re[lane][c], S.G_im[lane][c]);
+                const double ctr = -S.G_im[lane][lane];
+                hi = ctr + rad; lo = ctr - rad;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            }
+            spread = hi - lo;
+            double dlo = 0.0, dhi = 0.0;
+            for (int bp = 0; bp < N; ++bp) {
+                double slo = 1e300, shi = -1e300, sas = 0.0;
+#pragma unroll
+                for (int rc = 0; rc < 4; ++rc) {
+                    const int ra = rc >> 1, ca = rc & 1;
+                    const double dg = S.jw[bp * 8 + rc] - 0.5 * (S.kd[bp * 2 + ra] + S.kd[bp * 2 + ca]);
+                    const double fa = S.jw[bp * 8 + 4 + rc], fb = S.jw[bp * 8 + 4 + (3 - rc)];
+                    const double rad = 0.5 * fabs(fa + fb);
+                    slo = fmin(slo, dg - rad); shi = fmax(shi, dg + rad); sas = fmax(sas, 0.5 * fabs(fa - fb));
+                }
+                dlo += slo; dhi += shi; dasym += sas;
+            }
+            ac = -0.5 * (dlo + dhi); ah = 0.5 * (dhi - dlo);
+        }
+        const double yext = spread + dasym;
+        const double t_first = P.times[0];
+        const double span = P.times[T - 1] - t_first;
+        double Rb = 1.0, Sb = 1e300, Bb = 0.0;
+        {
+            bool have_ok = false;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double delta = (i == 0) ? 0.03 : (i == 1) ? 0.06 : (i == 2) ? 0.12 : (i == 3) ? 0.25 : (i == 4) ? 0.5 : 1.0;
+                const double Rc = fmax(fmax(yext * (1.0 + delta), ah), 1e-3 / fmax(span, 1e-300));
+                const double cc = Rc * Rc - ah * ah - yext * yext, xr2 = ah * ah * Rc * Rc;
+                const double disc = sqrt(cc * cc + 4.0 * xr2);
+                const double u = (cc > 0.0) ? 2.0 * xr2 / (cc + disc) : 0.5 * (disc - cc);
+                const double Bc = sqrt(u), Ac = sqrt(u + Rc * Rc);
+                const bool ok = span * Bc <= CHEB_HUMP;
+                if ((ok && !have_ok) || (ok == have_ok && Ac + Bc < Sb)) { Rb = Rc; Sb = Ac + Bc; Bb = Bc; have_ok = ok; }
+            }
+        }
+        double tau_max = cheb_zcap / Sb;
+        if (Bb > 0.0) tau_max = fmin(tau_max, CHEB_HUMP / Bb);
+        {   // |phi_k| can grow like (S/R)^k: keep k log(S/R) below ~560 so that nothing overflows
+            const double lnr = log(Sb / Rb);
+            if (lnr * (double)Scratch::KCAP > 560.0) {
+                const double kall = 560.0 / lnr;
+                tau_max = fmin(tau_max, fmax(kall - CHEB_C1 * cbrt(kall) - CHEB_C0, 1.0) / Sb);
+            }
+        }
+        {   // generator -> 2 (L + ac) / R  (stencil weights are stored halved)
+            const double sc = 2.0 / Rb;
+#pragma unroll
+            for (int I = 0; I < TL; ++I) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) { a_re[I][ks] *= sc; a_im[I][ks] *= sc; }
+#pragma unroll
+                for (int J = 0; J < TL; ++J) {
+                    F3[I][J] *= sc;
+                    W0[I][J][0] = (W0[I][J][0] + 0.5 * ac) * sc; W0[I][J][1] = (W0[I][J][1] + 0.5 * ac) * sc;
+                }
+            }
+            f2 *= sc; f1 *= sc; f0[0] *= sc; f0[1] *= sc;
+        }
+        double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
+        auto cheb_terms = [](const double z) { return (int)ceil(z + CHEB_C1 * cbrt(z) + CHEB_C0); };
+
+        int kidx = 0;
+        while (UNI(kidx < T - 1)) {
+            const double t0 = P.times[kidx];
+            int q = 0;
+            while (UNI(kidx + q + 1 <= T - 1 && P.times[kidx + q + 1] - t0 <= tau_max)) ++q;
+            int nsub = 1;
+            if (UNI(q == 0)) { nsub = (int)ceil((P.times[kidx + 1] - t0) / tau_max); q = 1; }
+            const double tau_end = (P.times[kidx + q] - t0) / nsub;
+            const bool final_step = (kidx + q == T - 1);
+            if (UNI(!(tau_end * Rb >= 1e-40))) {     // repeated time points: the state does not move
+                const double tr0 = partial_trace(acc_re, acc_im);
+                for (int pbase = 0; UNI(pbase < q); pbase += 32) {
+                    double r[4];
+#pragma unroll
+                    for (int vi = 0; vi < 4; ++vi) r[vi] = shfl(tr0, vi * 8);
+                    if (pbase + lane < q) finish_output(kidx + 1 + pbase + lane, r);
+                }
+                kidx += q;
+                continue;
+            }
+            int Kc = cheb_terms(tau_end * Sb);
+            if (Kc > Scratch::KCAP) Kc = Scratch::KCAP;
+            for (int sub = 0; UNI(sub < nsub); ++sub) {
+                const bool last = (sub == nsub - 1);
+                const bool need_acc = UNI(!(final_step && last));     // the state at the step end is needed
+                double cscale = 0.0;
+                if (need_acc) {
+                    // J_k(tau_end R), k = 0..Kc: Miller's backward recurrence, every lane redundantly, normalised by
+                    // J_0 + 2 sum J_2k = 1
+                    __syncwarp();
+                    const double tz = 2.0 / (tau_end * Rb);
+                    double jn = 1.0, jn1 = 0.0, ssum = 0.0;
+                    for (int k = Kc; k >= 1; --k) {
+                        if ((k & 31) == lane) cJ[k] = 2.0 * jn;
+                        if (!(k & 1)) ssum += jn;
+                        const double jm = fma((double)k * tz, jn, -jn1);
+                        jn1 = jn; jn = jm;
+                    }
+                    if (lane == 0) cJ[0] = jn;
+                    cscale = exp(-ac * tau_end) / (2.0 * ssum + jn);
+                    __syncwarp();
+                }
+                double v_re[TL][TL][2], v_im[TL][TL][2], ph_re[TL][TL][2], ph_im[TL][TL][2];
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            v_re[I][J][e] = 0.5 * acc_re[I][J][e]; v_im[I][J][e] = 0.5 * acc_im[I][J][e];   // phi_1 = (2 At)(phi_0 / 2)
+                            ph_re[I][J][e] = 0.0; ph_im[I][J][e] = 0.0;
+                            acc_re[I][J][e] = 0.0; acc_im[I][J][e] = 0.0;
+                        }
+                double hs = 1.0, ts = 2.0;     // phi_{k-1} / 2 from the stored input; the k = 0 input is phi_0 / 2
+                for (int k = 0; UNI(k < Kc); ++k) {
+                    {   // partial trace of phi_k (independent of the DMMAs below)
+                        const double trv = partial_trace(v_re, v_im) * ts;
+                        if ((lane & 7) == 0) S.tr[k * 4 + (lane >> 3)] = trv;
+                    }
+                    if (need_acc) {
+                        const double c = cJ[k] * cscale * ts;
+#pragma unroll
+                        for (int I = 0; I < TL; ++I)
+#pragma unroll
+                            for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
+                                    acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
+                                }
+                    }
+                    double x_re[TL][TL][2], x_im[TL][TL][2], w_re[TL][TL][2], w_im[TL][TL][2];
+#pragma unroll
+                    for (int I = 0; I < TL; ++I)
+#pragma unroll
+                        for (int J = 0; J < TL; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
+                                x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
+                            }
+                    apply_rest(v_re, v_im, x_re, x_im);
+                    symmetrise(x_re, x_im, w_re, w_im);       // phi_{k+1} = (2 At) v + phi_{k-1}
+#pragma unroll
+                    for (int I = 0; I < TL; ++I)
+#pragma unroll
+                        for (int J = 0; J < TL; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                ph_re[I][J][e] = hs * v_re[I][J][e]; ph_im[I][J][e] = hs * v_im[I][J][e];
+                                v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
+                            }
+                    hs = 0.5; ts = 1.0;
+                }
+                {   // the last term
+                    const double trv = partial_trace(v_re, v_im);
+                    if ((lane & 7) == 0) S.tr[Kc * 4 + (lane >> 3)] = trv;
+                    if (need_acc) {
+                        const double c = cJ[Kc] * cscale;
+#pragma unroll
+                        for (int I = 0; I < TL; ++I)
+#pragma unroll
+                            for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
+                                    acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
+                                }
+                    }
+                    // a non-finite last term means the enclosure failed: report instead of returning garbage
+                    const double chk = fabs(v_re[0][0][0]) + fabs(v_im[0][0][0]) + fabs(v_re[TL - 1][TL - 1][1]);
+                    if (!UNI(chk < 1e300)) capped = true;
+                }
+                n_apply += Kc;
+                __syncwarp();
+                if (UNI(last)) {
+                    // ---- outputs of the step: lane l takes outputs l, l + 32, ...; Bessel weights by backward recurrence
+                    for (int pbase = 0; UNI(pbase < q); pbase += 32) {
+                        const int p = pbase + lane;
+                        const bool act = p < q;
+                        const double tau = act ? ((nsub == 1) ? P.times[kidx + 1 + p] - t0 : tau_end) : 0.0;
+                        const double z = tau * Rb;
+                        const bool direct = !(z >= 1e-40);
+                        int Kp = 0;
+                        if (act && !direct) { Kp = cheb_terms(tau * Sb); if (Kp > Kc) Kp = Kc; }
+                        const int kmax = __reduce_max_sync(0xffffffffu, Kp);
+                        const double tz = direct ? 0.0 : 2.0 / z;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+                        for (int k = kmax; k >= 1; --k) {
+                            if (k == Kp) jn = 1.0;
+                            const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
+                            const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
+                            a0 = fma(jn, ta.x, a0); a1 = fma(jn, ta.y, a1); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            if (!(k & 1)) ssum += jn;
+                            const double jm = fma((double)k * tz, jn, -jn1);
+                            jn1 = jn; jn = jm;
+                        }
+                        const double2 ta = *reinterpret_cast<const double2*>(&S.tr[0]);
+                        const double2 tb = *reinterpret_cast<const double2*>(&S.tr[2]);
+                        double r[4];
+                        if (direct) {
+                            r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
+                        } else {
+                            const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
+                            r[0] = fma(2.0, a0, jn * ta.x) * nrm; r[1] = fma(2.0, a1, jn * ta.y) * nrm;
+                            r[2] = fma(2.0, a2, jn * tb.x) * nrm; r[3] = fma(2.0, a3, jn * tb.y) * nrm;
+                        }
+                        if (act) finish_output(kidx + 1 + p, r);
+                    }
+                    __syncwarp();
+                }
+            }
+            kidx += q;
+        }
+        } else {
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
             int q, nsub;
@@ -498,139 +906,22 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                 x_re[I][J][e] = W0[I][J][e] * v_re[I][J][e];
                                 x_im[I][J][e] = W0[I][J][e] * v_im[I][J][e];
                             }
-                    {
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    if (TL == 2) {
-                                        x_re[I][J][e] = fma(F3[I][J], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
-                                        x_im[I][J][e] = fma(F3[I][J], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
-                                    }
-                                }
-                    }
-                    {
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), x_re[I][J][e]);
-                                    x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), x_im[I][J][e]);
-                                }
-                    }
-                    {
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), x_re[I][J][e]);
-                                    x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), x_im[I][J][e]);
-                                }
-                    }
-                    {
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), x_re[I][J][e]);
-                                    x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), x_im[I][J][e]);
-                                }
-                    }
-                    // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
-                    //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        if (!REAL_H) {
-#pragma unroll
-                            for (int J = 0; J < TL; ++J) {
-                                const double b_re = v_re[J][ks >> 1][ks & 1];
-                                const double nb_im = neg(v_im[J][ks >> 1][ks & 1]);
-#pragma unroll
-                                for (int I = 0; I < TL; ++I) {
-                                    dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
-                                    dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], nb_im);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int J = 0; J < TL; ++J) {
-                            const double b_re = v_re[J][ks >> 1][ks & 1];
-                            const double b_im = v_im[J][ks >> 1][ks & 1];
-#pragma unroll
-                            for (int I = 0; I < TL; ++I) {
-                                dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
-                                dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
-                            }
-                        }
-                    }
+                    apply_rest(v_re, v_im, x_re, x_im);
                     // ---- u_{j+1} = X' + X'^dag;  term_{j+1} = u_{j+1} / (j+1)!
                     cfac *= INV_TABLE[j];
                     thr *= (double)(j + 1);
                     unsigned mx = 0;
                     double w_re[TL][TL][2], w_im[TL][TL][2];
-                    if constexpr (TL == 2) {     // d = 16: shuffles (measured 1 % faster than the shared-memory route)
-#pragma unroll
-                    for (int I = 0; I < TL; ++I)
-#pragma unroll
-                        for (int J = 0; J < TL; ++J) {
-                            // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I) with shuffles
-                            const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
-                            const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
-                            const double rAr = shfl(sAr, srcA), rBr = shfl(sBr, srcB);
-                            const double rAi = shfl(sAi, srcA), rBi = shfl(sBi, srcB);
-                            const double t_re[2] = {gp ? rBr : rAr, gp ? rAr : rBr};
-                            const double t_im[2] = {gp ? rBi : rAi, gp ? rAi : rBi};
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const double wr = x_re[I][J][e] + t_re[e];
-                                const double wi = x_im[I][J][e] - t_im[e];
-                                w_re[I][J][e] = wr; w_im[I][J][e] = wi;
-                                mx = max(mx, (unsigned)__double2hiint(wr) & 0x7fffffffu);
-                                mx = max(mx, (unsigned)__double2hiint(wi) & 0x7fffffffu);
-                            }
-                        }
-                    } else {                     // d = 8: issue-bound, the shared-memory route saves ~90 instructions (+5 %)
-                    // X'^dag through shared memory: element (R, C) of X' is stored at C*16 + (R ^ m(C)) with the swizzle
-                    // m(C) = 4*bit1(C) + 8*(bit2(C) ^ bit0(C)), which makes both the STS.64 of the accumulator
-                    // fragments and the LDS.128 of the transposed pairs bank-conflict free.
+                    symmetrise(x_re, x_im, w_re, w_im);
 #pragma unroll
                     for (int I = 0; I < TL; ++I)
 #pragma unroll
                         for (int J = 0; J < TL; ++J)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                const int Cc = 8 * J + 2 * t + e;
-                                const int m = 4 * (t & 1) + 8 * (((t >> 1) & 1) ^ e);
-                                S.xt_re[Cc * 16 + ((8 * I + g) ^ m)] = x_re[I][J][e];
-                                S.xt_im[Cc * 16 + ((8 * I + g) ^ m)] = x_im[I][J][e];
+                                mx = max(mx, (unsigned)__double2hiint(w_re[I][J][e]) & 0x7fffffffu);
+                                mx = max(mx, (unsigned)__double2hiint(w_im[I][J][e]) & 0x7fffffffu);
                             }
-                    __syncwarp();
-#pragma unroll
-                    for (int I = 0; I < TL; ++I)
-#pragma unroll
-                        for (int J = 0; J < TL; ++J) {
-                            const int m = 4 * ((g >> 1) & 1) + 8 * (((g >> 2) & 1) ^ (g & 1));
-                            const int o = (8 * I + g) * 16 + ((8 * J + 2 * t) ^ m);
-                            const double2 tr_ = *reinterpret_cast<const double2*>(&S.xt_re[o]);
-                            const double2 ti_ = *reinterpret_cast<const double2*>(&S.xt_im[o]);
-                            const double wr0 = x_re[I][J][0] + tr_.x, wr1 = x_re[I][J][1] + tr_.y;
-                            const double wi0 = x_im[I][J][0] - ti_.x, wi1 = x_im[I][J][1] - ti_.y;
-                            w_re[I][J][0] = wr0; w_re[I][J][1] = wr1; w_im[I][J][0] = wi0; w_im[I][J][1] = wi1;
-                            mx = max(mx, (unsigned)__double2hiint(wr0) & 0x7fffffffu);
-                            mx = max(mx, (unsigned)__double2hiint(wr1) & 0x7fffffffu);
-                            mx = max(mx, (unsigned)__double2hiint(wi0) & 0x7fffffffu);
-                            mx = max(mx, (unsigned)__double2hiint(wi1) & 0x7fffffffu);
-                        }
-                    __syncwarp();
-                    }
 #pragma unroll
                     for (int I = 0; I < TL; ++I)
 #pragma unroll
@@ -657,6 +948,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             kidx += q;
         }
 
+        }
+
         // ---- K5: loss, fixed-order warp reduction
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
@@ -668,8 +961,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-#define EML_WARP_INST(TL, RH) template __global__ void eval_warp_mma_kernel<TL, RH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
-EML_WARP_INST(1, true) EML_WARP_INST(1, false) EML_WARP_INST(2, true) EML_WARP_INST(2, false)
+#define EML_WARP_INST(TL, RH, CH) template __global__ void eval_warp_mma_kernel<TL, RH, CH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+EML_WARP_INST(1, true, false) EML_WARP_INST(1, false, false) EML_WARP_INST(2, true, false) EML_WARP_INST(2, false, false)
+EML_WARP_INST(1, true, true) EML_WARP_INST(1, false, true) EML_WARP_INST(2, true, true) EML_WARP_INST(2, false, true)
 
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -706,9 +1000,25 @@ static cudaError_t init_inv_table() {
     return e;
 }
 
+// largest z = tau (A + B) whose Chebyshev series fits `cap` terms
+static double cheb_zcap_for(int cap) {
+    double z = (double)cap;
+    while (z > 0.0 && std::ceil(z + CHEB_C1 * std::cbrt(z) + CHEB_C0) > (double)cap) z -= 0.25;
+    return z;
+}
+
+using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
+                          unsigned int*, const int*, const double);
+
+template <int TL, bool CH>
+static WarpKern pick_kernel(bool real_h, size_t& smem) {
+    smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH>);
+    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH> : (WarpKern)eval_warp_mma_kernel<TL, false, CH>;
+}
+
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
-                            bool real_h, const int* cost_hint, cudaStream_t stream) {
+                            bool real_h, bool chebyshev, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -721,18 +1031,26 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         launch_model_order(P, n_models, params, order, cost_hint, stream);
         use_order = order;
     }
-    using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
-                          unsigned int*, const int*);
-    const Kern kern = (P.n_tls == 4) ? (real_h ? (Kern)eval_warp_mma_kernel<2, true> : (Kern)eval_warp_mma_kernel<2, false>)
-                                     : (real_h ? (Kern)eval_warp_mma_kernel<1, true> : (Kern)eval_warp_mma_kernel<1, false>);
-    int per_sm = 1;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, 0)) != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    const bool tl2 = (P.n_tls == 4);
+    size_t smem = 0;
+    const WarpKern kern = tl2 ? (chebyshev ? pick_kernel<2, true>(real_h, smem) : pick_kernel<2, false>(real_h, smem))
+                              : (chebyshev ? pick_kernel<1, true>(real_h, smem) : pick_kernel<1, false>(real_h, smem));
+    // per device and kernel variant: dynamic shared memory opt-in and the resident CTAs per SM
+    static int per_sm_cache[64][8] = {{0}};
+    const int variant = (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
+    int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
+    if (per_sm == 0) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        if (dev < 64) per_sm_cache[dev][variant] = per_sm;
+    }
     long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
     if (ctas > max_ctas) ctas = max_ctas;
-    kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
-                                                           use_order);
+    const double zcap = chebyshev ? cheb_zcap_for(tl2 ? CHEB_KCAP_TL2 : CHEB_KCAP_TL1) : 0.0;
+    kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
+                                                              use_order, zcap);
     return cudaGetLastError();
 }
 

@@ -228,11 +228,13 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
       warp_mma: one complex d^3 product on the DMMA pipe (rho Hermitian => rho G^dag = (G rho)^dag),
                 the X + X^dag combine, n REAL-weighted site stencils, scale and accumulate;
       warp_mma_realH: the same with a real Hamiltonian, where only G.im = -H needs the DMMA pipe.
+      warp_cheb*: the same application inside the Chebyshev recurrence (the scale and accumulate of the Taylor
+                series become the fused + phi_{k-1}/2 and the halving of the stored term).
     """
     d = 2 ** n_tls
     if kernel_name == 'generic':
         return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
-    if kernel_name in ('warp_mma', 'warp_mma_realH', 'cta_mma', 'cta_mma_realH'):
+    if kernel_name in ('warp_mma', 'warp_mma_realH', 'warp_cheb', 'warp_cheb_realH', 'cta_mma', 'cta_mma_realH'):
         # DMMA: 4 (complex H) or 2 (real H: G.re diagonal, folded into the stencil) real d^3 products;
         # per complex element: diagonal weight 2, n site stencils 4n, X + X^dag 2, scale 2, accumulate 2
         mma = (2.0 if kernel_name.endswith('realH') else 4.0) * 2.0 * d ** 3

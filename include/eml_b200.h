@@ -97,8 +97,10 @@ typedef struct EmlOptions {
 
 #define EML_KERNEL_AUTO 0
 #define EML_KERNEL_GENERIC 1 /* one CTA per model, rho in shared memory, FP64 FMA */
-#define EML_KERNEL_WARP_MMA 2 /* one warp per model, rho in registers, FP64 DMMA (n_tls <= 4) */
+#define EML_KERNEL_WARP_MMA 2 /* one warp per model, rho in registers, FP64 DMMA (n_tls <= 4), Taylor series with dense output */
 #define EML_KERNEL_CTA_MMA 3  /* four warps per model, FP64 DMMA, terms exchanged through shared memory (n_tls == 5) */
+#define EML_KERNEL_WARP_CHEB 4 /* the warp kernel with the Chebyshev (Bessel-coefficient) series: one recurrence serves
+                                  every output time of a macro step; the default for n_tls <= 4 */
 
 int eml_version(void);
 const char* eml_last_error_string(void);

@@ -146,7 +146,8 @@ def use_kernel():
 
     def select(name):
         engine.default_kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC,
-                                 'warp_mma': _native.KERNEL_WARP_MMA, 'cta_mma': _native.KERNEL_CTA_MMA}[name]
+                                 'warp_mma': _native.KERNEL_WARP_MMA, 'cta_mma': _native.KERNEL_CTA_MMA,
+                                 'warp_cheb': _native.KERNEL_WARP_CHEB}[name]
         engine.clear_contexts()
     yield select
     engine.default_kernel = saved
@@ -168,7 +169,7 @@ def _d16_specs():
     return specs
 
 
-@pytest.mark.parametrize('kernel', ['warp_mma', 'generic'])
+@pytest.mark.parametrize('kernel', ['warp_cheb', 'warp_mma', 'generic'])
 def test_d16_kernels_match_oracle(use_kernel, kernel):
     from effective_model_learning_b200 import engine
     use_kernel(kernel)
@@ -184,15 +185,16 @@ def test_d16_kernels_match_oracle(use_kernel, kernel):
     print(f'{kernel}: worst abs err {worst:.2e}')
 
 
-def test_warp_mma_nonuniform_grid_long_steps_and_complex_observables(use_kernel):
-    use_kernel('warp_mma')
+@pytest.mark.parametrize('kernel', ['warp_cheb', 'warp_mma'])
+def test_warp_kernels_nonuniform_grid_long_steps_and_complex_observables(use_kernel, kernel):
+    use_kernel(kernel)
     rng = np.random.default_rng(4)
     ts = np.sort(np.concatenate([[0.1], 0.1 + np.cumsum(rng.uniform(1e-4, 0.3, 60)), [40.0]]))
     ts[20] = ts[19]
     for spec in _d16_specs()[10:]:
         m = model_from_spec(spec)
         obs = ['sigmap', 'exc', 'sigmay']
-        assert_close(m.calculate_dynamics(ts, obs), lo.expect_exact(spec, ts, obs), TOL, 'warp_mma non-uniform')
+        assert_close(m.calculate_dynamics(ts, obs), lo.expect_exact(spec, ts, obs), TOL, f'{kernel} non-uniform')
 
 
 def test_warp_mma_loss_and_batch_equals_generic(use_kernel):
@@ -202,16 +204,17 @@ def test_warp_mma_loss_and_batch_equals_generic(use_kernel):
     models = [model_from_spec(s) for s in specs]
     targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
     out = {}
-    for kernel in ('generic', 'warp_mma'):
+    for kernel in ('generic', 'warp_mma', 'warp_cheb'):
         use_kernel(kernel)
         out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
-    assert np.abs(out['generic'][0] - out['warp_mma'][0]).max() < 1e-10
-    np.testing.assert_allclose(out['generic'][1], out['warp_mma'][1], rtol=1e-9, atol=1e-14)
+    for kernel in ('warp_mma', 'warp_cheb'):
+        assert np.abs(out['generic'][0] - out[kernel][0]).max() < 1e-10, kernel
+        np.testing.assert_allclose(out['generic'][1], out[kernel][1], rtol=1e-9, atol=1e-14)
     want = np.array([lo.total_dev(lo.expect_exact(s, ts, OBS3), list(targets), len(ts)) for s in specs[:8]])
-    np.testing.assert_allclose(out['warp_mma'][1][:8], want, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(out['warp_cheb'][1][:8], want, rtol=1e-8, atol=1e-14)
 
 
-@pytest.mark.parametrize('kernel', ['warp_mma', 'generic'])
+@pytest.mark.parametrize('kernel', ['warp_cheb', 'warp_mma', 'generic'])
 @pytest.mark.parametrize('QD', [(1, 0), (1, 1), (1, 2)])
 def test_small_models_both_kernels(use_kernel, kernel, QD):
     """d = 2, 4 (embedded into 3 sites by the warp kernel) and d = 8, incl. qubit-not-first and sigma-/+ jumps."""
@@ -242,11 +245,12 @@ def test_d8_batch_loss_equals_generic(use_kernel):
     models = [model_from_spec(s) for s in specs]
     targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
     out = {}
-    for kernel in ('generic', 'warp_mma'):
+    for kernel in ('generic', 'warp_mma', 'warp_cheb'):
         use_kernel(kernel)
         out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
-    assert np.abs(out['generic'][0] - out['warp_mma'][0]).max() < 1e-10
-    np.testing.assert_allclose(out['generic'][1], out['warp_mma'][1], rtol=1e-9, atol=1e-14)
+    for kernel in ('warp_mma', 'warp_cheb'):
+        assert np.abs(out['generic'][0] - out[kernel][0]).max() < 1e-10, kernel
+        np.testing.assert_allclose(out['generic'][1], out[kernel][1], rtol=1e-9, atol=1e-14)
 
 
 def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use_kernel):
@@ -256,7 +260,7 @@ def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use
     spec = lo.random_library_spec(np.random.default_rng(1), 1, 3)
     m = model_from_spec(spec)
     m.calculate_dynamics(ts, OBS3)
-    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'warp_mma_realH'
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'warp_cheb_realH'
     spec['tls'][0]['couplings'].append((1, 0.7, [('sigmap', 'sigmam')]))      # non-Hermitian H
     m = model_from_spec(spec)
     got = m.calculate_dynamics(ts, OBS3)
@@ -381,7 +385,7 @@ def test_c_abi_edge_cases_and_error_codes():
         _native.Plan(6, 0, [], op_table, np.eye(64), 0, obs, ts)
     with pytest.raises(RuntimeError, match='n_obs'):
         _native.Plan(2, 3, terms, op_table, rho0, 0, np.stack([ops['id2']] * 9), ts)
-    with pytest.raises(RuntimeError, match='warp_mma'):
+    with pytest.raises(RuntimeError, match='warp kernels'):
         _native.Plan(5, 0, [], op_table, np.eye(32) / 32, 0, obs, ts, kernel=_native.KERNEL_WARP_MMA)
 
 
