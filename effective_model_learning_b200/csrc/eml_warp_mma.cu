@@ -28,6 +28,7 @@
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
 #include <cmath>
+#include <type_traits>
 #include "eml_common.cuh"
 
 namespace eml {
@@ -80,6 +81,12 @@ __constant__ double INV_TABLE[MCAP + 2];
 #define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// v * 2^-1 (hsub = 0x00100000) or v (hsub = 0) on the integer pipe; zeros and the very smallest numbers pass unchanged
+__device__ __forceinline__ double scale_pow2(double v, int hsub) {
+    const int hi = __double2hiint(v);
+    const bool ok = (unsigned)(hi & 0x7fffffff) > 0x001fffffu;
+    return __hiloint2double(ok ? hi - hsub : hi, __double2loint(v));
+}
 __device__ __forceinline__ double neg(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 
 // host-side structural test of the jump operators: A (x) conj(A) restricted to diag / both-flipped, real
@@ -700,6 +707,25 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             }
             f2 *= sc; f1 *= sc; f0[0] *= sc; f0[1] *= sc;
         }
+        // 2x2 partial trace of a term straight into shared memory (dst[0..3] = rho00, rho11, Re rho01, Im rho01).  d = 16:
+        // only the 8 lanes 4g + (g >> 1) hold partial-trace elements; a 3-stage reduce-scatter among exactly those lanes
+        // (4 double shuffles) leaves value 2*bit2(g) + bit1(g) in the lanes with g even.
+        const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
+        auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], double* dst) {
+            if constexpr (TL == 2) {
+                const double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
+                const double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
+                const bool hb = g & 4, mb = g & 2;
+                const double r0 = shfl(hb ? v0 : v2, dl4), r1 = shfl(hb ? v1 : v3, dl4);
+                const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
+                const double kk = (mb ? k1 : k0) + shfl(mb ? k0 : k1, dl2);
+                const double tot = kk + shfl(kk, dl1);
+                if (diag_lane && !(g & 1)) dst[(g >> 1)] = tot;
+            } else {
+                const double trv = partial_trace(xr, xi);
+                if ((lane & 7) == 0) dst[lane >> 3] = trv;
+            }
+        };
         double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
         auto cheb_terms = [](const double z) { return (int)ceil(z + CHEB_C1 * cbrt(z) + CHEB_C0); };
 
@@ -736,7 +762,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     const double tz = 2.0 / (tau_end * Rb);
                     double jn = 1.0, jn1 = 0.0, ssum = 0.0;
                     for (int k = Kc; k >= 1; --k) {
-                        if ((k & 31) == lane) cJ[k] = 2.0 * jn;
+                        if ((k & 31) == lane) cJ[k] = jn;
                         if (!(k & 1)) ssum += jn;
                         const double jm = fma((double)k * tz, jn, -jn1);
                         jn1 = jn; jn = jm;
@@ -752,55 +778,55 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            v_re[I][J][e] = 0.5 * acc_re[I][J][e]; v_im[I][J][e] = 0.5 * acc_im[I][J][e];   // phi_1 = (2 At)(phi_0 / 2)
+                            v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e];
                             ph_re[I][J][e] = 0.0; ph_im[I][J][e] = 0.0;
                             acc_re[I][J][e] = 0.0; acc_im[I][J][e] = 0.0;
                         }
-                double hs = 1.0, ts = 2.0;     // phi_{k-1} / 2 from the stored input; the k = 0 input is phi_0 / 2
-                for (int k = 0; UNI(k < Kc); ++k) {
-                    {   // partial trace of phi_k (independent of the DMMAs below)
-                        const double trv = partial_trace(v_re, v_im) * ts;
-                        if ((lane & 7) == 0) S.tr[k * 4 + (lane >> 3)] = trv;
-                    }
-                    if (need_acc) {
-                        const double c = cJ[k] * cscale * ts;
+                // Iteration 0 takes v = phi_0 with nothing added and gives 2 phi_1; from then on the stored input is halved
+                // (exponent decrement on the integer pipe) to supply phi_{k-1} / 2 ... so every term k >= 1 is carried
+                // DOUBLED, which is exactly the factor 2 of the series: the weights are plain J_k for all k.
+                auto run_terms = [&](auto na_tag) {
+                    constexpr bool NA = decltype(na_tag)::value;     // accumulate the state at the step end
+                    int hsub = 0;
+                    for (int k = 0; UNI(k < Kc); ++k) {
+                        trace_store(v_re, v_im, &S.tr[k * 4]);       // partial trace of term k (overlaps the DMMAs below)
+                        if constexpr (NA) {
+                            const double c = cJ[k] * cscale;
+#pragma unroll
+                            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                                for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
+                                        acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
+                                    }
+                        }
+                        double x_re[TL][TL][2], x_im[TL][TL][2], w_re[TL][TL][2], w_im[TL][TL][2];
 #pragma unroll
                         for (int I = 0; I < TL; ++I)
 #pragma unroll
                             for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
-                                    acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
-                                    acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
+                                    x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
+                                    x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
                                 }
+                        apply_rest(v_re, v_im, x_re, x_im);
+                        symmetrise(x_re, x_im, w_re, w_im);       // (2 At) v + (previous term)
+#pragma unroll
+                        for (int I = 0; I < TL; ++I)
+#pragma unroll
+                            for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    ph_re[I][J][e] = scale_pow2(v_re[I][J][e], hsub); ph_im[I][J][e] = scale_pow2(v_im[I][J][e], hsub);
+                                    v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
+                                }
+                        hsub = 0x00100000;
                     }
-                    double x_re[TL][TL][2], x_im[TL][TL][2], w_re[TL][TL][2], w_im[TL][TL][2];
-#pragma unroll
-                    for (int I = 0; I < TL; ++I)
-#pragma unroll
-                        for (int J = 0; J < TL; ++J)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
-                                x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
-                            }
-                    apply_rest(v_re, v_im, x_re, x_im);
-                    symmetrise(x_re, x_im, w_re, w_im);       // phi_{k+1} = (2 At) v + phi_{k-1}
-#pragma unroll
-                    for (int I = 0; I < TL; ++I)
-#pragma unroll
-                        for (int J = 0; J < TL; ++J)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                ph_re[I][J][e] = hs * v_re[I][J][e]; ph_im[I][J][e] = hs * v_im[I][J][e];
-                                v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
-                            }
-                    hs = 0.5; ts = 1.0;
-                }
-                {   // the last term
-                    const double trv = partial_trace(v_re, v_im);
-                    if ((lane & 7) == 0) S.tr[Kc * 4 + (lane >> 3)] = trv;
-                    if (need_acc) {
+                    trace_store(v_re, v_im, &S.tr[Kc * 4]);          // the last term
+                    if constexpr (NA) {
                         const double c = cJ[Kc] * cscale;
 #pragma unroll
                         for (int I = 0; I < TL; ++I)
@@ -812,7 +838,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                     acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
                                 }
                     }
-                    // a non-finite last term means the enclosure failed: report instead of returning garbage
+                };
+                if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
+                {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
                     const double chk = fabs(v_re[0][0][0]) + fabs(v_im[0][0][0]) + fabs(v_re[TL - 1][TL - 1][1]);
                     if (!UNI(chk < 1e300)) capped = true;
                 }
@@ -831,6 +859,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         const int kmax = __reduce_max_sync(0xffffffffu, Kp);
                         const double tz = direct ? 0.0 : 2.0 / z;
                         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+#pragma unroll 2
                         for (int k = kmax; k >= 1; --k) {
                             if (k == Kp) jn = 1.0;
                             const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
@@ -847,8 +876,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
                         } else {
                             const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
-                            r[0] = fma(2.0, a0, jn * ta.x) * nrm; r[1] = fma(2.0, a1, jn * ta.y) * nrm;
-                            r[2] = fma(2.0, a2, jn * tb.x) * nrm; r[3] = fma(2.0, a3, jn * tb.y) * nrm;
+                            r[0] = fma(jn, ta.x, a0) * nrm; r[1] = fma(jn, ta.y, a1) * nrm;
+                            r[2] = fma(jn, tb.x, a2) * nrm; r[3] = fma(jn, tb.y, a3) * nrm;
                         }
                         if (act) finish_output(kidx + 1 + p, r);
                     }
