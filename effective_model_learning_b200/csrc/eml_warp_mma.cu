@@ -732,8 +732,14 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
             const double t0 = P.times[kidx];
-            int q = 0;
-            while (UNI(kidx + q + 1 <= T - 1 && P.times[kidx + q + 1] - t0 <= tau_max)) ++q;
+            int q = 0;      // output times within tau_max of t0: 32 candidates per ballot
+            for (;;) {
+                const int cand = kidx + q + 1 + lane;
+                const unsigned in = __ballot_sync(0xffffffffu, cand <= T - 1 && P.times[min(cand, T - 1)] - t0 <= tau_max);
+                const int run = __ffs(~in) - 1;       // leading run of accepted candidates (-1: all 32)
+                if (run >= 0) { q += run; break; }
+                q += 32;
+            }
             int nsub = 1;
             if (UNI(q == 0)) { nsub = (int)ceil((P.times[kidx + 1] - t0) / tau_max); q = 1; }
             const double tau_end = (P.times[kidx + q] - t0) / nsub;
@@ -859,14 +865,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         const int kmax = __reduce_max_sync(0xffffffffu, Kp);
                         const double tz = direct ? 0.0 : 2.0 / z;
                         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+                        double kd = (double)kmax;
 #pragma unroll 2
-                        for (int k = kmax; k >= 1; --k) {
+                        for (int k = kmax; k >= 1; --k, kd -= 1.0) {
                             if (k == Kp) jn = 1.0;
                             const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
                             const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
                             a0 = fma(jn, ta.x, a0); a1 = fma(jn, ta.y, a1); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
                             if (!(k & 1)) ssum += jn;
-                            const double jm = fma((double)k * tz, jn, -jn1);
+                            const double jm = fma(kd * tz, jn, -jn1);
                             jn1 = jn; jn = jm;
                         }
                         const double2 ta = *reinterpret_cast<const double2*>(&S.tr[0]);
