@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get('EML_B200_LIB', os.path.join(_HERE, 'libeml_b200.so'))
 EML_OK = 0
 EML_ERR_NOT_CONVERGED = -4
 TERM_ENERGY, TERM_COUPLING, TERM_LINDBLAD = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA, KERNEL_CTA_MMA, KERNEL_WARP_CHEB = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA, KERNEL_CTA_MMA, KERNEL_WARP_CHEB, KERNEL_CTA_CHEB = 0, 1, 2, 3, 4, 5
 
 # every symbol include/eml_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',

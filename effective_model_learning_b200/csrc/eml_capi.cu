@@ -19,7 +19,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           const int* cost_hint, cudaStream_t stream);
+                           bool chebyshev, const int* cost_hint, cudaStream_t stream);
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
@@ -208,16 +208,16 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     int want = opts ? opts->kernel : EML_KERNEL_AUTO;
     if (want == EML_KERNEL_AUTO)
         want = eml::warp_mma_supported(plan->Pw, herm) ? EML_KERNEL_WARP_CHEB
-               : eml::cta_mma_supported(P, herm) ? EML_KERNEL_CTA_MMA : EML_KERNEL_GENERIC;
-    if (want == EML_KERNEL_CTA_MMA && !eml::cta_mma_supported(P, herm)) {
+               : eml::cta_mma_supported(P, herm) ? EML_KERNEL_CTA_CHEB : EML_KERNEL_GENERIC;
+    if ((want == EML_KERNEL_CTA_MMA || want == EML_KERNEL_CTA_CHEB) && !eml::cta_mma_supported(P, herm)) {
         eml_plan_destroy(plan);
-        return fail(EML_ERR_UNSUPPORTED, "cta_mma kernel needs n_tls == 5, Hermitian H and rho0, generalized-permutation jump operators");
+        return fail(EML_ERR_UNSUPPORTED, "cta kernels need n_tls == 5, Hermitian H and rho0, generalized-permutation jump operators");
     }
     if ((want == EML_KERNEL_WARP_MMA || want == EML_KERNEL_WARP_CHEB) && !eml::warp_mma_supported(plan->Pw, herm)) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_UNSUPPORTED, "warp kernels need n_tls <= 4, Hermitian H and rho0, generalized-permutation jump operators");
     }
-    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA && want != EML_KERNEL_CTA_MMA && want != EML_KERNEL_WARP_CHEB) {
+    if (want != EML_KERNEL_GENERIC && want != EML_KERNEL_WARP_MMA && want != EML_KERNEL_CTA_MMA && want != EML_KERNEL_WARP_CHEB && want != EML_KERNEL_CTA_CHEB) {
         eml_plan_destroy(plan);
         return fail(EML_ERR_INVALID_ARGUMENT, "unknown kernel id");
     }
@@ -235,6 +235,7 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
     if (plan->kernel == EML_KERNEL_WARP_CHEB) return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
     if (plan->kernel == EML_KERNEL_CTA_MMA) return plan->real_h ? "cta_mma_realH" : "cta_mma";
+    if (plan->kernel == EML_KERNEL_CTA_CHEB) return plan->real_h ? "cta_cheb_realH" : "cta_cheb";
     return "generic";
 }
 
@@ -261,9 +262,9 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
                                  plan->kernel == EML_KERNEL_WARP_CHEB,
                                  cost_hint, (cudaStream_t)stream);
-    else if (plan->kernel == EML_KERNEL_CTA_MMA)
+    else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
-                                plan->real_h, cost_hint, (cudaStream_t)stream);
+                                plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, cost_hint, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)

@@ -11,7 +11,9 @@
 // Two __syncthreads per application.  REAL_H as in the warp kernel (half the DMMAs when H is a real matrix).
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
+#include <type_traits>
 #include "eml_common.cuh"
+#include "eml_cheb.cuh"
 
 namespace eml {
 
@@ -20,16 +22,25 @@ constexpr int CMAXP = 192;
 constexpr int LDV = 40;       // row stride (doubles) of Vs: conflict-free LDS.128 over (g, t)
 constexpr int LDX = 34;       // column stride of Xs: conflict-free STS.64 over (g, t)
 
-struct CtaScratch {
+constexpr int CTA_CHEB_KCAP = 1024;   // Chebyshev terms per macro step that fit the trace table (32 KB)
+
+template <bool CHEB>
+struct alignas(16) CtaScratch {
+    static constexpr int KCAP = CHEB ? CTA_CHEB_KCAP : 0;
     double Vs_re[32 * LDV], Vs_im[32 * LDV];     // also hosts G during assembly: G_re = Vs_re (ld 40), G_im = Vs_im
     double Xs_re[32 * LDX], Xs_im[32 * LDX];
     double par[CMAXP];
     double jw[40];            // [bitpos 0..4][type (0 diag, 1 flip)][ra][ca]
-    double colsum[32];
+    double kd[10];            // [bitpos][ra]: diagonal of sum rate * A^dag A per site
+    double colsum[32], rowlo[32], diagh[32];
     double trp[4][4];         // per-warp partial traces: b0.re, b0.im, b1.re, b1.im
     double misc[4];
+    double lossw[4];
     unsigned int mxs[4];
     unsigned int fetch;
+    unsigned int pad_;
+    alignas(16) double tr[(KCAP + 1) * 4];       // partial traces of the Chebyshev terms (also scratch for the spread bound)
+    double cJ[KCAP + 1];                          // Bessel coefficients of the step end
 };
 
 #define CUNI(c) (__all_sync(0xffffffffu, (c)) != 0)
@@ -43,13 +54,16 @@ __device__ __forceinline__ void dmma_c(double& d0, double& d1, double a, double 
 }
 __device__ __forceinline__ double neg_c(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 
-template <bool REAL_H>
+template <bool REAL_H, bool CHEB>
 __global__ void __launch_bounds__(128, 2)
 eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                     const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
-                    int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order) {
+                    int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
+                    const double cheb_zcap) {
     constexpr int N = 5, D = 32;
-    __shared__ __align__(16) CtaScratch S;
+    extern __shared__ __align__(16) unsigned char cta_smem_raw[];
+    using Scratch = CtaScratch<CHEB>;
+    Scratch& S = *reinterpret_cast<Scratch*>(cta_smem_raw);
     const int tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -136,6 +150,21 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             }
             S.jw[e_] = wgt;
         }
+        if (CHEB && tid >= 32 && tid < 42) {
+            const int bp = (tid - 32) >> 1, ra = (tid - 32) & 1;
+            double kdv = 0.0;
+            for (int ti = 0; ti < P.n_terms; ++ti) {
+                const EmlTerm tm = P.terms[ti];
+                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
+                const double v = S.par[tm.param];
+                if (v == 0.0) continue;
+                for (int z = 0; z < 2; ++z) {
+                    const cplx m = ld_op(P.op_table, tm.op_a, z, ra);
+                    kdv += v * (m.re * m.re + m.im * m.im);
+                }
+            }
+            S.kd[tid - 32] = kdv;
+        }
         __syncthreads();
         if (tid < D) {
             double cs = 0.0;
@@ -193,7 +222,73 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         double f0[2] = {0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 0], 0.5 * S.jw[0 * 8 + 4 + (g & 1) * 2 + 1]};
         // the generator is kept pre-multiplied by the current step length (see eml_warp_mma.cu): u_{j+1} = (h L) u_j
         double h_cur = 1.0;
-        __syncthreads();     // G has been consumed: the Vs planes are free for the Taylor terms
+        // ---- Chebyshev enclosure (see eml_cheb.cuh): G is still in the Vs planes, Xs and the trace table are free
+        [[maybe_unused]] ChebPlan plan{};
+        if constexpr (CHEB) {
+            if (tid < D) {
+                double rad = 0.0;
+                for (int c = 0; c < D; ++c)
+                    if (c != tid) rad += REAL_H ? fabs(G_im[tid * LDV + c]) : hypot(G_re[tid * LDV + c], G_im[tid * LDV + c]);
+                const double ctr = -G_im[tid * LDV + tid];
+                S.colsum[tid] = ctr + rad; S.rowlo[tid] = ctr - rad; S.diagh[tid] = ctr;
+            }
+            __syncthreads();
+            double hi = -1e300, lo = 1e300, mu = 0.0;
+            for (int i = 0; i < D; ++i) { hi = fmax(hi, S.colsum[i]); lo = fmin(lo, S.rowlo[i]); mu += S.diagh[i]; }
+            mu *= 1.0 / D;
+            double spread = hi - lo;
+            // 2 rho(H - mu) <= 2 ||(H - mu)^8||_1^(1/8): three squarings, planes [re | im] of 32 x 32
+            double* Ma_re = S.Xs_re; double* Ma_im = S.Xs_im;
+            double* Mb_re = S.tr;    double* Mb_im = S.tr + D * D;
+            for (int i = tid; i < D * D; i += 128) {
+                const int r = i / D, c = i % D;
+                Ma_re[i] = -G_im[r * LDV + c] - ((r == c) ? mu : 0.0);
+                if (!REAL_H) Ma_im[i] = (r == c) ? 0.0 : G_re[r * LDV + c];
+            }
+            __syncthreads();
+            for (int sq = 0; sq < 3; ++sq) {
+                for (int i = tid; i < D * D; i += 128) {
+                    const int r = i / D, c = i % D;
+                    double sre = 0.0, sim = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < D; ++k) {
+                        const double are = Ma_re[r * D + k], bre = Ma_re[k * D + c];
+                        sre = fma(are, bre, sre);
+                        if (!REAL_H) {
+                            const double aim = Ma_im[r * D + k], bim = Ma_im[k * D + c];
+                            sre = fma(-aim, bim, sre);
+                            sim = fma(are, bim, fma(aim, bre, sim));
+                        }
+                    }
+                    Mb_re[i] = sre;
+                    if (!REAL_H) Mb_im[i] = sim;
+                }
+                __syncthreads();
+                double* tmp = Ma_re; Ma_re = Mb_re; Mb_re = tmp;
+                tmp = Ma_im; Ma_im = Mb_im; Mb_im = tmp;
+            }
+            if (tid < D) {
+                double cs = 0.0;
+                for (int r = 0; r < D; ++r) cs += REAL_H ? fabs(Ma_re[r * D + tid]) : hypot(Ma_re[r * D + tid], Ma_im[r * D + tid]);
+                S.colsum[tid] = cs;
+            }
+            __syncthreads();
+            double cs = 0.0;
+            for (int i = 0; i < D; ++i) cs = fmax(cs, S.colsum[i]);
+            spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
+            double dlo, dhi, dasym;
+            cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
+            plan = cheb_make_plan(spread, dlo, dhi, dasym, P.times[T - 1] - P.times[0], cheb_zcap, Scratch::KCAP);
+            // generator -> 2 (L + ac) / R  (stencil weights are stored halved)
+            const double sc = 2.0 / plan.R;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) { a_re[ks] *= sc; a_im[ks] *= sc; }
+#pragma unroll
+            for (int J = 0; J < 4; ++J) { W0[J][0] = (W0[J][0] + 0.5 * plan.ac) * sc; W0[J][1] = (W0[J][1] + 0.5 * plan.ac) * sc; }
+            F4[0] *= sc; F4[1] *= sc; F3[0] *= sc; F3[1] *= sc;
+            f2 *= sc; f1 *= sc; f0[0] *= sc; f0[1] *= sc;
+        }
+        __syncthreads();     // G has been consumed: the Vs planes are free for the series terms
 
         // ---- state: this warp's rows of rho(t_k)
         double acc_re[4][2], acc_im[4][2];
@@ -273,10 +368,256 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             }
         };
 
+        // ---- generator application core, shared by both series.  Given x = (diagonal weight) * v (+ anything Hermitian / 2)
+        //      and v published in Vs: add the site stencils (J(v)/2) and G v on the DMMA pipe, publish X' in Xs.
+        auto apply_core = [&](const double (&v_re)[4][2], const double (&v_im)[4][2], double (&x_re)[4][2], double (&x_im)[4][2]) {
+#pragma unroll
+            for (int J = 0; J < 4; ++J) {
+                const int base = 8 * J + 2 * t;
+                // bit 4: (I^2, J^2); bit 3: (I^1, J^1); bit 2: (g^4, t^2); bit 1: (g^2, t^1); bit 0: (g^1, e^1)
+                const int o4 = (8 * (w ^ 2) + g) * LDV + 8 * (J ^ 2) + 2 * t;
+                const int o3 = (8 * (w ^ 1) + g) * LDV + 8 * (J ^ 1) + 2 * t;
+                const int o2 = (8 * w + (g ^ 4)) * LDV + 8 * J + 2 * (t ^ 2);
+                const int o1 = (8 * w + (g ^ 2)) * LDV + 8 * J + 2 * (t ^ 1);
+                const int o0 = (8 * w + (g ^ 1)) * LDV + base;
+                const double2 r4 = *reinterpret_cast<const double2*>(&S.Vs_re[o4]), i4 = *reinterpret_cast<const double2*>(&S.Vs_im[o4]);
+                const double2 r3 = *reinterpret_cast<const double2*>(&S.Vs_re[o3]), i3 = *reinterpret_cast<const double2*>(&S.Vs_im[o3]);
+                const double2 r2 = *reinterpret_cast<const double2*>(&S.Vs_re[o2]), i2 = *reinterpret_cast<const double2*>(&S.Vs_im[o2]);
+                const double2 r1 = *reinterpret_cast<const double2*>(&S.Vs_re[o1]), i1 = *reinterpret_cast<const double2*>(&S.Vs_im[o1]);
+                const double2 r0 = *reinterpret_cast<const double2*>(&S.Vs_re[o0]), i0 = *reinterpret_cast<const double2*>(&S.Vs_im[o0]);
+                const double w4 = F4[J >> 1], w3 = F3[J & 1];
+                x_re[J][0] = fma(w4, r4.x, x_re[J][0]); x_re[J][1] = fma(w4, r4.y, x_re[J][1]);
+                x_im[J][0] = fma(w4, i4.x, x_im[J][0]); x_im[J][1] = fma(w4, i4.y, x_im[J][1]);
+                x_re[J][0] = fma(w3, r3.x, x_re[J][0]); x_re[J][1] = fma(w3, r3.y, x_re[J][1]);
+                x_im[J][0] = fma(w3, i3.x, x_im[J][0]); x_im[J][1] = fma(w3, i3.y, x_im[J][1]);
+                x_re[J][0] = fma(f2, r2.x, x_re[J][0]); x_re[J][1] = fma(f2, r2.y, x_re[J][1]);
+                x_im[J][0] = fma(f2, i2.x, x_im[J][0]); x_im[J][1] = fma(f2, i2.y, x_im[J][1]);
+                x_re[J][0] = fma(f1, r1.x, x_re[J][0]); x_re[J][1] = fma(f1, r1.y, x_re[J][1]);
+                x_im[J][0] = fma(f1, i1.x, x_im[J][0]); x_im[J][1] = fma(f1, i1.y, x_im[J][1]);
+                x_re[J][0] = fma(f0[0], r0.y, x_re[J][0]); x_re[J][1] = fma(f0[1], r0.x, x_re[J][1]);   // e^1
+                x_im[J][0] = fma(f0[0], i0.y, x_im[J][0]); x_im[J][1] = fma(f0[1], i0.x, x_im[J][1]);
+            }
+            // B fragments: v[k][n] = conj(v[n][k]) with n = 8J+g (a row of warp J), k = pi(ks,t): read pairs
+            // (ks even, ks odd) = columns (2t, 2t+1) of column tile ks/2 with one LDS.128
+#pragma unroll
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) {
+                    const int o = (8 * J + g) * LDV + 8 * kt + 2 * t;
+                    const double2 br = *reinterpret_cast<const double2*>(&S.Vs_re[o]);
+                    const double2 bi = *reinterpret_cast<const double2*>(&S.Vs_im[o]);
+                    // X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
+                    if (!REAL_H) {
+                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt], br.x);
+                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt], neg_c(bi.x));
+                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt + 1], br.y);
+                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt + 1], neg_c(bi.y));
+                    }
+                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt], bi.x);
+                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt], br.x);
+                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt + 1], bi.y);
+                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt + 1], br.y);
+                }
+            // publish X' column-major so that the transpose is a vector load
+#pragma unroll
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    S.Xs_re[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_re[J][e];
+                    S.Xs_im[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_im[J][e];
+                }
+        };
+        // after a __syncthreads: w = X' + X'^dag,  X'^dag[8w+g][8J+2t+e] = conj(X'[8J+2t+e][8w+g])
+        auto transpose_add = [&](const double (&x_re)[4][2], const double (&x_im)[4][2], double (&w_re)[4][2], double (&w_im)[4][2]) {
+#pragma unroll
+            for (int J = 0; J < 4; ++J) {
+                const int o = (8 * w + g) * LDX + 8 * J + 2 * t;
+                const double2 tr_ = *reinterpret_cast<const double2*>(&S.Xs_re[o]);
+                const double2 ti_ = *reinterpret_cast<const double2*>(&S.Xs_im[o]);
+                w_re[J][0] = x_re[J][0] + tr_.x; w_re[J][1] = x_re[J][1] + tr_.y;
+                w_im[J][0] = x_im[J][0] - ti_.x; w_im[J][1] = x_im[J][1] - ti_.y;
+            }
+        };
+        // observables and loss of one output time from the reduced density matrix r = (rho00, rho11, Re rho01, Im rho01)
+        auto finish_output = [&](const int k, const double (&r)[4]) {
+            for (int m = 0; m < K; ++m) {
+                const double* O = P.obs + m * 8;
+                const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
+                const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
+                if (expect != nullptr) {
+                    double* e = expect + (((size_t)b * K + m) * T + k) * 2;
+                    e[0] = ere; e[1] = eim;
+                }
+                if (tgt != nullptr) {
+                    const double dre = ere - tgt[((size_t)m * T + k) * 2], dim = eim - tgt[((size_t)m * T + k) * 2 + 1];
+                    my_loss += dre * dre + dim * dim;
+                }
+            }
+        };
+
         partial_trace_store(acc_re, acc_im);
         __syncthreads();
         emit(1, 0, trace_total(), 0.0);
 
+        if constexpr (CHEB) {
+        const double Rb = plan.R, Sb = plan.S, ac = plan.ac, tau_max = plan.tau_max;
+        int kidx = 0;
+        while (kidx < T - 1) {           // every scalar below is computed identically by all threads
+            const double t0 = P.times[kidx];
+            int q = 0;
+            while (kidx + q + 1 <= T - 1 && P.times[kidx + q + 1] - t0 <= tau_max) ++q;
+            int nsub = 1;
+            if (q == 0) { nsub = (int)ceil((P.times[kidx + 1] - t0) / tau_max); q = 1; }
+            const double tau_end = (P.times[kidx + q] - t0) / nsub;
+            const bool final_step = (kidx + q == T - 1);
+            if (!(tau_end * Rb >= 1e-40)) {     // repeated time points: the state does not move
+                __syncthreads();
+                partial_trace_store(acc_re, acc_im);
+                __syncthreads();
+                const double r[4] = {S.trp[0][0] + S.trp[1][0], S.trp[2][2] + S.trp[3][2], S.trp[0][2] + S.trp[1][2],
+                                     S.trp[0][3] + S.trp[1][3]};
+                for (int p = tid; p < q; p += 128) finish_output(kidx + 1 + p, r);
+                kidx += q;
+                continue;
+            }
+            int Kc = cheb_terms(tau_end * Sb);
+            if (Kc > Scratch::KCAP) Kc = Scratch::KCAP;
+            for (int sub = 0; sub < nsub; ++sub) {
+                const bool last = (sub == nsub - 1);
+                const bool need_acc = !(final_step && last);
+                double cscale = 0.0;
+                __syncthreads();     // the previous step's readers of tr / cJ / trp are done
+                if (need_acc) {
+                    const double tz = 2.0 / (tau_end * Rb);
+                    double jn = 1.0, jn1 = 0.0, ssum = 0.0;
+                    for (int k = Kc; k >= 1; --k) {
+                        if ((k & 127) == tid) S.cJ[k] = jn;
+                        if (!(k & 1)) ssum += jn;
+                        const double jm = fma((double)k * tz, jn, -jn1);
+                        jn1 = jn; jn = jm;
+                    }
+                    if (tid == 0) S.cJ[0] = jn;
+                    cscale = exp(-ac * tau_end) / (2.0 * ssum + jn);
+                }
+                double v_re[4][2], v_im[4][2], ph_re[4][2], ph_im[4][2];
+#pragma unroll
+                for (int J = 0; J < 4; ++J)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        v_re[J][e] = acc_re[J][e]; v_im[J][e] = acc_im[J][e];
+                        ph_re[J][e] = 0.0; ph_im[J][e] = 0.0;
+                        acc_re[J][e] = 0.0; acc_im[J][e] = 0.0;
+                    }
+                auto run_terms = [&](auto na_tag) {
+                    constexpr bool NA = decltype(na_tag)::value;     // accumulate the state at the step end
+                    int hsub = 0;
+                    for (int k = 0; k <= Kc; ++k) {
+                        // ---- [A] publish term k: rows of this warp into Vs, per-warp partial trace
+                        if (k < Kc) {
+#pragma unroll
+                            for (int J = 0; J < 4; ++J) {
+                                *reinterpret_cast<double2*>(&S.Vs_re[(8 * w + g) * LDV + 8 * J + 2 * t]) = make_double2(v_re[J][0], v_re[J][1]);
+                                *reinterpret_cast<double2*>(&S.Vs_im[(8 * w + g) * LDV + 8 * J + 2 * t]) = make_double2(v_im[J][0], v_im[J][1]);
+                            }
+                        }
+                        partial_trace_store(v_re, v_im);
+                        __syncthreads();
+                        if (tid < 4) {   // rho00, rho11, Re rho01, Im rho01 (see trace_total)
+                            const int wa = (tid == 1) ? 2 : 0, ci = (tid == 0) ? 0 : (tid == 3) ? 3 : 2;
+                            S.tr[k * 4 + tid] = S.trp[wa][ci] + S.trp[wa + 1][ci];
+                        }
+                        if constexpr (NA) {
+                            const double c = S.cJ[k] * cscale;
+#pragma unroll
+                            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    acc_re[J][e] = fma(c, v_re[J][e], acc_re[J][e]);
+                                    acc_im[J][e] = fma(c, v_im[J][e], acc_im[J][e]);
+                                }
+                        }
+                        if (k == Kc) break;
+                        // ---- [B] accumulators = W0 v + (previous term) / 2, site stencils, G v; X' published in Xs
+                        double x_re[4][2], x_im[4][2];
+#pragma unroll
+                        for (int J = 0; J < 4; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                x_re[J][e] = fma(W0[J][e], v_re[J][e], ph_re[J][e]);
+                                x_im[J][e] = fma(W0[J][e], v_im[J][e], ph_im[J][e]);
+                            }
+                        apply_core(v_re, v_im, x_re, x_im);
+                        __syncthreads();
+                        // ---- [C] next term = X' + X'^dag
+#pragma unroll
+                        for (int J = 0; J < 4; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                ph_re[J][e] = scale_pow2(v_re[J][e], hsub); ph_im[J][e] = scale_pow2(v_im[J][e], hsub);
+                            }
+                        transpose_add(x_re, x_im, v_re, v_im);
+                        hsub = 0x00100000;
+                    }
+                };
+                if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
+                {   // a non-finite or absurd last term means the enclosure failed
+                    const double chk = fabs(v_re[0][0]) + fabs(v_im[0][0]) + fabs(v_re[3][1]);
+                    if (!(chk < 1e300)) capped = true;
+                }
+                n_apply += Kc;
+                __syncthreads();     // the trace table is complete
+                if (last) {
+                    // ---- outputs of the step: warp w takes the blocks of 32 outputs w, w + 4, ...
+                    for (int pbase = 32 * w; pbase < q; pbase += 128) {
+                        const int p = pbase + lane;
+                        const bool act = p < q;
+                        const double tau = act ? ((nsub == 1) ? P.times[kidx + 1 + p] - t0 : tau_end) : 0.0;
+                        const double z = tau * Rb;
+                        const bool direct = !(z >= 1e-40);
+                        int Kp = 0;
+                        if (act && !direct) { Kp = cheb_terms(tau * Sb); if (Kp > Kc) Kp = Kc; }
+                        const int kmax = __reduce_max_sync(0xffffffffu, Kp);
+                        const double tz = direct ? 0.0 : 2.0 / z;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+                        double kd = (double)kmax;
+#pragma unroll 2
+                        for (int k = kmax; k >= 1; --k, kd -= 1.0) {
+                            if (k == Kp) jn = 1.0;
+                            const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
+                            const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
+                            a0 = fma(jn, ta.x, a0); a1 = fma(jn, ta.y, a1); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            if (!(k & 1)) ssum += jn;
+                            const double jm = fma(kd * tz, jn, -jn1);
+                            jn1 = jn; jn = jm;
+                        }
+                        const double2 ta = *reinterpret_cast<const double2*>(&S.tr[0]);
+                        const double2 tb = *reinterpret_cast<const double2*>(&S.tr[2]);
+                        double r[4];
+                        if (direct) {
+                            r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
+                        } else {
+                            const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
+                            r[0] = fma(jn, ta.x, a0) * nrm; r[1] = fma(jn, ta.y, a1) * nrm;
+                            r[2] = fma(jn, tb.x, a2) * nrm; r[3] = fma(jn, tb.y, a3) * nrm;
+                        }
+                        if (act) finish_output(kidx + 1 + p, r);
+                    }
+                }
+            }
+            kidx += q;
+        }
+        // every warp produced outputs: combine the per-warp losses in a fixed order
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+        __syncthreads();
+        if (lane == 0) S.lossw[w] = my_loss;
+        __syncthreads();
+        my_loss = (S.lossw[0] + S.lossw[1]) + (S.lossw[2] + S.lossw[3]);
+        if (tid == 0) {
+            if (loss != nullptr) loss[b] = (tgt != nullptr) ? my_loss / ((double)T * (double)K) : 0.0;
+            if (status != nullptr) status[b] = capped ? -1 : n_apply;
+        }
+        } else {
         int kidx = 0;
         while (CUNI(kidx < T - 1)) {
             int q, nsub;
@@ -364,61 +705,7 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                             x_re[J][e] = W0[J][e] * v_re[J][e];
                             x_im[J][e] = W0[J][e] * v_im[J][e];
                         }
-#pragma unroll
-                    for (int J = 0; J < 4; ++J) {
-                        const int base = 8 * J + 2 * t;
-                        // bit 4: (I^2, J^2); bit 3: (I^1, J^1); bit 2: (g^4, t^2); bit 1: (g^2, t^1); bit 0: (g^1, e^1)
-                        const int o4 = (8 * (w ^ 2) + g) * LDV + 8 * (J ^ 2) + 2 * t;
-                        const int o3 = (8 * (w ^ 1) + g) * LDV + 8 * (J ^ 1) + 2 * t;
-                        const int o2 = (8 * w + (g ^ 4)) * LDV + 8 * J + 2 * (t ^ 2);
-                        const int o1 = (8 * w + (g ^ 2)) * LDV + 8 * J + 2 * (t ^ 1);
-                        const int o0 = (8 * w + (g ^ 1)) * LDV + base;
-                        const double2 r4 = *reinterpret_cast<const double2*>(&S.Vs_re[o4]), i4 = *reinterpret_cast<const double2*>(&S.Vs_im[o4]);
-                        const double2 r3 = *reinterpret_cast<const double2*>(&S.Vs_re[o3]), i3 = *reinterpret_cast<const double2*>(&S.Vs_im[o3]);
-                        const double2 r2 = *reinterpret_cast<const double2*>(&S.Vs_re[o2]), i2 = *reinterpret_cast<const double2*>(&S.Vs_im[o2]);
-                        const double2 r1 = *reinterpret_cast<const double2*>(&S.Vs_re[o1]), i1 = *reinterpret_cast<const double2*>(&S.Vs_im[o1]);
-                        const double2 r0 = *reinterpret_cast<const double2*>(&S.Vs_re[o0]), i0 = *reinterpret_cast<const double2*>(&S.Vs_im[o0]);
-                        const double w4 = F4[J >> 1], w3 = F3[J & 1];
-                        x_re[J][0] = fma(w4, r4.x, x_re[J][0]); x_re[J][1] = fma(w4, r4.y, x_re[J][1]);
-                        x_im[J][0] = fma(w4, i4.x, x_im[J][0]); x_im[J][1] = fma(w4, i4.y, x_im[J][1]);
-                        x_re[J][0] = fma(w3, r3.x, x_re[J][0]); x_re[J][1] = fma(w3, r3.y, x_re[J][1]);
-                        x_im[J][0] = fma(w3, i3.x, x_im[J][0]); x_im[J][1] = fma(w3, i3.y, x_im[J][1]);
-                        x_re[J][0] = fma(f2, r2.x, x_re[J][0]); x_re[J][1] = fma(f2, r2.y, x_re[J][1]);
-                        x_im[J][0] = fma(f2, i2.x, x_im[J][0]); x_im[J][1] = fma(f2, i2.y, x_im[J][1]);
-                        x_re[J][0] = fma(f1, r1.x, x_re[J][0]); x_re[J][1] = fma(f1, r1.y, x_re[J][1]);
-                        x_im[J][0] = fma(f1, i1.x, x_im[J][0]); x_im[J][1] = fma(f1, i1.y, x_im[J][1]);
-                        x_re[J][0] = fma(f0[0], r0.y, x_re[J][0]); x_re[J][1] = fma(f0[1], r0.x, x_re[J][1]);   // e^1
-                        x_im[J][0] = fma(f0[0], i0.y, x_im[J][0]); x_im[J][1] = fma(f0[1], i0.x, x_im[J][1]);
-                    }
-                    // B fragments: v[k][n] = conj(v[n][k]) with n = 8J+g (a row of warp J), k = pi(ks,t): read pairs
-                    // (ks even, ks odd) = columns (2t, 2t+1) of column tile ks/2 with one LDS.128
-#pragma unroll
-                    for (int J = 0; J < 4; ++J)
-#pragma unroll
-                        for (int kt = 0; kt < 4; ++kt) {
-                            const int o = (8 * J + g) * LDV + 8 * kt + 2 * t;
-                            const double2 br = *reinterpret_cast<const double2*>(&S.Vs_re[o]);
-                            const double2 bi = *reinterpret_cast<const double2*>(&S.Vs_im[o]);
-                            // X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
-                            if (!REAL_H) {
-                                dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt], br.x);
-                                dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt], neg_c(bi.x));
-                                dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt + 1], br.y);
-                                dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt + 1], neg_c(bi.y));
-                            }
-                            dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt], bi.x);
-                            dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt], br.x);
-                            dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt + 1], bi.y);
-                            dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt + 1], br.y);
-                        }
-                    // publish X' column-major so that the transpose is a vector load
-#pragma unroll
-                    for (int J = 0; J < 4; ++J)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            S.Xs_re[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_re[J][e];
-                            S.Xs_im[(8 * J + 2 * t + e) * LDX + 8 * w + g] = x_im[J][e];
-                        }
+                    apply_core(v_re, v_im, x_re, x_im);
                     __syncthreads();
 
                     // ---- [C] next term = f (X' + X'^dag):  X'^dag[8w+g][8J+2t+e] = conj(X'[8J+2t+e][8w+g])
@@ -426,21 +713,16 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                     thr *= (double)(j + 1);
                     thr_term = (unsigned)__double2hiint(thr) & 0x7fffffffu;
                     unsigned mxl = 0;
+                    transpose_add(x_re, x_im, v_re, v_im);
 #pragma unroll
-                    for (int J = 0; J < 4; ++J) {
-                        const int o = (8 * w + g) * LDX + 8 * J + 2 * t;
-                        const double2 tr_ = *reinterpret_cast<const double2*>(&S.Xs_re[o]);
-                        const double2 ti_ = *reinterpret_cast<const double2*>(&S.Xs_im[o]);
-                        const double wr0 = x_re[J][0] + tr_.x, wr1 = x_re[J][1] + tr_.y;
-                        const double wi0 = x_im[J][0] - ti_.x, wi1 = x_im[J][1] - ti_.y;
-                        v_re[J][0] = wr0; v_re[J][1] = wr1; v_im[J][0] = wi0; v_im[J][1] = wi1;
-                        acc_re[J][0] = fma(cfac, wr0, acc_re[J][0]); acc_re[J][1] = fma(cfac, wr1, acc_re[J][1]);
-                        acc_im[J][0] = fma(cfac, wi0, acc_im[J][0]); acc_im[J][1] = fma(cfac, wi1, acc_im[J][1]);
-                        mxl = max(mxl, (unsigned)__double2hiint(wr0) & 0x7fffffffu);
-                        mxl = max(mxl, (unsigned)__double2hiint(wr1) & 0x7fffffffu);
-                        mxl = max(mxl, (unsigned)__double2hiint(wi0) & 0x7fffffffu);
-                        mxl = max(mxl, (unsigned)__double2hiint(wi1) & 0x7fffffffu);
-                    }
+                    for (int J = 0; J < 4; ++J)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            acc_re[J][e] = fma(cfac, v_re[J][e], acc_re[J][e]);
+                            acc_im[J][e] = fma(cfac, v_im[J][e], acc_im[J][e]);
+                            mxl = max(mxl, (unsigned)__double2hiint(v_re[J][e]) & 0x7fffffffu);
+                            mxl = max(mxl, (unsigned)__double2hiint(v_im[J][e]) & 0x7fffffffu);
+                        }
                     mx_term = __reduce_max_sync(0xffffffffu, mxl);
                 }
                 n_apply += j;
@@ -458,11 +740,12 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                 if (status != nullptr) status[b] = capped ? -1 : n_apply;
             }
         }
+        }
     }
 }
 
-template __global__ void eval_cta_mma_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
-template __global__ void eval_cta_mma_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*);
+#define EML_CTA_INST(RH, CH) template __global__ void eval_cta_mma_kernel<RH, CH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+EML_CTA_INST(true, false) EML_CTA_INST(false, false) EML_CTA_INST(true, true) EML_CTA_INST(false, true)
 
 bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian && P.n_tls == 5 && P.n_params <= CMAXP; }
 
@@ -472,7 +755,7 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
 
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           const int* cost_hint, cudaStream_t stream) {
+                           bool chebyshev, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -492,12 +775,24 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
         launch_model_order(P, n_models, params, order, cost_hint, stream);
         use_order = order;
     }
+    using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
+                          const int*, const double);
+    const Kern kern = chebyshev ? (real_h ? (Kern)eval_cta_mma_kernel<true, true> : (Kern)eval_cta_mma_kernel<false, true>)
+                                : (real_h ? (Kern)eval_cta_mma_kernel<true, false> : (Kern)eval_cta_mma_kernel<false, false>);
+    const size_t smem = chebyshev ? sizeof(CtaScratch<true>) : sizeof(CtaScratch<false>);
+    static int per_sm_cache[64][4] = {{0}};
+    const int variant = (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
+    int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
+    if (per_sm == 0) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        if (dev < 64) per_sm_cache[dev][variant] = per_sm;
+    }
     long long ctas = n_models;
-    if (ctas > 2LL * sms) ctas = 2LL * sms;
-    if (real_h)
-        eval_cta_mma_kernel<true><<<(unsigned)ctas, 128, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order);
-    else
-        eval_cta_mma_kernel<false><<<(unsigned)ctas, 128, 0, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order);
+    if (ctas > (long long)per_sm * sms) ctas = (long long)per_sm * sms;
+    const double zcap = chebyshev ? cheb_zcap_for(CTA_CHEB_KCAP) : 0.0;
+    kern<<<(unsigned)ctas, 128, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order, zcap);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,7 @@
 #include <cmath>
 #include <type_traits>
 #include "eml_common.cuh"
+#include "eml_cheb.cuh"
 
 namespace eml {
 
@@ -48,8 +49,6 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 // Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26 KB at d = 16,
 // 16 warps x 13 KB at d <= 8), and the largest  tau * (A + B)  whose series fits (cheb_terms(z) <= cap)
 constexpr int CHEB_KCAP_TL2 = 640, CHEB_KCAP_TL1 = 256;
-constexpr double CHEB_C1 = 9.25, CHEB_C0 = 5.0;        // |J_k(z)| < 1e-14 for k >= z + C1 z^(1/3) + C0 (z <= 2000)
-constexpr double CHEB_HUMP = 14.0;                     // cap on tau * B: partial sums stay below e^14 (as theta = 16 did)
 
 template <int TL, bool CHEB>
 struct alignas(16) WarpScratch {
@@ -81,12 +80,6 @@ __constant__ double INV_TABLE[MCAP + 2];
 #define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-// v * 2^-1 (hsub = 0x00100000) or v (hsub = 0) on the integer pipe; zeros and the very smallest numbers pass unchanged
-__device__ __forceinline__ double scale_pow2(double v, int hsub) {
-    const int hi = __double2hiint(v);
-    const bool ok = (unsigned)(hi & 0x7fffffff) > 0x001fffffu;
-    return __hiloint2double(ok ? hi - hsub : hi, __double2loint(v));
-}
 __device__ __forceinline__ double neg(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 
 // host-side structural test of the jump operators: A (x) conj(A) restricted to diag / both-flipped, real
@@ -590,7 +583,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // range: Gershgorin on H for the commutator, per-site Gershgorin for the dissipator (real range [dlo, dhi],
         // centred by the shift ac; antisymmetric part added to the imaginary extent); the series is truncated for
         // the confocal ellipse (semi-axes A along the imaginary axis, B real) through the corner of that rectangle.
-        double spread, ac, ah, dasym = 0.0;
+        double spread, dlo, dhi, dasym;
         {
             double hi = -1e300, lo = 1e300;
             if (lane < D) {
@@ -651,48 +644,10 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
                 __syncwarp();
             }
-            double dlo = 0.0, dhi = 0.0;
-            for (int bp = 0; bp < N; ++bp) {
-                double slo = 1e300, shi = -1e300, sas = 0.0;
-#pragma unroll
-                for (int rc = 0; rc < 4; ++rc) {
-                    const int ra = rc >> 1, ca = rc & 1;
-                    const double dg = S.jw[bp * 8 + rc] - 0.5 * (S.kd[bp * 2 + ra] + S.kd[bp * 2 + ca]);
-                    const double fa = S.jw[bp * 8 + 4 + rc], fb = S.jw[bp * 8 + 4 + (3 - rc)];
-                    const double rad = 0.5 * fabs(fa + fb);
-                    slo = fmin(slo, dg - rad); shi = fmax(shi, dg + rad); sas = fmax(sas, 0.5 * fabs(fa - fb));
-                }
-                dlo += slo; dhi += shi; dasym += sas;
-            }
-            ac = -0.5 * (dlo + dhi); ah = 0.5 * (dhi - dlo);
+            cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
         }
-        const double yext = spread + dasym;
-        const double t_first = P.times[0];
-        const double span = P.times[T - 1] - t_first;
-        double Rb = 1.0, Sb = 1e300, Bb = 0.0;
-        {
-            bool have_ok = false;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const double delta = (i == 0) ? 0.03 : (i == 1) ? 0.06 : (i == 2) ? 0.12 : (i == 3) ? 0.25 : (i == 4) ? 0.5 : 1.0;
-                const double Rc = fmax(fmax(yext * (1.0 + delta), ah), 1e-3 / fmax(span, 1e-300));
-                const double cc = Rc * Rc - ah * ah - yext * yext, xr2 = ah * ah * Rc * Rc;
-                const double disc = sqrt(cc * cc + 4.0 * xr2);
-                const double u = (cc > 0.0) ? 2.0 * xr2 / (cc + disc) : 0.5 * (disc - cc);
-                const double Bc = sqrt(u), Ac = sqrt(u + Rc * Rc);
-                const bool ok = span * Bc <= CHEB_HUMP;
-                if ((ok && !have_ok) || (ok == have_ok && Ac + Bc < Sb)) { Rb = Rc; Sb = Ac + Bc; Bb = Bc; have_ok = ok; }
-            }
-        }
-        double tau_max = cheb_zcap / Sb;
-        if (Bb > 0.0) tau_max = fmin(tau_max, CHEB_HUMP / Bb);
-        {   // |phi_k| can grow like (S/R)^k: keep k log(S/R) below ~560 so that nothing overflows
-            const double lnr = log(Sb / Rb);
-            if (lnr * (double)Scratch::KCAP > 560.0) {
-                const double kall = 560.0 / lnr;
-                tau_max = fmin(tau_max, fmax(kall - CHEB_C1 * cbrt(kall) - CHEB_C0, 1.0) / Sb);
-            }
-        }
+        const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, P.times[T - 1] - P.times[0], cheb_zcap, Scratch::KCAP);
+        const double Rb = plan.R, Sb = plan.S, ac = plan.ac, tau_max = plan.tau_max;
         {   // generator -> 2 (L + ac) / R  (stencil weights are stored halved)
             const double sc = 2.0 / Rb;
 #pragma unroll
@@ -727,7 +682,6 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             }
         };
         double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
-        auto cheb_terms = [](const double z) { return (int)ceil(z + CHEB_C1 * cbrt(z) + CHEB_C0); };
 
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
@@ -1079,13 +1033,6 @@ static cudaError_t init_inv_table() {
     e = cudaMemcpyToSymbol(INV_TABLE, h, sizeof(h));
     if (e == cudaSuccess && dev < 64) done[dev] = true;
     return e;
-}
-
-// largest z = tau (A + B) whose Chebyshev series fits `cap` terms
-static double cheb_zcap_for(int cap) {
-    double z = (double)cap;
-    while (z > 0.0 && std::ceil(z + CHEB_C1 * std::cbrt(z) + CHEB_C0) > (double)cap) z -= 0.25;
-    return z;
 }
 
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,

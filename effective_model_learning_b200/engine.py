@@ -234,7 +234,8 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
     d = 2 ** n_tls
     if kernel_name == 'generic':
         return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
-    if kernel_name in ('warp_mma', 'warp_mma_realH', 'warp_cheb', 'warp_cheb_realH', 'cta_mma', 'cta_mma_realH'):
+    if kernel_name in ('warp_mma', 'warp_mma_realH', 'warp_cheb', 'warp_cheb_realH', 'cta_mma', 'cta_mma_realH',
+                       'cta_cheb', 'cta_cheb_realH'):
         # DMMA: 4 (complex H) or 2 (real H: G.re diagonal, folded into the stencil) real d^3 products;
         # per complex element: diagonal weight 2, n site stencils 4n, X + X^dag 2, scale 2, accumulate 2
         mma = (2.0 if kernel_name.endswith('realH') else 4.0) * 2.0 * d ** 3

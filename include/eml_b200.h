@@ -101,6 +101,7 @@ typedef struct EmlOptions {
 #define EML_KERNEL_CTA_MMA 3  /* four warps per model, FP64 DMMA, terms exchanged through shared memory (n_tls == 5) */
 #define EML_KERNEL_WARP_CHEB 4 /* the warp kernel with the Chebyshev (Bessel-coefficient) series: one recurrence serves
                                   every output time of a macro step; the default for n_tls <= 4 */
+#define EML_KERNEL_CTA_CHEB 5  /* the four-warp kernel with the Chebyshev series; the default for n_tls == 5 */
 
 int eml_version(void);
 const char* eml_last_error_string(void);

@@ -147,7 +147,7 @@ def use_kernel():
     def select(name):
         engine.default_kernel = {'auto': _native.KERNEL_AUTO, 'generic': _native.KERNEL_GENERIC,
                                  'warp_mma': _native.KERNEL_WARP_MMA, 'cta_mma': _native.KERNEL_CTA_MMA,
-                                 'warp_cheb': _native.KERNEL_WARP_CHEB}[name]
+                                 'warp_cheb': _native.KERNEL_WARP_CHEB, 'cta_cheb': _native.KERNEL_CTA_CHEB}[name]
         engine.clear_contexts()
     yield select
     engine.default_kernel = saved
@@ -318,7 +318,7 @@ def _d32_specs():
     return specs
 
 
-@pytest.mark.parametrize('kernel', ['cta_mma', 'generic'])
+@pytest.mark.parametrize('kernel', ['cta_cheb', 'cta_mma', 'generic'])
 def test_d32_kernels_match_oracle(use_kernel, kernel):
     from effective_model_learning_b200 import engine
     use_kernel(kernel)
@@ -343,11 +343,12 @@ def test_d32_batch_loss_equals_generic(use_kernel):
     models = [model_from_spec(s) for s in specs]
     targets = np.array([np.asarray(e) for e in lo.expect_exact(specs[0], ts, OBS3)]) + 0.01
     out = {}
-    for kernel in ('generic', 'cta_mma'):
+    for kernel in ('generic', 'cta_mma', 'cta_cheb'):
         use_kernel(kernel)
         out[kernel] = engine.evaluate_models(models, ts, OBS3, targets=targets)
-    assert np.abs(out['generic'][0] - out['cta_mma'][0]).max() < 1e-10
-    np.testing.assert_allclose(out['generic'][1], out['cta_mma'][1], rtol=1e-9, atol=1e-14)
+    for kernel in ('cta_mma', 'cta_cheb'):
+        assert np.abs(out['generic'][0] - out[kernel][0]).max() < 1e-10, kernel
+        np.testing.assert_allclose(out['generic'][1], out[kernel][1], rtol=1e-9, atol=1e-14)
 
 
 def test_c_abi_edge_cases_and_error_codes():
