@@ -280,7 +280,7 @@ def run_b200(args):
     barrier()
     st = status.cpu().numpy()
     if (st < 0).any():
-        raise RuntimeError('a model hit the Taylor cap during warm-up')
+        raise RuntimeError('a model was reported as not converged during warm-up')
     applications = float(st.sum())
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -369,7 +369,10 @@ def run_b200(args):
         'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'kernel': plan.kernel_name,
-                   'algorithm': 'Taylor action on the d x d density matrix with dense output (DESIGN.md section 4)',
+                   'algorithm': ('Chebyshev (Bessel-coefficient) series of the propagator acting on the d x d density matrix, one '
+                                 'recurrence per macro step, Bessel-weighted dense output (DESIGN.md section 4)'
+                                 if 'cheb' in plan.kernel_name else
+                                 'Taylor action on the d x d density matrix with dense output (DESIGN.md section 4)'),
                    'l2': 'flushed between iterations (256 MB memset); inputs are 1.1 MB per step',
                    'partitioning': f'chains sharded contiguously over {world} GPU(s), no data-path collective; '
                                    'one all_gather of per-chain loss per timed region when n_gpus > 1'},
