@@ -78,6 +78,7 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
     };
     const int gp = g & 1;
     const bool diag_lane = (t == (g >> 1));
+    const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
 
     for (;;) {
         __syncthreads();
@@ -314,23 +315,15 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             const double ai0 = odd ? xi[1][0] : xi[0][0], ai1 = odd ? xi[1][1] : xi[0][1];
             const double br0 = odd ? xr[3][0] : xr[2][0], br1 = odd ? xr[3][1] : xr[2][1];
             const double bi0 = odd ? xi[3][0] : xi[2][0], bi1 = odd ? xi[3][1] : xi[2][1];
-            double v0 = diag_lane ? (gp ? ar1 : ar0) : 0.0;
-            double v1 = diag_lane ? (gp ? ai1 : ai0) : 0.0;
-            double v2 = diag_lane ? (gp ? br1 : br0) : 0.0;
-            double v3 = diag_lane ? (gp ? bi1 : bi0) : 0.0;
-            const bool up16 = lane & 16;
-            double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;
-            s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
-            s1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-            double k0 = (up16 ? v2 : v0) + s0, k1 = (up16 ? v3 : v1) + s1;
-            const bool up8 = lane & 8;
-            double s = up8 ? k0 : k1;
-            s = __shfl_xor_sync(0xffffffffu, s, 8);
-            double k = (up8 ? k1 : k0) + s;
-            k += __shfl_xor_sync(0xffffffffu, k, 4);
-            k += __shfl_xor_sync(0xffffffffu, k, 2);
-            k += __shfl_xor_sync(0xffffffffu, k, 1);
-            if ((lane & 7) == 0) S.trp[w][lane >> 3] = k;
+            // only the 8 lanes 4g + (g >> 1) hold partial-trace elements: 3-stage reduce-scatter among exactly those
+            // lanes (4 double shuffles); value 2*bit2(g) + bit1(g) ends up in the lanes with g even
+            const double v0 = gp ? ar1 : ar0, v1 = gp ? ai1 : ai0, v2 = gp ? br1 : br0, v3 = gp ? bi1 : bi0;
+            const bool hb = g & 4, mb = g & 2;
+            const double r0 = __shfl_sync(0xffffffffu, hb ? v0 : v2, dl4), r1 = __shfl_sync(0xffffffffu, hb ? v1 : v3, dl4);
+            const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
+            const double kk = (mb ? k1 : k0) + __shfl_sync(0xffffffffu, mb ? k0 : k1, dl2);
+            const double tot = kk + __shfl_sync(0xffffffffu, kk, dl1);
+            if (diag_lane && !(g & 1)) S.trp[w][g >> 1] = tot;
         };
         // after a __syncthreads: the total of value index vi = lane >> 3 (rho00.re, rho11.re, rho01.re, rho01.im)
         auto trace_total = [&]() -> double {
@@ -464,8 +457,14 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         int kidx = 0;
         while (kidx < T - 1) {           // every scalar below is computed identically by all threads
             const double t0 = P.times[kidx];
-            int q = 0;
-            while (kidx + q + 1 <= T - 1 && P.times[kidx + q + 1] - t0 <= tau_max) ++q;
+            int q = 0;      // output times within tau_max of t0: 32 candidates per ballot (every warp computes the same)
+            for (;;) {
+                const int cand = kidx + q + 1 + lane;
+                const unsigned in = __ballot_sync(0xffffffffu, cand <= T - 1 && P.times[min(cand, T - 1)] - t0 <= tau_max);
+                const int run = __ffs(~in) - 1;
+                if (run >= 0) { q += run; break; }
+                q += 32;
+            }
             int nsub = 1;
             if (q == 0) { nsub = (int)ceil((P.times[kidx + 1] - t0) / tau_max); q = 1; }
             const double tau_end = (P.times[kidx + q] - t0) / nsub;
