@@ -48,7 +48,10 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 
 // Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26 KB at d = 16,
 // 16 warps x 13 KB at d <= 8), and the largest  tau * (A + B)  whose series fits (cheb_terms(z) <= cap)
-constexpr int CHEB_KCAP_TL2 = 640, CHEB_KCAP_TL1 = 256;
+#ifndef EML_CHEB_KCAP_TL2
+#define EML_CHEB_KCAP_TL2 640
+#endif
+constexpr int CHEB_KCAP_TL2 = EML_CHEB_KCAP_TL2, CHEB_KCAP_TL1 = 256;
 
 template <int TL, bool CHEB>
 struct alignas(16) WarpScratch {

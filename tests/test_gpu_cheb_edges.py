@@ -1,0 +1,63 @@
+"""
+GPU tests of the Chebyshev-series kernels (warp_cheb, cta_cheb) on the cases that stress the spectral enclosure and
+the macro-step logic -- the same battery tests/test_cheb_model.py runs through the numpy model of the algorithm --
+checked against the exact oracle at a much tighter tolerance than the 1e-8 of the parity tests.
+"""
+import numpy as np
+import pytest
+
+from oracle import lindblad_oracle as lo
+from tests.helpers import OBS3, model_from_spec, max_err
+from tests.test_cheb_model import EDGE, _spec
+
+pytestmark = pytest.mark.gpu
+TIGHT = 2e-12
+
+
+@pytest.mark.parametrize('name', list(EDGE))
+def test_edge_cases_on_the_gpu(name):
+    from effective_model_learning_b200 import engine
+    spec, times = EDGE[name]
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(times, OBS3)
+    assert 'cheb' in engine.context_for(m, OBS3, times).plan.kernel_name
+    want = lo.expect_exact(spec, times, OBS3)
+    assert max_err(got, want) < TIGHT, (name, max_err(got, want))
+
+
+def test_wide_spectrum_splits_into_macro_steps_at_every_size():
+    """Couplings at the upper bound and a long grid: more terms than the trace tables hold (640 / 256 / 1024), so the
+    end-of-step state path runs several times; d = 8, 16 and 32."""
+    from effective_model_learning_b200 import engine
+    for n_def, n_q in ((2, 1), (3, 1), (3, 2)):
+        n = n_q + n_def
+        couplings = [(0, k, 4.0, [('sigmax', 'sigmax')]) for k in range(n_q, n)] + \
+                    [(i, j, 3.5, [('sigmay', 'sigmay')]) for i in range(n_q, n) for j in range(i + 1, n)]
+        tls = [{'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmaz': 0.05}, 'couplings': [], 'initial_state': lo.OPS['plus'].copy()}
+               for _ in range(n_q)]
+        tls += [{'is_qubit': False, 'energy': 0.2 + 0.05 * v, 'Ls': {'sigmax': 0.1}, 'couplings': [], 'initial_state': lo.OPS['mm'].copy()}
+                for v in range(n_def)]
+        for (i, j, s, pairs) in couplings:
+            tls[i]['couplings'].append((j, s, pairs))
+        spec = {'tls': tls}
+        times = np.linspace(0.0, 30.0, 40)
+        m = model_from_spec(spec)
+        ctx = engine.context_for(m, OBS3, times)
+        got = m.calculate_dynamics(times, OBS3)
+        assert 'cheb' in ctx.plan.kernel_name
+        want = lo.expect_exact(spec, times, OBS3)
+        assert max_err(got, want) < 1e-11, (n, max_err(got, want))
+
+
+def test_chebyshev_and_taylor_kernels_agree_on_a_batch():
+    """The two series are independent implementations of the propagator action: 256 library models, d = 16."""
+    from effective_model_learning_b200 import _native, configs, synthetic
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    lay = synthetic.LibraryLayout(1, 3, hyper)
+    ts = np.linspace(0.0, 2.5, 200)
+    p = lay.batch_params(5000 + np.arange(256))
+    out = {}
+    for name, kid in (('cheb', _native.KERNEL_WARP_CHEB), ('taylor', _native.KERNEL_WARP_MMA)):
+        ctx = lay.context(ts, OBS3, kernel=kid)
+        out[name], _ = ctx.evaluate(p, want_expect=True)
+    assert np.abs(out['cheb'] - out['taylor']).max() < 1e-10
