@@ -15,7 +15,7 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h, bool chebyshev,
-                            const int* cost_hint, cudaStream_t stream);
+                            bool parity_h, const int* cost_hint, cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
@@ -175,6 +175,22 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         }
     }
     plan->real_h = realh;
+    // parity-conserving H: energy operators diagonal, coupling pairs diag (x) diag or flip (x) flip -- then H is block
+    // diagonal by the parity of the basis index and the d = 16 kernel needs half the DMMAs
+    bool parity = herm;
+    {
+        auto is_diag = [&](const double* A) { return std::fabs(A[2]) + std::fabs(A[3]) + std::fabs(A[4]) + std::fabs(A[5]) < 1e-15; };
+        auto is_flip = [&](const double* A) { return std::fabs(A[0]) + std::fabs(A[1]) + std::fabs(A[6]) + std::fabs(A[7]) < 1e-15; };
+        for (int t = 0; t < d->n_terms && parity; ++t) {
+            const EmlTerm& tm = d->terms[t];
+            if (tm.kind == EML_TERM_LINDBLAD) continue;
+            const double* A = d->op_table + tm.op_a * 8;
+            if (tm.kind == EML_TERM_ENERGY) { parity = is_diag(A); continue; }
+            const double* B = d->op_table + tm.op_b * 8;
+            parity = (is_diag(A) && is_diag(B)) || (is_flip(A) && is_flip(B));
+        }
+    }
+    plan->parity_h = parity;
     // Models with fewer than 3 sites are embedded for the warp kernel: spectator sites (identity dynamics,
     // state |0><0|) are appended as the least significant factors, which changes neither the reduced dynamics of
     // the real sites nor the observables.
@@ -233,7 +249,10 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
 const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (!plan) return "";
     if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
-    if (plan->kernel == EML_KERNEL_WARP_CHEB) return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
+    if (plan->kernel == EML_KERNEL_WARP_CHEB) {
+        if (plan->parity_h && plan->Pw.n_tls == 4) return plan->real_h ? "warp_cheb_parity_realH" : "warp_cheb_parity";
+        return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
+    }
     if (plan->kernel == EML_KERNEL_CTA_MMA) return plan->real_h ? "cta_mma_realH" : "cta_mma";
     if (plan->kernel == EML_KERNEL_CTA_CHEB) return plan->real_h ? "cta_cheb_realH" : "cta_cheb";
     return "generic";
@@ -260,8 +279,7 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA || plan->kernel == EML_KERNEL_WARP_CHEB)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
-                                 plan->kernel == EML_KERNEL_WARP_CHEB,
-                                 cost_hint, (cudaStream_t)stream);
+                                 plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
                                 plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, cost_hint, (cudaStream_t)stream);

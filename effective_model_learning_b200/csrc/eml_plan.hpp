@@ -24,6 +24,7 @@ struct EmlPlan {
     int kernel = EML_KERNEL_GENERIC;
     bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
     bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs
+    bool parity_h = false;    // additionally every Hamiltonian term conserves the parity of the basis index: G block diagonal
     std::vector<void*> owned; // device allocations
     // staging for the host entry point
     cudaStream_t stream = nullptr;

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     }
 }
 
-template <int TL, bool REAL_H, bool CHEB>
+template <int TL, bool REAL_H, bool CHEB, bool PARITY>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : CTAS_PER_SM)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
@@ -158,6 +158,14 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                      const double cheb_zcap) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
+    static_assert(!PARITY || (CHEB && TL == 2), "the parity-blocked variant exists for the d = 16 Chebyshev kernel");
+    // PARITY (every Hamiltonian term conserves the parity of the computational-basis index: sigma_z energies,
+    // diag (x) diag or flip (x) flip couplings -- all libraries of configs.py): H is block diagonal in the coordinates
+    // x' = x ^ (parity(x & 7) << 3), i.e. the top (tile) bit of the kernel's row / column index is the PARITY of the
+    // physical index instead of the observed site's bit.  Then G has only diagonal tiles and G v needs HALF the DMMAs;
+    // a flip of any site also flips the tile bit of row and column (pure register renaming, as the observed site's
+    // flip already was), the lane shuffles are unchanged.
+    auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Scratch = WarpScratch<TL, CHEB>;
     Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
@@ -310,26 +318,30 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         for (int I = 0; I < TL; ++I)
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
-                a_re[I][ks] = REAL_H ? 0.0 : S.G_re[8 * I + g][k];
-                a_im[I][ks] = S.G_im[8 * I + g][k];
+                // PARITY: only the diagonal tile K' = I is non-zero; it is kept in ks = 0, 1
+                const int k = PARITY ? 8 * I + 2 * t + (ks & 1) : 8 * (ks >> 1) + 2 * t + (ks & 1);
+                a_re[I][ks] = REAL_H ? 0.0 : S.G_re[phys(8 * I + g)][phys(k)];
+                a_im[I][ks] = S.G_im[phys(8 * I + g)][phys(k)];
             }
         // Stencil weights are stored HALVED: the DMMA accumulators start from J(v)/2, so that
         // X' + X'^dag = G v + v G^dag + J(v)  (J(v) is Hermitian).
         double W0[TL][TL][2];
-        double F3[TL][TL];
+        constexpr int FE = PARITY ? 2 : 1;      // PARITY: the observed site's column bit depends on e
+        double F3[TL][TL][FE];
 #pragma unroll
         for (int I = 0; I < TL; ++I)
 #pragma unroll
             for (int J = 0; J < TL; ++J) {
-                F3[I][J] = (TL == 2) ? 0.5 * S.jw[3 * 8 + 4 + I * 2 + J] : 0.0;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
+                    const int row = phys(8 * I + g), col = phys(8 * J + 2 * t + e);     // physical indices
+                    const int r3 = (row >> 3) & 1, c3 = (col >> 3) & 1;                 // the observed site's bits (d = 16)
                     double w = S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] + S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] +
                                S.jw[0 * 8 + (g & 1) * 2 + e];
-                    if (TL == 2) w += S.jw[3 * 8 + I * 2 + J];
-                    if (REAL_H) w += S.G_re[8 * I + g][8 * I + g] + S.G_re[8 * J + 2 * t + e][8 * J + 2 * t + e];
+                    if (TL == 2) w += S.jw[3 * 8 + r3 * 2 + c3];
+                    if (REAL_H) w += S.G_re[row][row] + S.G_re[col][col];
                     W0[I][J][e] = 0.5 * w;
+                    if (e < FE) F3[I][J][e] = (TL == 2) ? 0.5 * S.jw[3 * 8 + 4 + r3 * 2 + c3] : 0.0;
                 }
             }
         double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
@@ -347,7 +359,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             for (int J = 0; J < TL; ++J)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int r = orig_index(8 * I + g), c = orig_index(8 * J + 2 * t + e);
+                    const int r = orig_index(phys(8 * I + g)), c = orig_index(phys(8 * J + 2 * t + e));
                     acc_re[I][J][e] = P.rho0[2 * (r * D + c)];
                     acc_im[I][J][e] = P.rho0[2 * (r * D + c) + 1];
                 }
@@ -434,7 +446,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
           }
         };
 
-        {
+        if constexpr (!CHEB) {
             const double v = partial_trace(acc_re, acc_im);
             double y1st[NY];
 #pragma unroll
@@ -445,6 +457,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // ---- generator application core, shared by both series: given x = (diagonal stencil weight) * v (+ anything
         //      Hermitian / 2), add the remaining site stencils (J(v)/2) and G v on the DMMA pipe -> X'
         auto apply_rest = [&](const double (&v_re)[TL][TL][2], const double (&v_im)[TL][TL][2], double (&x_re)[TL][TL][2], double (&x_im)[TL][TL][2]) {
+            constexpr int PX = PARITY ? 1 : 0;     // PARITY: a flip of a lane-bit site also flips the tile (parity) bit
             {
 #pragma unroll
                 for (int I = 0; I < TL; ++I)
@@ -453,8 +466,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             if (TL == 2) {
-                                x_re[I][J][e] = fma(F3[I][J], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
-                                x_im[I][J][e] = fma(F3[I][J], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
+                                x_re[I][J][e] = fma(F3[I][J][e & (FE - 1)], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
+                                x_im[I][J][e] = fma(F3[I][J][e & (FE - 1)], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
                             }
                         }
             }
@@ -465,8 +478,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 18), x_re[I][J][e]);
-                            x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 18), x_im[I][J][e]);
+                            x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e], 18), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e], 18), x_im[I][J][e]);
                         }
             }
             {
@@ -476,8 +489,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I][J][e], 9), x_re[I][J][e]);
-                            x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I][J][e], 9), x_im[I][J][e]);
+                            x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e], 9), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e], 9), x_im[I][J][e]);
                         }
             }
             {
@@ -487,12 +500,29 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I][J][e ^ 1], 4), x_re[I][J][e]);
-                            x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I][J][e ^ 1], 4), x_im[I][J][e]);
+                            x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e ^ 1], 4), x_re[I][J][e]);
+                            x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e ^ 1], 4), x_im[I][J][e]);
                         }
             }
             // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
             //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
+            if constexpr (PARITY) {
+                // only the diagonal tiles of G: X[I][J] = G[I][I] v[I][J], B = conj of the own registers v[J][I]
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                        for (int I = 0; I < TL; ++I) {
+                            const double b_re = v_re[J][I][ks], b_im = v_im[J][I][ks];
+                            if (!REAL_H) {
+                                dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
+                                dmma(x_im[I][J][0], x_im[I][J][1], a_re[I][ks], neg(b_im));
+                            }
+                            dmma(x_re[I][J][0], x_re[I][J][1], a_im[I][ks], b_im);
+                            dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
+                        }
+            } else {
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 if (!REAL_H) {
@@ -517,6 +547,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         dmma(x_im[I][J][0], x_im[I][J][1], a_im[I][ks], b_re);
                     }
                 }
+            }
             }
         };
         // w = X' + X'^dag (the conjugate transpose gathered with shuffles, d = 8: through shared memory)
@@ -659,7 +690,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 for (int ks = 0; ks < KS; ++ks) { a_re[I][ks] *= sc; a_im[I][ks] *= sc; }
 #pragma unroll
                 for (int J = 0; J < TL; ++J) {
-                    F3[I][J] *= sc;
+#pragma unroll
+                    for (int e = 0; e < FE; ++e) F3[I][J][e] *= sc;
                     W0[I][J][0] = (W0[I][J][0] + 0.5 * ac) * sc; W0[I][J][1] = (W0[I][J][1] + 0.5 * ac) * sc;
                 }
             }
@@ -671,8 +703,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
         auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], double* dst) {
             if constexpr (TL == 2) {
-                const double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
-                const double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
+                double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
+                double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
+                if constexpr (PARITY) {
+                    // the observed site's bits are (I ^ p, J ^ p), p = parity of the (equal) low bits of row and column
+                    const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
+                    const double w2 = gp ? xr[1][0][1] : xr[1][0][0], w3 = gp ? xi[1][0][1] : xi[1][0][0];
+                    const double a0 = v0, a1 = v1;
+                    v0 = pl ? a1 : a0; v1 = pl ? a0 : a1; v2 = pl ? w2 : v2; v3 = pl ? w3 : v3;
+                }
                 const bool hb = g & 4, mb = g & 2;
                 const double r0 = shfl(hb ? v0 : v2, dl4), r1 = shfl(hb ? v1 : v3, dl4);
                 const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
@@ -686,6 +725,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         };
         double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
 
+        {   // the first output time carries the initial state
+            trace_store(acc_re, acc_im, &S.tr[0]);
+            __syncwarp();
+            const double r[4] = {S.tr[0], S.tr[1], S.tr[2], S.tr[3]};
+            if (lane == 0) finish_output(0, r);
+            __syncwarp();
+        }
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
             const double t0 = P.times[kidx];
@@ -702,13 +748,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             const double tau_end = (P.times[kidx + q] - t0) / nsub;
             const bool final_step = (kidx + q == T - 1);
             if (UNI(!(tau_end * Rb >= 1e-40))) {     // repeated time points: the state does not move
-                const double tr0 = partial_trace(acc_re, acc_im);
-                for (int pbase = 0; UNI(pbase < q); pbase += 32) {
-                    double r[4];
-#pragma unroll
-                    for (int vi = 0; vi < 4; ++vi) r[vi] = shfl(tr0, vi * 8);
+                __syncwarp();
+                trace_store(acc_re, acc_im, &S.tr[0]);
+                __syncwarp();
+                const double r[4] = {S.tr[0], S.tr[1], S.tr[2], S.tr[3]};
+                for (int pbase = 0; UNI(pbase < q); pbase += 32)
                     if (pbase + lane < q) finish_output(kidx + 1 + pbase + lane, r);
-                }
+                __syncwarp();
                 kidx += q;
                 continue;
             }
@@ -904,7 +950,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         for (int ks = 0; ks < KS; ++ks) { a_re[I][ks] *= rs; a_im[I][ks] *= rs; }
 #pragma unroll
                         for (int J = 0; J < TL; ++J) {
-                            F3[I][J] *= rs;
+                            F3[I][J][0] *= rs;
                             W0[I][J][0] *= rs; W0[I][J][1] *= rs;
                         }
                     }
@@ -999,9 +1045,10 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-#define EML_WARP_INST(TL, RH, CH) template __global__ void eval_warp_mma_kernel<TL, RH, CH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
-EML_WARP_INST(1, true, false) EML_WARP_INST(1, false, false) EML_WARP_INST(2, true, false) EML_WARP_INST(2, false, false)
-EML_WARP_INST(1, true, true) EML_WARP_INST(1, false, true) EML_WARP_INST(2, true, true) EML_WARP_INST(2, false, true)
+#define EML_WARP_INST(TL, RH, CH, PA) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+EML_WARP_INST(1, true, false, false) EML_WARP_INST(1, false, false, false) EML_WARP_INST(2, true, false, false) EML_WARP_INST(2, false, false, false)
+EML_WARP_INST(1, true, true, false) EML_WARP_INST(1, false, true, false) EML_WARP_INST(2, true, true, false) EML_WARP_INST(2, false, true, false)
+EML_WARP_INST(2, true, true, true) EML_WARP_INST(2, false, true, true)
 
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1041,15 +1088,15 @@ static cudaError_t init_inv_table() {
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
                           unsigned int*, const int*, const double);
 
-template <int TL, bool CH>
+template <int TL, bool CH, bool PA>
 static WarpKern pick_kernel(bool real_h, size_t& smem) {
     smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH>);
-    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH> : (WarpKern)eval_warp_mma_kernel<TL, false, CH>;
+    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH, PA> : (WarpKern)eval_warp_mma_kernel<TL, false, CH, PA>;
 }
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
-                            bool real_h, bool chebyshev, const int* cost_hint, cudaStream_t stream) {
+                            bool real_h, bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1064,11 +1111,13 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     }
     const bool tl2 = (P.n_tls == 4);
     size_t smem = 0;
-    const WarpKern kern = tl2 ? (chebyshev ? pick_kernel<2, true>(real_h, smem) : pick_kernel<2, false>(real_h, smem))
-                              : (chebyshev ? pick_kernel<1, true>(real_h, smem) : pick_kernel<1, false>(real_h, smem));
+    const bool parity = parity_h && chebyshev && tl2;     // H block diagonal by parity: half the DMMAs (d = 16)
+    const WarpKern kern = tl2 ? (chebyshev ? (parity ? pick_kernel<2, true, true>(real_h, smem) : pick_kernel<2, true, false>(real_h, smem))
+                                           : pick_kernel<2, false, false>(real_h, smem))
+                              : (chebyshev ? pick_kernel<1, true, false>(real_h, smem) : pick_kernel<1, false, false>(real_h, smem));
     // per device and kernel variant: dynamic shared memory opt-in and the resident CTAs per SM
-    static int per_sm_cache[64][8] = {{0}};
-    const int variant = (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
+    static int per_sm_cache[64][16] = {{0}};
+    const int variant = (parity ? 8 : 0) + (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
     int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
     if (per_sm == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

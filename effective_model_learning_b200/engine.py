@@ -235,9 +235,12 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
     if kernel_name == 'generic':
         return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
     if kernel_name in ('warp_mma', 'warp_mma_realH', 'warp_cheb', 'warp_cheb_realH', 'cta_mma', 'cta_mma_realH',
-                       'cta_cheb', 'cta_cheb_realH'):
+                       'cta_cheb', 'cta_cheb_realH', 'warp_cheb_parity', 'warp_cheb_parity_realH',
+                       'cta_cheb_parity', 'cta_cheb_parity_realH'):
         # DMMA: 4 (complex H) or 2 (real H: G.re diagonal, folded into the stencil) real d^3 products;
         # per complex element: diagonal weight 2, n site stencils 4n, X + X^dag 2, scale 2, accumulate 2
         mma = (2.0 if kernel_name.endswith('realH') else 4.0) * 2.0 * d ** 3
+        if 'parity' in kernel_name:      # H block diagonal by parity: only the diagonal tiles of G are multiplied
+            mma *= 0.5
         return mma + d * d * (2.0 + 4.0 * n_tls + 6.0)
     raise RuntimeError('unknown kernel ' + kernel_name)

@@ -61,3 +61,27 @@ def test_chebyshev_and_taylor_kernels_agree_on_a_batch():
         ctx = lay.context(ts, OBS3, kernel=kid)
         out[name], _ = ctx.evaluate(p, want_expect=True)
     assert np.abs(out['cheb'] - out['taylor']).max() < 1e-10
+
+
+def test_parity_blocked_and_general_variants_of_the_d16_kernel():
+    """Same-Pauli couplings conserve the parity of the basis index (H block diagonal, half the DMMAs); one sigma_z (x)
+    sigma_x coupling breaks it and selects the general variant.  Both against the exact oracle, qubit not first."""
+    from effective_model_learning_b200 import engine
+    ts = np.linspace(0.0, 2.5, 120)
+    base = lo.random_library_spec(np.random.default_rng(77), 1, 3)
+    base['tls'] = [base['tls'][1], base['tls'][0], base['tls'][2], base['tls'][3]]      # observed site = 1
+    remap = {0: 1, 1: 0, 2: 2, 3: 3}
+    for t in base['tls']:
+        t['couplings'] = [(remap[j], s, pairs) for (j, s, pairs) in t['couplings']]
+    base['tls'][3]['Ls']['sigmam'] = 0.2
+    base['tls'][0]['couplings'].append((2, 1.3, [('sigmay', 'sigmax')]))                 # flip (x) flip, complex H
+    names = []
+    for extra in (None, (1, 3, 0.9, [('sigmaz', 'sigmax')])):
+        spec = {'tls': [dict(t, couplings=list(t['couplings']), Ls=dict(t['Ls'])) for t in base['tls']]}
+        if extra:
+            spec['tls'][extra[0]]['couplings'].append(extra[1:])
+        m = model_from_spec(spec)
+        got = m.calculate_dynamics(ts, OBS3)
+        names.append(engine.context_for(m, OBS3, ts).plan.kernel_name)
+        assert max_err(got, lo.expect_exact(spec, ts, OBS3)) < TIGHT, names
+    assert names == ['warp_cheb_parity', 'warp_cheb'], names
