@@ -19,7 +19,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           bool chebyshev, const int* cost_hint, cudaStream_t stream);
+                           bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream);
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
@@ -254,7 +254,10 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
         return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
     }
     if (plan->kernel == EML_KERNEL_CTA_MMA) return plan->real_h ? "cta_mma_realH" : "cta_mma";
-    if (plan->kernel == EML_KERNEL_CTA_CHEB) return plan->real_h ? "cta_cheb_realH" : "cta_cheb";
+    if (plan->kernel == EML_KERNEL_CTA_CHEB) {
+        if (plan->parity_h) return plan->real_h ? "cta_cheb_parity_realH" : "cta_cheb_parity";
+        return plan->real_h ? "cta_cheb_realH" : "cta_cheb";
+    }
     return "generic";
 }
 
@@ -282,7 +285,7 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
                                  plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
-                                plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, cost_hint, (cudaStream_t)stream);
+                                plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)

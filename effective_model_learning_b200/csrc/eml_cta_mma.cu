@@ -54,13 +54,19 @@ __device__ __forceinline__ void dmma_c(double& d0, double& d1, double a, double 
 }
 __device__ __forceinline__ double neg_c(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 
-template <bool REAL_H, bool CHEB>
+template <bool REAL_H, bool CHEB, bool PARITY>
 __global__ void __launch_bounds__(128, 2)
 eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                     const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                     int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
                     const double cheb_zcap) {
     constexpr int N = 5, D = 32;
+    static_assert(!PARITY || CHEB, "the parity-blocked variant exists for the Chebyshev kernel");
+    // PARITY (every Hamiltonian term conserves the parity of the basis index, see eml_warp_mma.cu): the TOP bit of the
+    // kernel's row / column index is the parity of the physical index, x' = x ^ (parity(x & 15) << 4).  G then has
+    // non-zero tiles only between tile rows / columns with the same top bit: half the DMMAs and B-fragment loads; a
+    // flip of any site below the observed one also flips the top tile bit of row and column.
+    auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2) ^ (x >> 3)) & 1) << 4) : x; };
     extern __shared__ __align__(16) unsigned char cta_smem_raw[];
     using Scratch = CtaScratch<CHEB>;
     Scratch& S = *reinterpret_cast<Scratch*>(cta_smem_raw);
@@ -201,22 +207,36 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         double a_re[8], a_im[8];
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
-            a_re[ks] = REAL_H ? 0.0 : G_re[(8 * w + g) * LDV + k];
-            a_im[ks] = G_im[(8 * w + g) * LDV + k];
+            // PARITY: only the column tiles kt = 2 (w >> 1) + {0, 1} are non-zero; they are kept in ks = 0..3
+            const int kt = PARITY ? 2 * (w >> 1) + ((ks >> 1) & 1) : (ks >> 1);
+            const int k = 8 * kt + 2 * t + (ks & 1);
+            a_re[ks] = REAL_H ? 0.0 : G_re[phys(8 * w + g) * LDV + phys(k)];
+            a_im[ks] = G_im[phys(8 * w + g) * LDV + phys(k)];
         }
         double W0[4][2];     // halved diagonal weights for (J, e)
 #pragma unroll
         for (int J = 0; J < 4; ++J)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                double x = S.jw[4 * 8 + (w >> 1) * 2 + (J >> 1)] + S.jw[3 * 8 + (w & 1) * 2 + (J & 1)] +
+                const int row = phys(8 * w + g), col = phys(8 * J + 2 * t + e);      // physical indices
+                double x = S.jw[4 * 8 + (row >> 4) * 2 + (col >> 4)] + S.jw[3 * 8 + (w & 1) * 2 + (J & 1)] +
                            S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] + S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] +
                            S.jw[0 * 8 + (g & 1) * 2 + e];
-                if (REAL_H) x += G_re[(8 * w + g) * LDV + 8 * w + g] + G_re[(8 * J + 2 * t + e) * LDV + 8 * J + 2 * t + e];
+                if (REAL_H) x += G_re[row * LDV + row] + G_re[col * LDV + col];
                 W0[J][e] = 0.5 * x;
             }
-        double F4[2] = {0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 0], 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 1]};   // by J>>1
+        // flip weight of the observed site: by J >> 1; PARITY: by (J, e), the observed bits being (row >> 4, col >> 4)
+        constexpr int NF4 = PARITY ? 8 : 2;
+        double F4[NF4];
+        if constexpr (PARITY) {
+#pragma unroll
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    F4[2 * J + e] = 0.5 * S.jw[4 * 8 + 4 + (phys(8 * w + g) >> 4) * 2 + (phys(8 * J + 2 * t + e) >> 4)];
+        } else {
+            F4[0] = 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 0]; F4[1] = 0.5 * S.jw[4 * 8 + 4 + (w >> 1) * 2 + 1];
+        }
         double F3[2] = {0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 0], 0.5 * S.jw[3 * 8 + 4 + (w & 1) * 2 + 1]};     // by J&1
         double f2 = 0.5 * S.jw[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)];
         double f1 = 0.5 * S.jw[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)];
@@ -286,7 +306,9 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             for (int ks = 0; ks < 8; ++ks) { a_re[ks] *= sc; a_im[ks] *= sc; }
 #pragma unroll
             for (int J = 0; J < 4; ++J) { W0[J][0] = (W0[J][0] + 0.5 * plan.ac) * sc; W0[J][1] = (W0[J][1] + 0.5 * plan.ac) * sc; }
-            F4[0] *= sc; F4[1] *= sc; F3[0] *= sc; F3[1] *= sc;
+#pragma unroll
+            for (int i = 0; i < NF4; ++i) F4[i] *= sc;
+            F3[0] *= sc; F3[1] *= sc;
             f2 *= sc; f1 *= sc; f0[0] *= sc; f0[1] *= sc;
         }
         __syncthreads();     // G has been consumed: the Vs planes are free for the series terms
@@ -297,7 +319,7 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         for (int J = 0; J < 4; ++J)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int r = orig_index(8 * w + g), c = orig_index(8 * J + 2 * t + e);
+                const int r = orig_index(phys(8 * w + g)), c = orig_index(phys(8 * J + 2 * t + e));
                 acc_re[J][e] = P.rho0[2 * (r * D + c)];
                 acc_im[J][e] = P.rho0[2 * (r * D + c) + 1];
             }
@@ -317,7 +339,14 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             const double bi0 = odd ? xi[3][0] : xi[2][0], bi1 = odd ? xi[3][1] : xi[2][1];
             // only the 8 lanes 4g + (g >> 1) hold partial-trace elements: 3-stage reduce-scatter among exactly those
             // lanes (4 double shuffles); value 2*bit2(g) + bit1(g) ends up in the lanes with g even
-            const double v0 = gp ? ar1 : ar0, v1 = gp ? ai1 : ai0, v2 = gp ? br1 : br0, v3 = gp ? bi1 : bi0;
+            // this lane's contribution to (rho00, rho11, Re rho01, Im rho01) of the observed site: tile a has column bit
+            // 0, tile b column bit 1, the row bit is w >> 1; PARITY: both bits are XORed with the parity p of the low bits
+            const double are_ = gp ? ar1 : ar0, aim_ = gp ? ai1 : ai0, bre_ = gp ? br1 : br0, bim_ = gp ? bi1 : bi0;
+            const bool top = w & 2;
+            const bool pl = PARITY ? (((g ^ (g >> 1) ^ (g >> 2) ^ w) & 1) != 0) : false;
+            double v0, v1, v2, v3;
+            if (!top) { v0 = pl ? 0.0 : are_; v1 = pl ? are_ : 0.0; v2 = pl ? 0.0 : bre_; v3 = pl ? 0.0 : bim_; }
+            else      { v0 = pl ? bre_ : 0.0; v1 = pl ? 0.0 : bre_; v2 = pl ? are_ : 0.0; v3 = pl ? aim_ : 0.0; }
             const bool hb = g & 4, mb = g & 2;
             const double r0 = __shfl_sync(0xffffffffu, hb ? v0 : v2, dl4), r1 = __shfl_sync(0xffffffffu, hb ? v1 : v3, dl4);
             const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
@@ -329,10 +358,7 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         auto trace_total = [&]() -> double {
             const int vi = lane >> 3;
             // rho_red[a][b]: a = w>>1 of the contributing warps, b = tile half
-            if (vi == 0) return S.trp[0][0] + S.trp[1][0];
-            if (vi == 1) return S.trp[2][2] + S.trp[3][2];
-            if (vi == 2) return S.trp[0][2] + S.trp[1][2];
-            return S.trp[0][3] + S.trp[1][3];
+            return (S.trp[0][vi] + S.trp[1][vi]) + (S.trp[2][vi] + S.trp[3][vi]);
         };
         auto emit = [&](int q, int kbase, double y0, double y1) {
             const int p = lane;
@@ -368,19 +394,22 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
             for (int J = 0; J < 4; ++J) {
                 const int base = 8 * J + 2 * t;
                 // bit 4: (I^2, J^2); bit 3: (I^1, J^1); bit 2: (g^4, t^2); bit 1: (g^2, t^1); bit 0: (g^1, e^1)
+                // PARITY: a flip of a site below the observed one also flips the top (parity) tile bit of row and column
+                constexpr int PX = PARITY ? 2 : 0;
                 const int o4 = (8 * (w ^ 2) + g) * LDV + 8 * (J ^ 2) + 2 * t;
-                const int o3 = (8 * (w ^ 1) + g) * LDV + 8 * (J ^ 1) + 2 * t;
-                const int o2 = (8 * w + (g ^ 4)) * LDV + 8 * J + 2 * (t ^ 2);
-                const int o1 = (8 * w + (g ^ 2)) * LDV + 8 * J + 2 * (t ^ 1);
-                const int o0 = (8 * w + (g ^ 1)) * LDV + base;
+                const int o3 = (8 * (w ^ 1 ^ PX) + g) * LDV + 8 * (J ^ 1 ^ PX) + 2 * t;
+                const int o2 = (8 * (w ^ PX) + (g ^ 4)) * LDV + 8 * (J ^ PX) + 2 * (t ^ 2);
+                const int o1 = (8 * (w ^ PX) + (g ^ 2)) * LDV + 8 * (J ^ PX) + 2 * (t ^ 1);
+                const int o0 = (8 * (w ^ PX) + (g ^ 1)) * LDV + 8 * (J ^ PX) + 2 * t;
                 const double2 r4 = *reinterpret_cast<const double2*>(&S.Vs_re[o4]), i4 = *reinterpret_cast<const double2*>(&S.Vs_im[o4]);
                 const double2 r3 = *reinterpret_cast<const double2*>(&S.Vs_re[o3]), i3 = *reinterpret_cast<const double2*>(&S.Vs_im[o3]);
                 const double2 r2 = *reinterpret_cast<const double2*>(&S.Vs_re[o2]), i2 = *reinterpret_cast<const double2*>(&S.Vs_im[o2]);
                 const double2 r1 = *reinterpret_cast<const double2*>(&S.Vs_re[o1]), i1 = *reinterpret_cast<const double2*>(&S.Vs_im[o1]);
                 const double2 r0 = *reinterpret_cast<const double2*>(&S.Vs_re[o0]), i0 = *reinterpret_cast<const double2*>(&S.Vs_im[o0]);
-                const double w4 = F4[J >> 1], w3 = F3[J & 1];
-                x_re[J][0] = fma(w4, r4.x, x_re[J][0]); x_re[J][1] = fma(w4, r4.y, x_re[J][1]);
-                x_im[J][0] = fma(w4, i4.x, x_im[J][0]); x_im[J][1] = fma(w4, i4.y, x_im[J][1]);
+                const double w40 = PARITY ? F4[(2 * J) & (NF4 - 1)] : F4[J >> 1], w41 = PARITY ? F4[(2 * J + 1) & (NF4 - 1)] : F4[J >> 1];
+                const double w3 = F3[J & 1];
+                x_re[J][0] = fma(w40, r4.x, x_re[J][0]); x_re[J][1] = fma(w41, r4.y, x_re[J][1]);
+                x_im[J][0] = fma(w40, i4.x, x_im[J][0]); x_im[J][1] = fma(w41, i4.y, x_im[J][1]);
                 x_re[J][0] = fma(w3, r3.x, x_re[J][0]); x_re[J][1] = fma(w3, r3.y, x_re[J][1]);
                 x_im[J][0] = fma(w3, i3.x, x_im[J][0]); x_im[J][1] = fma(w3, i3.y, x_im[J][1]);
                 x_re[J][0] = fma(f2, r2.x, x_re[J][0]); x_re[J][1] = fma(f2, r2.y, x_re[J][1]);
@@ -395,21 +424,22 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
 #pragma unroll
             for (int J = 0; J < 4; ++J)
 #pragma unroll
-                for (int kt = 0; kt < 4; ++kt) {
+                for (int kk = 0; kk < (PARITY ? 2 : 4); ++kk) {
+                    const int kt = PARITY ? 2 * (w >> 1) + kk : kk;      // column tile of G = row tile of the B operand
                     const int o = (8 * J + g) * LDV + 8 * kt + 2 * t;
                     const double2 br = *reinterpret_cast<const double2*>(&S.Vs_re[o]);
                     const double2 bi = *reinterpret_cast<const double2*>(&S.Vs_im[o]);
                     // X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
                     if (!REAL_H) {
-                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt], br.x);
-                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt], neg_c(bi.x));
-                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kt + 1], br.y);
-                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kt + 1], neg_c(bi.y));
+                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kk], br.x);
+                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kk], neg_c(bi.x));
+                        dmma_c(x_re[J][0], x_re[J][1], a_re[2 * kk + 1], br.y);
+                        dmma_c(x_im[J][0], x_im[J][1], a_re[2 * kk + 1], neg_c(bi.y));
                     }
-                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt], bi.x);
-                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt], br.x);
-                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kt + 1], bi.y);
-                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kt + 1], br.y);
+                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kk], bi.x);
+                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kk], br.x);
+                    dmma_c(x_re[J][0], x_re[J][1], a_im[2 * kk + 1], bi.y);
+                    dmma_c(x_im[J][0], x_im[J][1], a_im[2 * kk + 1], br.y);
                 }
             // publish X' column-major so that the transpose is a vector load
 #pragma unroll
@@ -473,8 +503,9 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                 __syncthreads();
                 partial_trace_store(acc_re, acc_im);
                 __syncthreads();
-                const double r[4] = {S.trp[0][0] + S.trp[1][0], S.trp[2][2] + S.trp[3][2], S.trp[0][2] + S.trp[1][2],
-                                     S.trp[0][3] + S.trp[1][3]};
+                double r[4];
+#pragma unroll
+                for (int vi = 0; vi < 4; ++vi) r[vi] = (S.trp[0][vi] + S.trp[1][vi]) + (S.trp[2][vi] + S.trp[3][vi]);
                 for (int p = tid; p < q; p += 128) finish_output(kidx + 1 + p, r);
                 kidx += q;
                 continue;
@@ -521,10 +552,8 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                         }
                         partial_trace_store(v_re, v_im);
                         __syncthreads();
-                        if (tid < 4) {   // rho00, rho11, Re rho01, Im rho01 (see trace_total)
-                            const int wa = (tid == 1) ? 2 : 0, ci = (tid == 0) ? 0 : (tid == 3) ? 3 : 2;
-                            S.tr[k * 4 + tid] = S.trp[wa][ci] + S.trp[wa + 1][ci];
-                        }
+                        if (tid < 4)     // rho00, rho11, Re rho01, Im rho01
+                            S.tr[k * 4 + tid] = (S.trp[0][tid] + S.trp[1][tid]) + (S.trp[2][tid] + S.trp[3][tid]);
                         if constexpr (NA) {
                             const double c = S.cJ[k] * cscale;
 #pragma unroll
@@ -743,8 +772,9 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
     }
 }
 
-#define EML_CTA_INST(RH, CH) template __global__ void eval_cta_mma_kernel<RH, CH>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
-EML_CTA_INST(true, false) EML_CTA_INST(false, false) EML_CTA_INST(true, true) EML_CTA_INST(false, true)
+#define EML_CTA_INST(RH, CH, PA) template __global__ void eval_cta_mma_kernel<RH, CH, PA>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+EML_CTA_INST(true, false, false) EML_CTA_INST(false, false, false) EML_CTA_INST(true, true, false) EML_CTA_INST(false, true, false)
+EML_CTA_INST(true, true, true) EML_CTA_INST(false, true, true)
 
 bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian && P.n_tls == 5 && P.n_params <= CMAXP; }
 
@@ -754,7 +784,7 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
 
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           bool chebyshev, const int* cost_hint, cudaStream_t stream) {
+                           bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -776,11 +806,13 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
     }
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
                           const int*, const double);
-    const Kern kern = chebyshev ? (real_h ? (Kern)eval_cta_mma_kernel<true, true> : (Kern)eval_cta_mma_kernel<false, true>)
-                                : (real_h ? (Kern)eval_cta_mma_kernel<true, false> : (Kern)eval_cta_mma_kernel<false, false>);
+    const bool parity = parity_h && chebyshev;
+    const Kern kern = parity ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, true> : (Kern)eval_cta_mma_kernel<false, true, true>)
+                    : chebyshev ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, false> : (Kern)eval_cta_mma_kernel<false, true, false>)
+                                : (real_h ? (Kern)eval_cta_mma_kernel<true, false, false> : (Kern)eval_cta_mma_kernel<false, false, false>);
     const size_t smem = chebyshev ? sizeof(CtaScratch<true>) : sizeof(CtaScratch<false>);
-    static int per_sm_cache[64][4] = {{0}};
-    const int variant = (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
+    static int per_sm_cache[64][8] = {{0}};
+    const int variant = (parity ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
     int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
     if (per_sm == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

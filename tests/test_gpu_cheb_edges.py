@@ -85,3 +85,24 @@ def test_parity_blocked_and_general_variants_of_the_d16_kernel():
         names.append(engine.context_for(m, OBS3, ts).plan.kernel_name)
         assert max_err(got, lo.expect_exact(spec, ts, OBS3)) < TIGHT, names
     assert names == ['warp_cheb_parity', 'warp_cheb'], names
+
+
+def test_parity_blocked_d32_kernel_with_complex_hermitian_coupling():
+    """d = 32, observed qubit at site 2, sigma-/+ jumps, one sigma_x (x) sigma_y coupling (flip (x) flip: parity is still
+    conserved, H is complex) -> cta_cheb_parity; against the exact oracle."""
+    from effective_model_learning_b200 import engine
+    spec = lo.random_library_spec(np.random.default_rng(91), 2, 3)
+    order = [2, 3, 0, 1, 4]                                  # new site k is old site order[k]
+    inv = {old: new for new, old in enumerate(order)}
+    tls = [spec['tls'][o] for o in order]
+    for t in tls:
+        t['couplings'] = [(inv[j], s, pairs) for (j, s, pairs) in t['couplings']]
+    tls[0]['couplings'].append((4, 1.7, [('sigmax', 'sigmay')]))
+    tls[1]['Ls']['sigmam'] = 0.25
+    tls[2]['Ls']['sigmap'] = 0.15
+    spec = {'tls': tls}
+    ts = np.sort(np.concatenate([np.linspace(0.0, 2.5, 60), [7.0]]))
+    m = model_from_spec(spec)
+    got = m.calculate_dynamics(ts, OBS3)
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'cta_cheb_parity'
+    assert max_err(got, lo.expect_exact(spec, ts, OBS3)) < TIGHT
