@@ -46,12 +46,23 @@ constexpr int WARPS_PER_CTA = EML_WARPS_PER_CTA;
 constexpr int CTAS_PER_SM = EML_CTAS_PER_SM;   // 2 -> 8 warps per SM (<= 255 regs); 3 -> 12 warps (<= 168 regs)
 constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 
-// Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26 KB at d = 16,
+// Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26.4 KB at d = 16,
 // 16 warps x 13 KB at d <= 8), and the largest  tau * (A + B)  whose series fits (cheb_terms(z) <= cap)
 #ifndef EML_CHEB_KCAP_TL2
-#define EML_CHEB_KCAP_TL2 640
+#define EML_CHEB_KCAP_TL2 512
 #endif
+// kernel-variant switches for experiments (tools/build_variant.sh); the defaults are the measured best
+#ifndef EML_CHEB_UNROLL
+#define EML_CHEB_UNROLL 1          // unroll factor of the Chebyshev recurrence loop
+#endif
+#ifndef EML_HALVE_ON_FP64
+#define EML_HALVE_ON_FP64 2        // halving of the stored term: 0 integer-pipe exponent decrement, 1 DMUL, 2 DMUL in the
+#endif                             // parity-blocked variant only (its FP64 pipe has room, its issue slots do not): -2.7 %
+#ifndef EML_TL2_SMEM_TRANSPOSE
+#define EML_TL2_SMEM_TRANSPOSE 1   // d = 16 conjugate transpose through shared memory (as d = 8) instead of 32 SHFL + 64 FSEL:
+#endif                             // -2.3 % with the parity-blocked variant (was +1 % when the kernel was FP64-pipe bound)
 constexpr int CHEB_KCAP_TL2 = EML_CHEB_KCAP_TL2, CHEB_KCAP_TL1 = 256;
+constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
 
 template <int TL, bool CHEB>
 struct alignas(16) WarpScratch {
@@ -66,7 +77,7 @@ struct alignas(16) WarpScratch {
     double kd[8];       // [bitpos][ra]: diagonal of sum rate * A^dag A per site
     double colsum[16];
     double misc[4];
-    double xt_re[TL == 1 ? 128 : 2], xt_im[TL == 1 ? 128 : 2];   // d = 8: X' staged column-major (swizzled) for the conjugate transpose
+    double xt_re[TL == 1 ? 128 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2)], xt_im[TL == 1 ? 128 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2)];   // X' staged column-major (swizzled) for the conjugate transpose
     alignas(16) double tr[(KCAP + 1) * 4];                        // partial traces of the Chebyshev terms
 };
 static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
@@ -552,7 +563,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         };
         // w = X' + X'^dag (the conjugate transpose gathered with shuffles, d = 8: through shared memory)
         auto symmetrise = [&](const double (&x_re)[TL][TL][2], const double (&x_im)[TL][TL][2], double (&w_re)[TL][TL][2], double (&w_im)[TL][TL][2]) {
-            if constexpr (TL == 2) {     // d = 16: shuffles (measured 1 % faster than the shared-memory route)
+            if constexpr (TL == 2 && !EML_TL2_SMEM_TRANSPOSE) {     // d = 16: shuffles (measured faster than the shared-memory route)
 #pragma unroll
             for (int I = 0; I < TL; ++I)
 #pragma unroll
@@ -797,6 +808,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 auto run_terms = [&](auto na_tag) {
                     constexpr bool NA = decltype(na_tag)::value;     // accumulate the state at the step end
                     int hsub = 0;
+                    [[maybe_unused]] double hmul = 1.0;
+#pragma unroll CHEB_UNROLL
                     for (int k = 0; UNI(k < Kc); ++k) {
                         trace_store(v_re, v_im, &S.tr[k * 4]);       // partial trace of term k (overlaps the DMMAs below)
                         if constexpr (NA) {
@@ -829,10 +842,14 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
-                                    ph_re[I][J][e] = scale_pow2(v_re[I][J][e], hsub); ph_im[I][J][e] = scale_pow2(v_im[I][J][e], hsub);
+                                    if constexpr (EML_HALVE_ON_FP64 == 1 || (EML_HALVE_ON_FP64 == 2 && PARITY)) {
+                                        ph_re[I][J][e] = hmul * v_re[I][J][e]; ph_im[I][J][e] = hmul * v_im[I][J][e];
+                                    } else {
+                                        ph_re[I][J][e] = scale_pow2(v_re[I][J][e], hsub); ph_im[I][J][e] = scale_pow2(v_im[I][J][e], hsub);
+                                    }
                                     v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
                                 }
-                        hsub = 0x00100000;
+                        hsub = 0x00100000; hmul = 0.5;
                     }
                     trace_store(v_re, v_im, &S.tr[Kc * 4]);          // the last term
                     if constexpr (NA) {

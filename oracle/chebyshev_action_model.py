@@ -96,7 +96,7 @@ def make_plan(spread, dlo, dhi, dasym, span, zcap, kcap):
     return R, S, ac, tau_max
 
 
-def evaluate(H, c_ops, rho0, obs, times, kcap=640):
+def evaluate(H, c_ops, rho0, obs, times, kcap=512):
     """Returns expect (K, T complex), number of generator applications, info dict."""
     d = H.shape[0]
     times = np.asarray(times, float)

@@ -26,7 +26,7 @@ def test_edge_cases_on_the_gpu(name):
 
 
 def test_wide_spectrum_splits_into_macro_steps_at_every_size():
-    """Couplings at the upper bound and a long grid: more terms than the trace tables hold (640 / 256 / 1024), so the
+    """Couplings at the upper bound and a long grid: more terms than the trace tables hold (512 / 256 / 1024), so the
     end-of-step state path runs several times; d = 8, 16 and 32."""
     from effective_model_learning_b200 import engine
     for n_def, n_q in ((2, 1), (3, 1), (3, 2)):
