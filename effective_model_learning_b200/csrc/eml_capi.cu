@@ -347,8 +347,13 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     const size_t ne = (size_t)n_models * plan->P.n_obs * plan->P.n_times * 2;
     cudaStream_t s = plan->stream;
     if (np) {
-        std::memcpy(plan->h_params, params, np * sizeof(double));
-        EML_CUDA(cudaMemcpyAsync(plan->d_params, plan->h_params, np * sizeof(double), cudaMemcpyHostToDevice, s));
+        // staged in chunks so that the DMA of one chunk overlaps the host copy of the next
+        const size_t chunk = (size_t)1 << 15;      // 256 KB of doubles
+        for (size_t off = 0; off < np; off += chunk) {
+            const size_t cnt = (np - off < chunk) ? np - off : chunk;
+            std::memcpy(plan->h_params + off, params + off, cnt * sizeof(double));
+            EML_CUDA(cudaMemcpyAsync(plan->d_params + off, plan->h_params + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+        }
     }
     if (target_set) {
         std::memcpy(plan->h_tset, target_set, n_models * sizeof(int));
@@ -366,7 +371,7 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     if (cur >= 0 && cur != plan->device) cudaSetDevice(cur);
     for (long long i = 0; i < n_models; ++i)
         if (plan->h_status[i] < 0)
-            return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " hit the Taylor cap");
+            return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " did not converge (series cap or non-finite generator)");
     return EML_OK;
 }
 

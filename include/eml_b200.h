@@ -44,7 +44,7 @@ typedef enum EmlStatus {
     EML_ERR_INVALID_ARGUMENT = -1,
     EML_ERR_CUDA = -2,
     EML_ERR_UNSUPPORTED = -3,   /* e.g. n_tls outside 1..5 */
-    EML_ERR_NOT_CONVERGED = -4, /* a model hit the Taylor cap (reported by the host entry point) */
+    EML_ERR_NOT_CONVERGED = -4, /* a model did not converge: series cap hit or non-finite generator (reported by the host entry point) */
     EML_ERR_NO_DEVICE = -5
 } EmlStatus;
 
@@ -89,8 +89,9 @@ typedef struct EmlPlan EmlPlan; /* opaque */
 
 /* Tunables of the evaluator (0 / negative = keep default). */
 typedef struct EmlOptions {
-    double theta_target; /* norm-bound * step targeted per Taylor expansion (default and maximum 16) */
-    double tol;          /* absolute per-element stopping tolerance (default 1e-11) */
+    double theta_target; /* Taylor-series kernels: norm-bound * step targeted per expansion (default and maximum 16) */
+    double tol;          /* Taylor-series kernels: absolute per-element stopping tolerance (default 1e-11); the
+                            Chebyshev kernels truncate at |J_k| < 1e-14 regardless */
     int32_t kernel;      /* EML_KERNEL_AUTO or a specific kernel, for tests/benchmarks */
     int32_t reserved;
 } EmlOptions;
@@ -118,8 +119,8 @@ int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* tar
  *   target_set  [n_models] or NULL       which target set each model is scored against (NULL = set 0)
  *   expect      [n_models][K][T][2] or NULL   <O_m>(t_k), complex
  *   loss        [n_models] or NULL       sum_m sum_k |expect - target|^2 / (T*K)   (learning_chain.py:738-742)
- *   status      [n_models] or NULL       >= 0: number of generator applications (Taylor terms) the model
- *                                        needed; -1: the Taylor cap was hit (result not converged)
+ *   status      [n_models] or NULL       >= 0: number of generator applications (series terms) the model
+ *                                        needed; -1: not converged (series cap hit, or a non-finite / absurd generator)
  * `stream` is a cudaStream_t passed as void*.
  */
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
