@@ -143,7 +143,7 @@ def run_reference(args):
         'gpu_launches': 0,
         'rjmcmc_equivalent_steps_per_s': value / 3.0,   # the reference spends 3 evaluations per RJMCMC step
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -428,13 +428,30 @@ def run_b200(args):
                                           '(ZVODE adams/12, atol 1e-8, rtol 1e-6), one process per core',
                                 'max_abs_loss_diff_vs_gpu': float(np.abs(np.array(cpu_loss) - loss_host[:n]).max())}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # libraries (NCCL's version banner, for one) write to file descriptor 1: keep stdout for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
