@@ -873,10 +873,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 n_apply += Kc;
                 __syncwarp();
                 if (UNI(last)) {
-                    // ---- outputs of the step: lane l takes outputs l, l + 32, ...; Bessel weights by backward recurrence
+                    // ---- outputs of the step, 32 per round, Bessel weights by backward recurrence.  A round costs as many
+                    //      iterations as its LATEST output needs terms, so the rounds are cut from the end of the list: the
+                    //      partial round is the one with the earliest (cheapest) output times.
                     for (int pbase = 0; UNI(pbase < q); pbase += 32) {
-                        const int p = pbase + lane;
-                        const bool act = p < q;
+                        const int p = q - 1 - pbase - lane;
+                        const bool act = p >= 0;
                         const double tau = act ? ((nsub == 1) ? P.times[kidx + 1 + p] - t0 : tau_end) : 0.0;
                         const double z = tau * Rb;
                         const bool direct = !(z >= 1e-40);
