@@ -341,11 +341,13 @@ def run_b200(args):
     achieved = flops_launch / (kernel_ms * 1e-3)
     canon = canonical_dense_flops(layout.n_tls, N_TIMES, 3)
     traffic = None
+    ncu_pipes = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
             entry = json.load(f).get(f'{plan.kernel_name}:n_tls={layout.n_tls}:chains={B}')
         if entry:
             traffic = entry['bytes']
+            ncu_pipes = {k: entry[k] for k in ('fp64_pipe_pct', 'tensor_fp64_pct', 'issue_pct', 'duration_ms') if k in entry}
     except (OSError, ValueError):
         pass
     roofline = {
@@ -361,6 +363,9 @@ def run_b200(args):
         'canonical_dense_gflop_per_eval': canon / 1e9,
         'canonical_dense_equivalent_tflops': canon * B / (kernel_ms * 1e-3) / 1e12,
         'algorithmic_hbm_bytes_per_eval': 8 * layout.n_params + 8 + 4,
+        # pipe utilisation of the same kernel and workload from the committed ncu capture (percent of peak over the launch;
+        # the FP64 pipe and the FP64 tensor path share one datapath) -- not measured in this run
+        'ncu': ncu_pipes,
     }
 
     line = {
