@@ -392,7 +392,6 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
         auto apply_core = [&](const double (&v_re)[4][2], const double (&v_im)[4][2], double (&x_re)[4][2], double (&x_im)[4][2]) {
 #pragma unroll
             for (int J = 0; J < 4; ++J) {
-                const int base = 8 * J + 2 * t;
                 // bit 4: (I^2, J^2); bit 3: (I^1, J^1); bit 2: (g^4, t^2); bit 1: (g^2, t^1); bit 0: (g^1, e^1)
                 // PARITY: a flip of a site below the observed one also flips the top (parity) tile bit of row and column
                 constexpr int PX = PARITY ? 2 : 0;

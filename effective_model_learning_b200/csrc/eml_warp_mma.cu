@@ -58,6 +58,9 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 #ifndef EML_HALVE_ON_FP64
 #define EML_HALVE_ON_FP64 2        // halving of the stored term: 0 integer-pipe exponent decrement, 1 DMUL, 2 DMUL in the
 #endif                             // parity-blocked variant only (its FP64 pipe has room, its issue slots do not): -2.7 %
+#ifndef EML_TL2_SMEM_STENCIL
+#define EML_TL2_SMEM_STENCIL 0     // 1: d = 16 lane-bit site stencils read the published term from shared memory
+#endif                             // (8 STS.128 + 24 LDS.128) instead of 96 SHFL
 #ifndef EML_TL2_SMEM_TRANSPOSE
 #define EML_TL2_SMEM_TRANSPOSE 1   // d = 16 conjugate transpose through shared memory (as d = 8) instead of 32 SHFL + 64 FSEL:
 #endif                             // -2.3 % with the parity-blocked variant (was +1 % when the kernel was FP64-pipe bound)
@@ -77,7 +80,9 @@ struct alignas(16) WarpScratch {
     double kd[8];       // [bitpos][ra]: diagonal of sum rate * A^dag A per site
     double colsum[16];
     double misc[4];
-    double xt_re[TL == 1 ? 128 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2)], xt_im[TL == 1 ? 128 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2)];   // X' staged column-major (swizzled) for the conjugate transpose
+    static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
+    alignas(16) double xt_re[XT];
+    alignas(16) double xt_im[XT];   // X' staged column-major (swizzled) for the conjugate transpose
     alignas(16) double tr[(KCAP + 1) * 4];                        // partial traces of the Chebyshev terms
 };
 static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
@@ -482,6 +487,38 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             }
                         }
             }
+            if constexpr (TL == 2 && EML_TL2_SMEM_STENCIL) {
+                // the term is published row-major (ld 24: conflict-free 16-byte accesses over (g, t)) in the buffer the
+                // transposition uses later; every lane-bit site then costs one LDS.128 per tile and plane
+                constexpr int LD = 24;
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J) {
+                        *reinterpret_cast<double2*>(&S.xt_re[(8 * I + g) * LD + 8 * J + 2 * t]) = make_double2(v_re[I][J][0], v_re[I][J][1]);
+                        *reinterpret_cast<double2*>(&S.xt_im[(8 * I + g) * LD + 8 * J + 2 * t]) = make_double2(v_im[I][J][0], v_im[I][J][1]);
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J) {
+                        const int ro = 8 * (I ^ PX), co = 8 * (J ^ PX);
+                        const int o2 = (ro + (g ^ 4)) * LD + co + 2 * (t ^ 2);
+                        const int o1 = (ro + (g ^ 2)) * LD + co + 2 * (t ^ 1);
+                        const int o0 = (ro + (g ^ 1)) * LD + co + 2 * t;
+                        const double2 r2 = *reinterpret_cast<const double2*>(&S.xt_re[o2]), i2 = *reinterpret_cast<const double2*>(&S.xt_im[o2]);
+                        const double2 r1 = *reinterpret_cast<const double2*>(&S.xt_re[o1]), i1 = *reinterpret_cast<const double2*>(&S.xt_im[o1]);
+                        const double2 r0 = *reinterpret_cast<const double2*>(&S.xt_re[o0]), i0 = *reinterpret_cast<const double2*>(&S.xt_im[o0]);
+                        x_re[I][J][0] = fma(f2, r2.x, x_re[I][J][0]); x_re[I][J][1] = fma(f2, r2.y, x_re[I][J][1]);
+                        x_im[I][J][0] = fma(f2, i2.x, x_im[I][J][0]); x_im[I][J][1] = fma(f2, i2.y, x_im[I][J][1]);
+                        x_re[I][J][0] = fma(f1, r1.x, x_re[I][J][0]); x_re[I][J][1] = fma(f1, r1.y, x_re[I][J][1]);
+                        x_im[I][J][0] = fma(f1, i1.x, x_im[I][J][0]); x_im[I][J][1] = fma(f1, i1.y, x_im[I][J][1]);
+                        x_re[I][J][0] = fma(f0[0], r0.y, x_re[I][J][0]); x_re[I][J][1] = fma(f0[1], r0.x, x_re[I][J][1]);   // e ^ 1
+                        x_im[I][J][0] = fma(f0[0], i0.y, x_im[I][J][0]); x_im[I][J][1] = fma(f0[1], i0.x, x_im[I][J][1]);
+                    }
+                __syncwarp();      // the buffer is reused by the transposition
+            } else {
             {
 #pragma unroll
                 for (int I = 0; I < TL; ++I)
@@ -514,6 +551,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e ^ 1], 4), x_re[I][J][e]);
                             x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e ^ 1], 4), x_im[I][J][e]);
                         }
+            }
             }
             // ---- X' = J(v)/2 + G v on the DMMA pipe (B fragments = conj of own registers):
             //      X.re += a.re*b_re + a.im*b_im ; X.im += -a.re*b_im + a.im*b_re   (B = conj(b))
