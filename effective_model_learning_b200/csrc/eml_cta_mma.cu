@@ -1,8 +1,9 @@
 // d = 32 (n_tls = 5) evaluator: ONE CTA OF FOUR WARPS PER MODEL, FP64 DMMA.
 //
-// Same algorithm and register layout as eml_warp_mma.cu (Taylor action with dense output on the d x d density
-// matrix, Hermitian B-operand trick, real-weighted site stencils, accumulators started from J(v)/2), scaled up:
-// warp w owns the tile row I = w (rows 8w .. 8w+7) of rho, of the current Taylor term v and of X = G v, each as
+// Same algorithms and register layout as eml_warp_mma.cu (Chebyshev / Bessel series by default, Taylor series with
+// dense output as the cross-check, both acting on the d x d density matrix; Hermitian B-operand trick, real-weighted
+// site stencils, accumulators started from J(v)/2; parity-blocked G when H conserves the index parity), scaled up:
+// warp w owns the tile row I = w (rows 8w .. 8w+7) of rho, of the current series term v and of X = G v, each as
 // 4 column tiles x 2 elements per lane -- the same 16 complex numbers per lane as the d = 16 kernel.  What a warp
 // needs from the other rows goes through shared memory, twice per generator application:
 //   Vs  (row-major, ld 40)  the whole current term: B fragments v[k][n] = conj(v[n][k]) and all five site stencils

@@ -1,5 +1,5 @@
 // d = 8 and d = 16 (n_tls = 3, 4; smaller models are embedded) evaluator: ONE WARP PER MODEL, density matrix and
-// Taylor terms resident in registers in the FP64 mma.m8n8k4 accumulator layout, generator product on the DMMA pipe.
+// series terms resident in registers in the FP64 mma.m8n8k4 accumulator layout, generator product on the DMMA pipe.
 //
 //   L rho = X + X^dag + J(rho),  X = G rho  (rho Hermitian => rho G^dag = X^dag),  G = -iH - 1/2 sum c^dag c
 //   J(rho)[r,c] = W0[r,c] rho[r,c] + sum_sites F_s[r_s,c_s] rho[r ^ m_s, c ^ m_s]   (real weights)
@@ -8,19 +8,24 @@
 // (r, c) = (8I + g, 8J + 2t + e) -- exactly the m8n8 accumulator fragment, so X lands where rho lives.
 // Because rho is Hermitian the B operand rho[k][n] = conj(rho[n][k]) is ALSO in the lane's own registers when
 // the k index of k-step ks is permuted to pi(ks,t) = 8(ks/2) + 2t + (ks%2); G's A fragments are loaded once per
-// model with the same permutation.  X^dag needs 32 shuffles per application (d = 8: a swizzled, conflict-free
-// shared-memory round trip instead), the site stencils 32 per site (none for the site mapped to the tile bits), the
-// partial trace for the observables 12.
+// model with the same permutation.  X^dag is gathered through a swizzled, conflict-free shared-memory round trip
+// (or 32 shuffles), the site stencils cost 32 shuffles per site (none for the site mapped to the tile bits).
+// The accumulators of the DMMA start from J(u)/2 (weights stored halved), so X' + X'^dag = G u + u G^dag + J(u).
 //
-// Series: the generator is kept pre-multiplied by the current step length h, u_{j+1} = (hL) u_j, and the Taylor
-// term is u_j / j! -- no per-element scaling; rho(t_s + x h) = sum_j (x^j / j!) u_j, so interior output times only
-// need the 2x2 partial trace of every u_j (dense output), NY accumulators per lane.  The accumulators of the DMMA
-// start from J(u)/2 (weights stored halved), so X' + X'^dag = G u + u G^dag + J(u).
+// Two series turn generator applications into the propagator action (template flag CHEB):
+//   CHEB = true (default, kernel ids "warp_cheb*"): Chebyshev / Bessel series, see eml_cheb.cuh -- one three-term
+//     recurrence serves every output time of a macro step; only the 2x2 partial trace of each term is kept (shared
+//     memory) and each output is a Bessel-weighted sum of them (Miller's backward recurrence, one lane per output).
+//   CHEB = false ("warp_mma*", the independent cross-check): Taylor series with dense output -- the generator is kept
+//     pre-multiplied by the step length h, u_{j+1} = (hL) u_j, rho(t_s + x h) = sum_j (x^j / j!) u_j, NY dense-output
+//     accumulators per lane, a macro step is limited to nu h <= 16 by the e^theta cancellation hump.
+// PARITY (d = 16, CHEB): H block diagonal by the parity of the basis index -> half the DMMAs (see the kernel body).
+//
 // Control flow is made provably warp-uniform with votes (UNI), which keeps ptxas from guarding every shuffle
 // against divergence and lets it schedule SHFL / DFMA / DMMA of one application in a single basic block.
 //
-// TL = d/8 tiles per side: d = 16 has 2x2 tiles per lane (the observed site on the tile bits), d = 8 a single
-// tile (all three site stencils go through shuffles).
+// TL = d/8 tiles per side: d = 16 has 2x2 tiles per lane (the observed site, or the parity, on the tile bits),
+// d = 8 a single tile (all three site stencils go through shuffles).
 //
 // Requirements (checked at plan creation, else the generic kernel runs): n_tls == 3 or 4, Hermitian H and rho0,
 // every jump operator A has A (x) conj(A) real with only "diagonal" and "both bits flipped" entries
