@@ -314,13 +314,15 @@ def run_b200(args):
         elapsed_ms, kernel_ms = float(t[0]), float(t[1])
     value = B * world * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- end-to-end through the public host API: host params in, host loss out, every step
+    # ---- end-to-end through the public host API: params in page-locked host memory in, host loss out, every step
+    params_pinned = torch.from_numpy(params_host).pin_memory().numpy()
+    loss_pinned = torch.empty(B, dtype=torch.float64).pin_memory().numpy()
     for _ in range(2):
-        ctx.evaluate(params_host, want_expect=False, want_loss=True)
+        ctx.evaluate(params_pinned, want_expect=False, want_loss=True, loss_out=loss_pinned)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, loss_host = ctx.evaluate(params_host, want_expect=False, want_loss=True)
+        _, loss_host = ctx.evaluate(params_pinned, want_expect=False, want_loss=True, loss_out=loss_pinned)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -188,13 +188,22 @@ class Plan:
         check(self._lib.eml_plan_set_targets(self._h, tg.shape[0], _dptr(tg.view(np.float64))), 'eml_plan_set_targets')
         self.n_target_sets = tg.shape[0]
 
-    def eval_host(self, params, target_set=None, want_expect=True, want_loss=True):
-        """params: [B][P] float64 host array.  Returns (expect [B][K][T] complex | None, loss [B] | None)."""
+    def eval_host(self, params, target_set=None, want_expect=True, want_loss=True, loss_out=None, expect_out=None):
+        """params: [B][P] float64 host array.  Returns (expect [B][K][T] complex | None, loss [B] | None).
+        loss_out / expect_out: optional preallocated result arrays; page-locked arrays (and page-locked params, e.g.
+        views of torch pin_memory() tensors) are used for the DMA directly instead of the plan's staging buffers."""
         params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 0)) \
             if self.n_params > 0 else np.zeros((int(np.shape(params)[0]), 0))
         B = params.shape[0]
-        expect = np.empty((B, self.n_obs, self.n_times), dtype=np.complex128) if want_expect else None
-        loss = np.empty(B, dtype=np.float64) if want_loss else None
+        expect = loss = None
+        if want_expect:
+            expect = expect_out if expect_out is not None else np.empty((B, self.n_obs, self.n_times), dtype=np.complex128)
+            if expect.shape != (B, self.n_obs, self.n_times) or expect.dtype != np.complex128 or not expect.flags.c_contiguous:
+                raise RuntimeError('expect_out must be a C-contiguous complex128 array of shape [B][K][T]')
+        if want_loss:
+            loss = loss_out if loss_out is not None else np.empty(B, dtype=np.float64)
+            if loss.shape != (B,) or loss.dtype != np.float64 or not loss.flags.c_contiguous:
+                raise RuntimeError('loss_out must be a C-contiguous float64 array of shape [B]')
         ts = None
         if target_set is not None:
             ts = np.ascontiguousarray(target_set, dtype=np.int32)

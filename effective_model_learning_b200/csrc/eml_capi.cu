@@ -346,7 +346,19 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     const size_t np = (size_t)n_models * plan->P.n_params;
     const size_t ne = (size_t)n_models * plan->P.n_obs * plan->P.n_times * 2;
     cudaStream_t s = plan->stream;
-    if (np) {
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for the DMA directly
+    auto is_pinned = [](const void* ptr) {
+        if (!ptr) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool params_pinned = np && is_pinned(params);
+    const bool loss_pinned = loss && is_pinned(loss);
+    const bool expect_pinned = expect && is_pinned(expect);
+    if (params_pinned) {
+        EML_CUDA(cudaMemcpyAsync(plan->d_params, params, np * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else if (np) {
         // staged in chunks so that the DMA of one chunk overlaps the host copy of the next
         const size_t chunk = (size_t)1 << 15;      // 256 KB of doubles
         for (size_t off = 0; off < np; off += chunk) {
@@ -362,12 +374,12 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     rc = eml_eval_batch(plan, n_models, plan->d_params, target_set ? plan->d_tset : nullptr,
                         expect ? plan->d_expect : nullptr, loss ? plan->d_loss : nullptr, plan->d_status, s);
     if (rc != EML_OK) return rc;
-    if (expect) EML_CUDA(cudaMemcpyAsync(plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (loss) EML_CUDA(cudaMemcpyAsync(plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (expect) EML_CUDA(cudaMemcpyAsync(expect_pinned ? expect : plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (loss) EML_CUDA(cudaMemcpyAsync(loss_pinned ? loss : plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
     EML_CUDA(cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s));
     EML_CUDA(cudaStreamSynchronize(s));
-    if (expect) std::memcpy(expect, plan->h_expect, ne * sizeof(double));
-    if (loss) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
+    if (expect && !expect_pinned) std::memcpy(expect, plan->h_expect, ne * sizeof(double));
+    if (loss && !loss_pinned) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
     if (cur >= 0 && cur != plan->device) cudaSetDevice(cur);
     for (long long i = 0; i < n_models; ++i)
         if (plan->h_status[i] < 0)

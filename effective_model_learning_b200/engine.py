@@ -162,8 +162,9 @@ class EvalContext:
                 out[b, self.columns[key]] = val
         return out
 
-    def evaluate(self, params, target_set=None, want_expect=True, want_loss=False):
-        return self.plan.eval_host(params, target_set, want_expect=want_expect, want_loss=want_loss)
+    def evaluate(self, params, target_set=None, want_expect=True, want_loss=False, loss_out=None, expect_out=None):
+        return self.plan.eval_host(params, target_set, want_expect=want_expect, want_loss=want_loss,
+                                   loss_out=loss_out, expect_out=expect_out)
 
 
 def context_for(model, obs_names, times, device=None) -> EvalContext:

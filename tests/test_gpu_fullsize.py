@@ -69,3 +69,21 @@ def test_full_size_batch_properties(Q, D, B):
         spec = spec_from_context_row(ctx, params[b])
         want_b = np.array([np.asarray(e) for e in lo.expect_exact(spec, TS, ['sigmax', 'sigmay', 'sigmaz'])])
         assert np.abs(ex[b] - want_b.real).max() < 1e-11, b
+
+
+def test_page_locked_caller_buffers_are_used_directly_and_give_the_same_results():
+    """eml_eval_batch_host DMAs straight from / into page-locked caller arrays (no staging copy): same bits as pageable."""
+    import torch
+    lay = _layout(1, 2)
+    params = lay.batch_params(2000 + np.arange(300))
+    ctx = lay.context(TS, ['sigmax', 'sigmay', 'sigmaz'])
+    ctx.set_targets(np.zeros((3, len(TS))))
+    ex, loss = ctx.evaluate(params, want_expect=True, want_loss=True)
+    p_pin = torch.from_numpy(params).pin_memory().numpy()
+    loss_pin = torch.empty(300, dtype=torch.float64).pin_memory().numpy()
+    ex_pin = torch.empty((300, 3, len(TS)), dtype=torch.complex128).pin_memory().numpy()
+    ex2, loss2 = ctx.evaluate(p_pin, want_expect=True, want_loss=True, loss_out=loss_pin, expect_out=ex_pin)
+    assert ex2 is ex_pin and loss2 is loss_pin
+    assert np.array_equal(ex2, ex) and np.array_equal(loss2, loss)
+    with pytest.raises(RuntimeError, match='loss_out'):
+        ctx.evaluate(params, want_expect=False, want_loss=True, loss_out=np.empty(7))
