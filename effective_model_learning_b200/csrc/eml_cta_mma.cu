@@ -606,14 +606,14 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                         if (act && !direct) { Kp = cheb_terms(tau * Sb); if (Kp > Kc) Kp = Kc; }
                         const int kmax = __reduce_max_sync(0xffffffffu, Kp);
                         const double tz = direct ? 0.0 : 2.0 / z;
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+                        double a0 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
                         double kd = (double)kmax;
 #pragma unroll 2
                         for (int k = kmax; k >= 1; --k, kd -= 1.0) {
                             if (k == Kp) jn = 1.0;
                             const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
                             const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
-                            a0 = fma(jn, ta.x, a0); a1 = fma(jn, ta.y, a1); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            a0 = fma(jn, ta.x, a0); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
                             if (!(k & 1)) ssum += jn;
                             const double jm = fma(kd * tz, jn, -jn1);
                             jn1 = jn; jn = jm;
@@ -625,7 +625,8 @@ eval_cta_mma_kernel(const DevProblem P, const long long n_models, const double* 
                             r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
                         } else {
                             const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
-                            r[0] = fma(jn, ta.x, a0) * nrm; r[1] = fma(jn, ta.y, a1) * nrm;
+                            // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
+                            r[0] = fma(jn, ta.x, a0) * nrm; r[1] = (ta.x + ta.y) - r[0];
                             r[2] = fma(jn, tb.x, a2) * nrm; r[3] = fma(jn, tb.y, a3) * nrm;
                         }
                         if (act) finish_output(kidx + 1 + p, r);
