@@ -19,6 +19,7 @@ EML_OK = 0
 EML_ERR_NOT_CONVERGED = -4
 TERM_ENERGY, TERM_COUPLING, TERM_LINDBLAD = 0, 1, 2
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_WARP_MMA, KERNEL_CTA_MMA, KERNEL_WARP_CHEB, KERNEL_CTA_CHEB = 0, 1, 2, 3, 4, 5
+FLAG_NO_SECTOR_REDUCTION = 1     # EmlOptions.reserved bit 0: evolve the whole density matrix even when a parity sector is steady
 
 # every symbol include/eml_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
@@ -134,7 +135,7 @@ class Plan:
     """Owns one EmlPlan (device copies of the data shared by a batch of models)."""
 
     def __init__(self, n_tls, n_params, terms, op_table, rho0, obs_site, obs, times, targets=None,
-                 device=0, kernel=KERNEL_AUTO, theta_target=0.0, tol=0.0):
+                 device=0, kernel=KERNEL_AUTO, theta_target=0.0, tol=0.0, flags=0):
         lib = load()
         self._lib = lib
         self.n_tls, self.n_params = int(n_tls), int(n_params)
@@ -164,7 +165,7 @@ class Plan:
                               int(obs_site), self.n_obs, _dptr(self.obs.view(np.float64)),
                               self.n_times, _dptr(self.times),
                               nsets, _dptr(tg.view(np.float64)) if tg is not None else None)
-        opts = EmlOptions(float(theta_target), float(tol), int(kernel), 0)
+        opts = EmlOptions(float(theta_target), float(tol), int(kernel), int(flags))
         handle = C.c_void_p()
         check(lib.eml_plan_create(C.byref(desc), int(device), C.byref(opts), C.byref(handle)), 'eml_plan_create')
         self._h = handle

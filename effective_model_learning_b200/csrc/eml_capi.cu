@@ -15,7 +15,7 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h, bool chebyshev,
-                            bool parity_h, const int* cost_hint, cudaStream_t stream);
+                            bool parity_h, bool sector_b, const int* cost_hint, cudaStream_t stream);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
@@ -191,6 +191,32 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         }
     }
     plan->parity_h = parity;
+    // Steady parity-even sector (d = 16 kernel): in the parity coordinates the even tiles of rho evolve independently of
+    // the odd ones; they are a steady state when they are a multiple of the identity and every jump operator of the
+    // library is unital (A A^dag = A^dag A).  Then only the odd tiles are evolved (EmlOptions.reserved bit 0 disables it).
+    bool sector = parity && d->n_tls == 4 && !(opts && (opts->reserved & 1));
+    for (int t = 0; t < d->n_terms && sector; ++t) {
+        if (d->terms[t].kind != EML_TERM_LINDBLAD) continue;
+        const double* A = d->op_table + d->terms[t].op_a * 8;      // [[a, b], [c, d]] complex
+        // (A A^dag - A^dag A)_00 = |b|^2 - |c|^2;  (..)_01 = a conj(c) + b conj(d) - conj(a) b - conj(c) d
+        const double bb = A[2] * A[2] + A[3] * A[3], cc = A[4] * A[4] + A[5] * A[5];
+        const double ore = (A[0] * A[4] + A[1] * A[5]) + (A[2] * A[6] + A[3] * A[7]) - (A[0] * A[2] + A[1] * A[3]) - (A[4] * A[6] + A[5] * A[7]);
+        const double oim = (A[1] * A[4] - A[0] * A[5]) + (A[3] * A[6] - A[2] * A[7]) - (A[0] * A[3] - A[1] * A[2]) - (A[4] * A[7] - A[5] * A[6]);
+        if (std::fabs(bb - cc) > 1e-15 || std::fabs(ore) > 1e-15 || std::fabs(oim) > 1e-15) sector = false;
+    }
+    if (sector) {
+        const int Dn = 1 << d->n_tls;
+        double tr = 0.0;
+        for (int r = 0; r < Dn; ++r) tr += d->rho0[2 * (r * Dn + r)];
+        auto par = [](int x) { return __builtin_popcount((unsigned)x) & 1; };
+        for (int r = 0; r < Dn && sector; ++r)
+            for (int c = 0; c < Dn; ++c) {
+                if (par(r) != par(c)) continue;
+                const double want = (r == c) ? tr / Dn : 0.0;
+                if (std::fabs(d->rho0[2 * (r * Dn + c)] - want) > 1e-15 || std::fabs(d->rho0[2 * (r * Dn + c) + 1]) > 1e-15) { sector = false; break; }
+            }
+    }
+    plan->sector_b = sector;
     // Models with fewer than 3 sites are embedded for the warp kernel: spectator sites (identity dynamics,
     // state |0><0|) are appended as the least significant factors, which changes neither the reduced dynamics of
     // the real sites nor the observables.
@@ -250,6 +276,7 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
     if (!plan) return "";
     if (plan->kernel == EML_KERNEL_WARP_MMA) return plan->real_h ? "warp_mma_realH" : "warp_mma";
     if (plan->kernel == EML_KERNEL_WARP_CHEB) {
+        if (plan->sector_b && plan->Pw.n_tls == 4) return plan->real_h ? "warp_cheb_parity_sector_realH" : "warp_cheb_parity_sector";
         if (plan->parity_h && plan->Pw.n_tls == 4) return plan->real_h ? "warp_cheb_parity_realH" : "warp_cheb_parity";
         return plan->real_h ? "warp_cheb_realH" : "warp_cheb";
     }
@@ -282,7 +309,7 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA || plan->kernel == EML_KERNEL_WARP_CHEB)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
-                                 plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
+                                 plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, plan->sector_b, cost_hint, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
                                 plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);

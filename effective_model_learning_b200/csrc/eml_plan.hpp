@@ -25,6 +25,7 @@ struct EmlPlan {
     bool hermitian = false;   // H (every coupling term set) and rho0 Hermitian -> specialised kernels allowed
     bool real_h = false;      // additionally every Hamiltonian term is a real matrix (G.re diagonal): half the DMMAs
     bool parity_h = false;    // additionally every Hamiltonian term conserves the parity of the basis index: G block diagonal
+    bool sector_b = false;    // additionally the parity-even part of rho0 is a steady state (d = 16): only the odd tiles evolve
     std::vector<void*> owned; // device allocations
     // staging for the host entry point
     cudaStream_t stream = nullptr;

@@ -71,11 +71,14 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 #endif                             // -2.3 % with the parity-blocked variant (was +1 % when the kernel was FP64-pipe bound)
 constexpr int CHEB_KCAP_TL2 = EML_CHEB_KCAP_TL2, CHEB_KCAP_TL1 = 256;
 constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
+constexpr int CHEB_KCAP_SB = 540;      // sector variant: 12 warps per SM, two trace values per term
+constexpr int CTAS_PER_SM_SB = 3;
 
-template <int TL, bool CHEB>
+template <int TL, bool CHEB, bool SB = false>
 struct alignas(16) WarpScratch {
     static constexpr int D = 8 * TL;
-    static constexpr int KCAP = CHEB ? (TL == 2 ? CHEB_KCAP_TL2 : CHEB_KCAP_TL1) : 0;
+    static constexpr int KCAP = CHEB ? (TL == 2 ? (SB ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1) : 0;
+    static constexpr int NTR = SB ? 2 : 4;      // partial-trace values kept per term
     // G_re, G_im, par are contiguous: dead once the A fragments are in registers, the Chebyshev path reuses them
     // for the coefficient table of the step end (KCAP + 1 <= 2 D (D + 1) + MAXP doubles)
     double G_re[D][D + 1];
@@ -88,9 +91,10 @@ struct alignas(16) WarpScratch {
     static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
     alignas(16) double xt_re[XT];
     alignas(16) double xt_im[XT];   // X' staged column-major (swizzled) for the conjugate transpose
-    alignas(16) double tr[(KCAP + 1) * 4];                        // partial traces of the Chebyshev terms
+    alignas(16) double tr[(KCAP + 1) * NTR];                      // partial traces of the Chebyshev terms
 };
-static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
+static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_SB + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
+static_assert((CHEB_KCAP_SB + 1) * 2 >= 4 * 16 * 16, "the trace table doubles as scratch for the spread bound");
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     }
 }
 
-template <int TL, bool REAL_H, bool CHEB, bool PARITY>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : CTAS_PER_SM)
+template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : (SB ? CTAS_PER_SM_SB : CTAS_PER_SM))
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
@@ -180,6 +184,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
     static_assert(!PARITY || (CHEB && TL == 2), "the parity-blocked variant exists for the d = 16 Chebyshev kernel");
+    static_assert(!SB || PARITY, "the sector variant builds on the parity coordinates");
+    // SB ("sector B only"): in the parity coordinates the generator maps tile (I, J) to itself (commutator) or to
+    // (I ^ 1, J ^ 1) (site flips), so the parity-even tiles (0,0), (1,1) and the parity-odd tiles (0,1), (1,0) evolve
+    // INDEPENDENTLY.  When the parity-even part of rho0 is a multiple of the identity and every jump operator of the
+    // library is unital (c c^dag = c^dag c: the Paulis), that part is a steady state: rho00 and rho11 of the observed
+    // site stay at Tr(rho0) / 2 and only the two odd tiles -- half the state, half of every stencil, shuffle and DMMA --
+    // are evolved.  Both conditions are properties of the plan (checked at plan creation): the production initial state
+    // of the reference (qubit |+><+|, defects maximally mixed, execute_learning_full.py:151-164) with any configs.py library.
+    auto live = [](const int I, const int J) { return !SB || (((I ^ J) & 1) != 0); };
     // PARITY (every Hamiltonian term conserves the parity of the computational-basis index: sigma_z energies,
     // diag (x) diag or flip (x) flip couplings -- all libraries of configs.py): H is block diagonal in the coordinates
     // x' = x ^ (parity(x & 7) << 3), i.e. the top (tile) bit of the kernel's row / column index is the PARITY of the
@@ -188,7 +201,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     // flip already was), the lane shuffles are unchanged.
     auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Scratch = WarpScratch<TL, CHEB>;
+    using Scratch = WarpScratch<TL, CHEB, SB>;
+    constexpr int NTR = Scratch::NTR;
     Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -486,6 +500,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
+                            if (!live(I, J)) continue;
                             if (TL == 2) {
                                 x_re[I][J][e] = fma(F3[I][J][e & (FE - 1)], v_re[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_re[I][J][e]);
                                 x_im[I][J][e] = fma(F3[I][J][e & (FE - 1)], v_im[(I ^ 1) & (TL - 1)][(J ^ 1) & (TL - 1)][e], x_im[I][J][e]);
@@ -531,6 +546,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
+                            if (!live(I, J)) continue;
                             x_re[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e], 18), x_re[I][J][e]);
                             x_im[I][J][e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e], 18), x_im[I][J][e]);
                         }
@@ -542,6 +558,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
+                            if (!live(I, J)) continue;
                             x_re[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e], 9), x_re[I][J][e]);
                             x_im[I][J][e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e], 9), x_im[I][J][e]);
                         }
@@ -553,6 +570,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
+                            if (!live(I, J)) continue;
                             x_re[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_re[I ^ PX][J ^ PX][e ^ 1], 4), x_re[I][J][e]);
                             x_im[I][J][e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, v_im[I ^ PX][J ^ PX][e ^ 1], 4), x_im[I][J][e]);
                         }
@@ -568,6 +586,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int I = 0; I < TL; ++I) {
+                            if (!live(I, J)) continue;
                             const double b_re = v_re[J][I][ks], b_im = v_im[J][I][ks];
                             if (!REAL_H) {
                                 dmma(x_re[I][J][0], x_re[I][J][1], a_re[I][ks], b_re);
@@ -611,6 +630,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             for (int I = 0; I < TL; ++I)
 #pragma unroll
                 for (int J = 0; J < TL; ++J) {
+                    if (!live(I, J)) continue;
                     // X^dag[I][J][e] = conj(X[8J+2t+e][8I+g]) gathered from tile (J,I) with shuffles
                     const double sAr = gp ? x_re[J][I][1] : x_re[J][I][0], sBr = gp ? x_re[J][I][0] : x_re[J][I][1];
                     const double sAi = gp ? x_im[J][I][1] : x_im[J][I][0], sBi = gp ? x_im[J][I][0] : x_im[J][I][1];
@@ -635,6 +655,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 for (int J = 0; J < TL; ++J)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
+                        if (!live(I, J)) continue;
                         const int Cc = 8 * J + 2 * t + e;
                         const int m = 4 * (t & 1) + 8 * (((t >> 1) & 1) ^ e);
                         S.xt_re[Cc * 16 + ((8 * I + g) ^ m)] = x_re[I][J][e];
@@ -645,6 +666,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             for (int I = 0; I < TL; ++I)
 #pragma unroll
                 for (int J = 0; J < TL; ++J) {
+                    if (!live(I, J)) continue;
                     const int m = 4 * ((g >> 1) & 1) + 8 * (((g >> 2) & 1) ^ (g & 1));
                     const int o = (8 * I + g) * 16 + ((8 * J + 2 * t) ^ m);
                     const double2 tr_ = *reinterpret_cast<const double2*>(&S.xt_re[o]);
@@ -756,7 +778,18 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // (4 double shuffles) leaves value 2*bit2(g) + bit1(g) in the lanes with g even.
         const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
         auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], double* dst) {
-            if constexpr (TL == 2) {
+            if constexpr (SB) {
+                // only rho01 of the observed site moves: tile (p, 1 ^ p), p = parity of the (equal) low bits; dst[0..1]
+                const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
+                const double a2 = gp ? xr[0][1][1] : xr[0][1][0], a3 = gp ? xi[0][1][1] : xi[0][1][0];
+                const double b2 = gp ? xr[1][0][1] : xr[1][0][0], b3 = gp ? xi[1][0][1] : xi[1][0][0];
+                const double v2 = pl ? b2 : a2, v3 = pl ? b3 : a3;
+                const bool hb = g & 4;
+                double kk = (hb ? v3 : v2) + shfl(hb ? v2 : v3, dl4);
+                kk += shfl(kk, dl2);
+                kk += shfl(kk, dl1);
+                if (diag_lane && (g & 3) == 0) dst[g >> 2] = kk;
+            } else if constexpr (TL == 2) {
                 double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
                 double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
                 if constexpr (PARITY) {
@@ -779,10 +812,18 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         };
         double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
 
+        // SB: rho00 = rho11 = Tr(rho0) / 2 of the observed site never move
+        double half_tr = 0.0;
+        if constexpr (SB) {
+            half_tr = (lane < D) ? P.rho0[2 * (lane * D + lane)] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) half_tr += __shfl_xor_sync(0xffffffffu, half_tr, o);
+            half_tr *= 0.5;
+        }
         {   // the first output time carries the initial state
             trace_store(acc_re, acc_im, &S.tr[0]);
             __syncwarp();
-            const double r[4] = {S.tr[0], S.tr[1], S.tr[2], S.tr[3]};
+            const double r[4] = {SB ? half_tr : S.tr[0], SB ? half_tr : S.tr[1], S.tr[NTR - 2], S.tr[NTR - 1]};
             if (lane == 0) finish_output(0, r);
             __syncwarp();
         }
@@ -805,7 +846,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 __syncwarp();
                 trace_store(acc_re, acc_im, &S.tr[0]);
                 __syncwarp();
-                const double r[4] = {S.tr[0], S.tr[1], S.tr[2], S.tr[3]};
+                const double r[4] = {SB ? half_tr : S.tr[0], SB ? half_tr : S.tr[1], S.tr[NTR - 2], S.tr[NTR - 1]};
                 for (int pbase = 0; UNI(pbase < q); pbase += 32)
                     if (pbase + lane < q) finish_output(kidx + 1 + pbase + lane, r);
                 __syncwarp();
@@ -841,6 +882,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     for (int J = 0; J < TL; ++J)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
+                            if (!live(I, J)) continue;
                             v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e];
                             ph_re[I][J][e] = 0.0; ph_im[I][J][e] = 0.0;
                             acc_re[I][J][e] = 0.0; acc_im[I][J][e] = 0.0;
@@ -854,7 +896,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     [[maybe_unused]] double hmul = 1.0;
 #pragma unroll CHEB_UNROLL
                     for (int k = 0; UNI(k < Kc); ++k) {
-                        trace_store(v_re, v_im, &S.tr[k * 4]);       // partial trace of term k (overlaps the DMMAs below)
+                        trace_store(v_re, v_im, &S.tr[k * NTR]);       // partial trace of term k (overlaps the DMMAs below)
                         if constexpr (NA) {
                             const double c = cJ[k] * cscale;
 #pragma unroll
@@ -863,6 +905,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                 for (int J = 0; J < TL; ++J)
 #pragma unroll
                                     for (int e = 0; e < 2; ++e) {
+                                        if (!live(I, J)) continue;
                                         acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
                                         acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
                                     }
@@ -874,6 +917,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
+                                    if (!live(I, J)) continue;
                                     x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
                                     x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
                                 }
@@ -885,6 +929,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
+                                    if (!live(I, J)) continue;
                                     if constexpr (EML_HALVE_ON_FP64 == 1 || (EML_HALVE_ON_FP64 == 2 && PARITY)) {
                                         ph_re[I][J][e] = hmul * v_re[I][J][e]; ph_im[I][J][e] = hmul * v_im[I][J][e];
                                     } else {
@@ -894,7 +939,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                 }
                         hsub = 0x00100000; hmul = 0.5;
                     }
-                    trace_store(v_re, v_im, &S.tr[Kc * 4]);          // the last term
+                    trace_store(v_re, v_im, &S.tr[Kc * NTR]);          // the last term
                     if constexpr (NA) {
                         const double c = cJ[Kc] * cscale;
 #pragma unroll
@@ -903,6 +948,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             for (int J = 0; J < TL; ++J)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
+                                    if (!live(I, J)) continue;
                                     acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
                                     acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
                                 }
@@ -910,7 +956,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 };
                 if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
                 {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
-                    const double chk = fabs(v_re[0][0][0]) + fabs(v_im[0][0][0]) + fabs(v_re[TL - 1][TL - 1][1]);
+                    const double chk = fabs(v_re[0][TL - 1][0]) + fabs(v_im[0][TL - 1][0]) + fabs(v_re[TL - 1][0][1]);
                     if (!UNI(chk < 1e300)) capped = true;
                 }
                 n_apply += Kc;
@@ -934,22 +980,27 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll 2
                         for (int k = kmax; k >= 1; --k, kd -= 1.0) {
                             if (k == Kp) jn = 1.0;
-                            const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
-                            const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
-                            a0 = fma(jn, ta.x, a0); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            if constexpr (SB) {
+                                const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 2]);
+                                a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            } else {
+                                const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
+                                const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
+                                a0 = fma(jn, ta.x, a0); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                            }
                             if (!(k & 1)) ssum += jn;
                             const double jm = fma(kd * tz, jn, -jn1);
                             jn1 = jn; jn = jm;
                         }
-                        const double2 ta = *reinterpret_cast<const double2*>(&S.tr[0]);
-                        const double2 tb = *reinterpret_cast<const double2*>(&S.tr[2]);
+                        const double2 ta = SB ? make_double2(half_tr, half_tr) : *reinterpret_cast<const double2*>(&S.tr[0]);
+                        const double2 tb = *reinterpret_cast<const double2*>(&S.tr[NTR - 2]);
                         double r[4];
                         if (direct) {
                             r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
                         } else {
                             const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
                             // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
-                            r[0] = fma(jn, ta.x, a0) * nrm; r[1] = (ta.x + ta.y) - r[0];
+                            r[0] = SB ? half_tr : fma(jn, ta.x, a0) * nrm; r[1] = (ta.x + ta.y) - r[0];
                             r[2] = fma(jn, tb.x, a2) * nrm; r[3] = fma(jn, tb.y, a3) * nrm;
                         }
                         if (act) finish_output(kidx + 1 + p, r);
@@ -1108,10 +1159,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-#define EML_WARP_INST(TL, RH, CH, PA) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
-EML_WARP_INST(1, true, false, false) EML_WARP_INST(1, false, false, false) EML_WARP_INST(2, true, false, false) EML_WARP_INST(2, false, false, false)
-EML_WARP_INST(1, true, true, false) EML_WARP_INST(1, false, true, false) EML_WARP_INST(2, true, true, false) EML_WARP_INST(2, false, true, false)
-EML_WARP_INST(2, true, true, true) EML_WARP_INST(2, false, true, true)
+#define EML_WARP_INST(TL, RH, CH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA, SB>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+EML_WARP_INST(1, true, false, false, false) EML_WARP_INST(1, false, false, false, false) EML_WARP_INST(2, true, false, false, false) EML_WARP_INST(2, false, false, false, false)
+EML_WARP_INST(1, true, true, false, false) EML_WARP_INST(1, false, true, false, false) EML_WARP_INST(2, true, true, false, false) EML_WARP_INST(2, false, true, false, false)
+EML_WARP_INST(2, true, true, true, false) EML_WARP_INST(2, false, true, true, false)
+EML_WARP_INST(2, true, true, true, true) EML_WARP_INST(2, false, true, true, true)
 
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1151,15 +1203,15 @@ static cudaError_t init_inv_table() {
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
                           unsigned int*, const int*, const double);
 
-template <int TL, bool CH, bool PA>
+template <int TL, bool CH, bool PA, bool SB = false>
 static WarpKern pick_kernel(bool real_h, size_t& smem) {
-    smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH>);
-    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH, PA> : (WarpKern)eval_warp_mma_kernel<TL, false, CH, PA>;
+    smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH, SB>);
+    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH, PA, SB> : (WarpKern)eval_warp_mma_kernel<TL, false, CH, PA, SB>;
 }
 
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
-                            bool real_h, bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream) {
+                            bool real_h, bool chebyshev, bool parity_h, bool sector_b, const int* cost_hint, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1168,19 +1220,21 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
     const int* use_order = nullptr;
-    if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {
+    if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {      // more than one model per resident warp
         launch_model_order(P, n_models, params, order, cost_hint, stream);
         use_order = order;
     }
     const bool tl2 = (P.n_tls == 4);
     size_t smem = 0;
     const bool parity = parity_h && chebyshev && tl2;     // H block diagonal by parity: half the DMMAs (d = 16)
-    const WarpKern kern = tl2 ? (chebyshev ? (parity ? pick_kernel<2, true, true>(real_h, smem) : pick_kernel<2, true, false>(real_h, smem))
+    const bool sector = parity && sector_b;               // parity-even part of rho0 is a steady state: evolve the odd tiles only
+    const WarpKern kern = tl2 ? (chebyshev ? (sector ? pick_kernel<2, true, true, true>(real_h, smem)
+                                              : parity ? pick_kernel<2, true, true>(real_h, smem) : pick_kernel<2, true, false>(real_h, smem))
                                            : pick_kernel<2, false, false>(real_h, smem))
                               : (chebyshev ? pick_kernel<1, true, false>(real_h, smem) : pick_kernel<1, false, false>(real_h, smem));
     // per device and kernel variant: dynamic shared memory opt-in and the resident CTAs per SM
-    static int per_sm_cache[64][16] = {{0}};
-    const int variant = (parity ? 8 : 0) + (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
+    static int per_sm_cache[64][32] = {{0}};
+    const int variant = (sector ? 16 : 0) + (parity ? 8 : 0) + (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
     int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
     if (per_sm == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -1191,7 +1245,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
     if (ctas > max_ctas) ctas = max_ctas;
-    const double zcap = chebyshev ? cheb_zcap_for(tl2 ? CHEB_KCAP_TL2 : CHEB_KCAP_TL1) : 0.0;
+    const double zcap = chebyshev ? cheb_zcap_for(tl2 ? (sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1) : 0.0;
     kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
                                                               use_order, zcap);
     return cudaGetLastError();

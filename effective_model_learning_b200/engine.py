@@ -24,6 +24,7 @@ _MAX_CONTEXTS = 32
 _contexts: "collections.OrderedDict[tuple, EvalContext]" = collections.OrderedDict()
 default_device = 0
 default_kernel = _native.KERNEL_AUTO
+default_flags = 0                       # EmlOptions.reserved bits (e.g. _native.FLAG_NO_SECTOR_REDUCTION), for tests / A-B runs
 
 
 def _initial_state_array(tls) -> np.ndarray:
@@ -83,7 +84,7 @@ def model_processes(model) -> list[tuple[tuple, float]]:
 class EvalContext:
     """Everything shared by a batch + the process library + the native plan."""
 
-    def __init__(self, n_tls, site_states, obs_site, obs_names, times, device=None, kernel=None):
+    def __init__(self, n_tls, site_states, obs_site, obs_names, times, device=None, kernel=None, flags=None):
         self.n_tls = n_tls
         self.site_states = [np.array(s, dtype=np.complex128) for s in site_states]
         self.rho0 = product_state(self.site_states)
@@ -92,6 +93,7 @@ class EvalContext:
         self.times = np.ascontiguousarray(times, dtype=np.float64)
         self.device = default_device if device is None else device
         self.kernel = default_kernel if kernel is None else kernel
+        self.flags = default_flags if flags is None else flags
         self.columns: dict[tuple, int] = {}     # process key -> parameter column
         self.op_index: dict[str, int] = {}      # operator name -> row of op table
         self.op_rows: list[np.ndarray] = []
@@ -151,7 +153,7 @@ class EvalContext:
             self._plan = _native.Plan(self.n_tls, len(self.columns), terms, np.stack(self.op_rows) if self.op_rows
                                       else np.zeros((1, 2, 2), dtype=np.complex128),
                                       self.rho0, self.obs_site, obs, self.times, self.targets,
-                                      device=self.device, kernel=self.kernel)
+                                      device=self.device, kernel=self.kernel, flags=self.flags)
         return self._plan
 
     def params_of(self, processes_per_model) -> np.ndarray:
@@ -173,7 +175,7 @@ def context_for(model, obs_names, times, device=None) -> EvalContext:
     times = np.ascontiguousarray(times, dtype=np.float64)
     q = first_qubit_site(model)
     key = (len(model.TLSs), q, tuple(obs_names), times.tobytes(), b''.join(s.tobytes() for s in states),
-           default_device if device is None else device, default_kernel)
+           default_device if device is None else device, default_kernel, default_flags)
     ctx = _contexts.get(key)
     if ctx is None:
         if q is None:
@@ -237,11 +239,13 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
         return d * d * (16.0 * d + 32.0 * n_tls + 4.0)
     if kernel_name in ('warp_mma', 'warp_mma_realH', 'warp_cheb', 'warp_cheb_realH', 'cta_mma', 'cta_mma_realH',
                        'cta_cheb', 'cta_cheb_realH', 'warp_cheb_parity', 'warp_cheb_parity_realH',
-                       'cta_cheb_parity', 'cta_cheb_parity_realH'):
+                       'cta_cheb_parity', 'cta_cheb_parity_realH', 'warp_cheb_parity_sector', 'warp_cheb_parity_sector_realH'):
         # DMMA: 4 (complex H) or 2 (real H: G.re diagonal, folded into the stencil) real d^3 products;
         # per complex element: diagonal weight 2, n site stencils 4n, X + X^dag 2, scale 2, accumulate 2
         mma = (2.0 if kernel_name.endswith('realH') else 4.0) * 2.0 * d ** 3
         if 'parity' in kernel_name:      # H block diagonal by parity: only the diagonal tiles of G are multiplied
             mma *= 0.5
+        if 'sector' in kernel_name:      # only the parity-odd tiles of rho are evolved: half of everything
+            return 0.5 * (mma + d * d * (2.0 + 4.0 * n_tls + 6.0))
         return mma + d * d * (2.0 + 4.0 * n_tls + 6.0)
     raise RuntimeError('unknown kernel ' + kernel_name)

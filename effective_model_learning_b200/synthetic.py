@@ -54,12 +54,12 @@ class LibraryLayout:
         self.classes = classes
         self.n_params = len(keys)
 
-    def context(self, times, obs_names, qubit_state=None, defect_state=None, device=None, kernel=None) -> engine.EvalContext:
+    def context(self, times, obs_names, qubit_state=None, defect_state=None, device=None, kernel=None, flags=None) -> engine.EvalContext:
         """EvalContext whose parameter columns are exactly this layout."""
         qs = definitions.ops['plus'] if qubit_state is None else qubit_state
         ds = definitions.ops['mm'] if defect_state is None else defect_state
         ctx = engine.EvalContext(self.n_tls, [qs] * self.Q + [ds] * self.D, 0, list(obs_names), times,
-                                 device=device, kernel=kernel)
+                                 device=device, kernel=kernel, flags=flags)
         ctx.ensure_columns(self.keys)
         assert [ctx.columns[k] for k in self.keys] == list(range(self.n_params))
         return ctx

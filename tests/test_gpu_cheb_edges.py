@@ -106,3 +106,33 @@ def test_parity_blocked_d32_kernel_with_complex_hermitian_coupling():
     got = m.calculate_dynamics(ts, OBS3)
     assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'cta_cheb_parity'
     assert max_err(got, lo.expect_exact(spec, ts, OBS3)) < TIGHT
+
+
+def test_steady_parity_sector_reduction_equals_the_full_evolution():
+    """Production initial state (qubit |+><+|, defects maximally mixed) and a Pauli library: the parity-even half of rho
+    is a steady state and the d = 16 kernel evolves the odd tiles only.  Same results as with the reduction disabled,
+    also on a long non-uniform grid that needs several macro steps; other initial states / non-unital jump operators
+    do not select it."""
+    from effective_model_learning_b200 import _native, configs, definitions, synthetic
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    lay = synthetic.LibraryLayout(1, 3, hyper)
+    p = lay.batch_params(7000 + np.arange(200))
+    rng = np.random.default_rng(3)
+    for ts in (np.linspace(0.0, 2.5, 200), np.sort(np.concatenate([[0.0, 0.0], rng.uniform(0, 40.0, 50), [40.0, 40.0]]))):
+        out = {}
+        for name, flags in (('sector', 0), ('full', _native.FLAG_NO_SECTOR_REDUCTION)):
+            ctx = lay.context(ts, ['sigmax', 'sigmap', 'sigmaz'], flags=flags)
+            ctx.set_targets(np.zeros((3, len(ts))))
+            out[name] = ctx.evaluate(p, want_expect=True, want_loss=True)
+            assert ('sector' in ctx.plan.kernel_name) == (flags == 0), ctx.plan.kernel_name
+        assert np.abs(out['sector'][0] - out['full'][0]).max() < 1e-12
+        np.testing.assert_allclose(out['sector'][1], out['full'][1], rtol=1e-11, atol=1e-15)
+    spec_row = lay.batch_params([7000])[0]
+    want = lo.expect_exact(__import__('tests.helpers', fromlist=['x']).spec_from_context_row(
+        lay.context(np.linspace(0.0, 2.5, 200), OBS3), spec_row), np.linspace(0.0, 2.5, 200), OBS3)
+    got, _ = lay.context(np.linspace(0.0, 2.5, 200), OBS3).evaluate(spec_row[None], want_expect=True)
+    assert max_err(list(got[0].real), want) < TIGHT
+    # a polarised defect state: the even sector is not a multiple of the identity
+    ctx = lay.context(np.linspace(0.0, 2.5, 50), OBS3, defect_state=definitions.ops['gnd'])
+    ctx.evaluate(p[:4], want_expect=True)
+    assert 'sector' not in ctx.plan.kernel_name and 'parity' in ctx.plan.kernel_name

@@ -260,7 +260,7 @@ def test_auto_dispatch_falls_back_to_generic_when_structure_is_not_supported(use
     spec = lo.random_library_spec(np.random.default_rng(1), 1, 3)
     m = model_from_spec(spec)
     m.calculate_dynamics(ts, OBS3)
-    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'warp_cheb_parity_realH'
+    assert engine.context_for(m, OBS3, ts).plan.kernel_name == 'warp_cheb_parity_sector_realH'
     spec['tls'][0]['couplings'].append((1, 0.7, [('sigmap', 'sigmam')]))      # non-Hermitian H
     m = model_from_spec(spec)
     got = m.calculate_dynamics(ts, OBS3)
