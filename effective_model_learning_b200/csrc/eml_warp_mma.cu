@@ -777,7 +777,16 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // only the 8 lanes 4g + (g >> 1) hold partial-trace elements; a 3-stage reduce-scatter among exactly those lanes
         // (4 double shuffles) leaves value 2*bit2(g) + bit1(g) in the lanes with g even.
         const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
-        auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], double* dst) {
+        // (the table entry is addressed by term index so that the store stays a predicated STS with a shared-window address)
+        const bool tr_lane = SB ? (diag_lane && (g & 3) == 0) : (TL == 2) ? (diag_lane && !(g & 1)) : ((lane & 7) == 0);
+        const int tr_off = SB ? (g >> 2) : (TL == 2) ? (g >> 1) : (lane >> 3);
+        const unsigned tr_base = (unsigned)__cvta_generic_to_shared(&S.tr[tr_off]);
+        // predicated shared store of one table entry (kept out of a branch so that the recurrence loop stays one basic block)
+        auto tr_put = [&](const int kterm, const double val) {
+            asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }"
+                         :: "r"(tr_base + (unsigned)(kterm * NTR * 8)), "d"(val), "r"((int)tr_lane) : "memory");
+        };
+        auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], const int kterm) {
             if constexpr (SB) {
                 // only rho01 of the observed site moves: tile (p, 1 ^ p), p = parity of the (equal) low bits; dst[0..1]
                 const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
@@ -788,7 +797,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 double kk = (hb ? v3 : v2) + shfl(hb ? v2 : v3, dl4);
                 kk += shfl(kk, dl2);
                 kk += shfl(kk, dl1);
-                if (diag_lane && (g & 3) == 0) dst[g >> 2] = kk;
+                tr_put(kterm, kk);
             } else if constexpr (TL == 2) {
                 double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
                 double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
@@ -804,10 +813,10 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
                 const double kk = (mb ? k1 : k0) + shfl(mb ? k0 : k1, dl2);
                 const double tot = kk + shfl(kk, dl1);
-                if (diag_lane && !(g & 1)) dst[(g >> 1)] = tot;
+                tr_put(kterm, tot);
             } else {
                 const double trv = partial_trace(xr, xi);
-                if ((lane & 7) == 0) dst[lane >> 3] = trv;
+                tr_put(kterm, trv);
             }
         };
         double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
@@ -821,7 +830,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             half_tr *= 0.5;
         }
         {   // the first output time carries the initial state
-            trace_store(acc_re, acc_im, &S.tr[0]);
+            trace_store(acc_re, acc_im, 0);
             __syncwarp();
             const double r[4] = {SB ? half_tr : S.tr[0], SB ? half_tr : S.tr[1], S.tr[NTR - 2], S.tr[NTR - 1]};
             if (lane == 0) finish_output(0, r);
@@ -844,7 +853,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             const bool final_step = (kidx + q == T - 1);
             if (UNI(!(tau_end * Rb >= 1e-40))) {     // repeated time points: the state does not move
                 __syncwarp();
-                trace_store(acc_re, acc_im, &S.tr[0]);
+                trace_store(acc_re, acc_im, 0);
                 __syncwarp();
                 const double r[4] = {SB ? half_tr : S.tr[0], SB ? half_tr : S.tr[1], S.tr[NTR - 2], S.tr[NTR - 1]};
                 for (int pbase = 0; UNI(pbase < q); pbase += 32)
@@ -896,7 +905,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     [[maybe_unused]] double hmul = 1.0;
 #pragma unroll CHEB_UNROLL
                     for (int k = 0; UNI(k < Kc); ++k) {
-                        trace_store(v_re, v_im, &S.tr[k * NTR]);       // partial trace of term k (overlaps the DMMAs below)
+                        trace_store(v_re, v_im, k);       // partial trace of term k (overlaps the DMMAs below)
                         if constexpr (NA) {
                             const double c = cJ[k] * cscale;
 #pragma unroll
@@ -939,7 +948,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                 }
                         hsub = 0x00100000; hmul = 0.5;
                     }
-                    trace_store(v_re, v_im, &S.tr[Kc * NTR]);          // the last term
+                    trace_store(v_re, v_im, Kc);          // the last term
                     if constexpr (NA) {
                         const double c = cJ[Kc] * cscale;
 #pragma unroll
