@@ -263,7 +263,10 @@ def run_b200(args):
     params = torch.from_numpy(params_host).to(dev)
     loss = torch.zeros(B, dtype=torch.float64, device=dev)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    # L2 flush between timed iterations: a buffer 1.25x the L2 capacity the device reports (B200: 126 MB -> 158 MB)
+    l2_bytes = int(torch.cuda.get_device_properties(dev).L2_cache_size)
+    flush_bytes = max(int(1.25 * l2_bytes), 64 * 1024 * 1024)
+    flush = torch.empty(flush_bytes // 4, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
@@ -370,6 +373,29 @@ def run_b200(args):
         'ncu': ncu_pipes,
     }
 
+    # ---- transparency: the same batch with the steady-sector reduction switched off (the whole density matrix evolves)
+    if 'sector' in plan.kernel_name:
+        ctx_full = layout.context(ts, OBS3, device=local, kernel=kernel, flags=_native.FLAG_NO_SECTOR_REDUCTION)
+        ctx_full.set_targets(targets)
+        plan_full = ctx_full.plan
+        loss_full = torch.zeros(B, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            plan_full.eval_device(B, params.data_ptr(), 0, 0, loss_full.data_ptr(), status.data_ptr(), stream)
+        n_full = min(args.steps, 20)
+        f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_full)]
+        for a, b in f_ev:
+            flush.zero_()
+            a.record()
+            plan_full.eval_device(B, params.data_ptr(), 0, 0, loss_full.data_ptr(), status.data_ptr(), stream)
+            b.record()
+        torch.cuda.synchronize()
+        ms_full = float(np.mean([a.elapsed_time(b) for a, b in f_ev]))
+        roofline['without_sector_reduction'] = {
+            'kernel': plan_full.kernel_name, 'kernel_ms': ms_full, 'evals_per_s_kernel_only': B / (ms_full * 1e-3),
+            'max_abs_loss_diff': float((loss_full - loss).abs().max()),
+            'note': 'rho0 of this workload (qubit |+><+|, defects maximally mixed: the reference\'s production state) has a steady '
+                    'parity-even half under the Pauli library, which the default kernel does not evolve (DESIGN.md section 4.1)'}
+
     line = {
         'metric': 'model evaluations/sec (4-TLS, d=16)' if (args.qubits, args.defects) == (1, 3) else 'model evaluations/sec',
         'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -380,7 +406,7 @@ def run_b200(args):
                                  'recurrence per macro step, Bessel-weighted dense output (DESIGN.md section 4)'
                                  if 'cheb' in plan.kernel_name else
                                  'Taylor action on the d x d density matrix with dense output (DESIGN.md section 4)'),
-                   'l2': 'flushed between iterations (256 MB memset); inputs are 1.1 MB per step',
+                   'l2': f'flushed between iterations ({flush_bytes / 1e6:.0f} MB memset = 1.25 x the {l2_bytes / 1e6:.0f} MB L2); inputs are 1.1 MB per step',
                    'partitioning': f'chains sharded contiguously over {world} GPU(s), no data-path collective; '
                                    'one all_gather of per-chain loss per timed region when n_gpus > 1'},
         'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(B * layout.n_params * 8),

@@ -164,9 +164,19 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     const float scale = (smax > 0.f) ? (ORDER_BINS - 1) / smax : 0.f;
     for (int b = tid; b < n_models; b += blockDim.x) atomicAdd(&hist[ORDER_BINS - 1 - (int)(cost[b] * scale)], 1u);
     __syncthreads();
-    if (tid == 0) {
-        unsigned int run = 0;
-        for (int i = 0; i < ORDER_BINS; ++i) { start[i] = run; run += hist[i]; }
+    if (tid < 32) {     // exclusive scan of the 256 bins by one warp: 8 bins per lane, then a shuffle scan of the lane totals
+        unsigned int loc[ORDER_BINS / 32], tot = 0;
+#pragma unroll
+        for (int i = 0; i < ORDER_BINS / 32; ++i) { loc[i] = tot; tot += hist[tid * (ORDER_BINS / 32) + i]; }
+        unsigned int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += up;
+        }
+        const unsigned int base = inc - tot;
+#pragma unroll
+        for (int i = 0; i < ORDER_BINS / 32; ++i) start[tid * (ORDER_BINS / 32) + i] = base + loc[i];
     }
     __syncthreads();
     for (int b = tid; b < n_models; b += blockDim.x) {
