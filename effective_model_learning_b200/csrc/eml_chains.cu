@@ -6,6 +6,7 @@
 #include <cmath>
 #include <new>
 
+#include <cstdlib>
 #include "eml_plan.hpp"
 
 namespace eml {
@@ -393,6 +394,10 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     CH_TRY(eml_eval_batch(plan, n_chains, S.cur, ch->d_target_set, nullptr, S.prop_loss, ch->d_status, nullptr));
     // groups: two halves when every half still has several models per resident warp
     ch->n_groups = (n_chains >= 2048) ? 2 : 1;
+    if (const char* env = std::getenv("EML_CHAIN_GROUPS")) {       // A/B switch for measurements
+        const int want = std::atoi(env);
+        if (want == 1 || (want == 2 && n_chains >= 2)) ch->n_groups = want;
+    }
     for (int g = 0; g < ch->n_groups; ++g) {
         ch->group_lo[g] = g * n_chains / ch->n_groups;
         ch->group_hi[g] = (g + 1) * n_chains / ch->n_groups;

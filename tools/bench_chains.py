@@ -6,7 +6,9 @@ from effective_model_learning_b200 import BatchedChains, configs, synthetic
 OBS3 = ['sigmax', 'sigmay', 'sigmaz']
 cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
 ts = np.linspace(0, 2.5, 200)
-for D, C, steps in ((1, 1024, 200), (1, 8192, 100), (2, 1024, 200), (2, 8192, 100), (3, 512, 100), (3, 4096, 100)):
+import os
+SHAPES = ((3, 4096, 100),) if os.environ.get("EML_CHAIN_GROUPS") else ((1, 1024, 200), (1, 8192, 100), (2, 1024, 200), (2, 8192, 100), (3, 512, 100), (3, 4096, 100))
+for D, C, steps in SHAPES:
     lay = synthetic.LibraryLayout(1, D, cfg)
     ctx = lay.context(ts, OBS3)
     ex, _ = ctx.evaluate(lay.random_params(np.random.default_rng(20260000 + 10 + D))[None], want_expect=True)
