@@ -295,7 +295,10 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         {
             const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
             const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
-            double w = 0.0;
+            // the lanes (type 0, ca 0) also collect the diagonal of sum rate * A^dag A of their site and row bit (the
+            // anticommutator part of the site generator, needed by the Chebyshev enclosure)
+            const bool kd_lane = CHEB && type == 0 && ca == 0;
+            double w = 0.0, kdv = 0.0;
             for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
                 const EmlTerm tm = P.terms[ti];
                 if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
@@ -303,23 +306,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 if (v == 0.0) continue;
                 const cplx x = cmul(ld_op(P.op_table, tm.op_a, ra, a), cconj(ld_op(P.op_table, tm.op_a, ca, bb)));
                 w += v * x.re;
-            }
-            S.jw[lane] = w;
-        }
-        if (CHEB && lane < 8) {     // diagonal of sum rate * A^dag A per site (the anticommutator part of the site generator)
-            const int bp = lane >> 1, ra = lane & 1;
-            double kdv = 0.0;
-            for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
-                const EmlTerm tm = P.terms[ti];
-                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
-                const double v = S.par[tm.param];
-                if (v == 0.0) continue;
-                for (int z = 0; z < 2; ++z) {
-                    const cplx m = ld_op(P.op_table, tm.op_a, z, ra);
-                    kdv += v * (m.re * m.re + m.im * m.im);
+                if (kd_lane) {
+                    const cplx m0 = ld_op(P.op_table, tm.op_a, 0, ra), m1 = ld_op(P.op_table, tm.op_a, 1, ra);
+                    kdv += v * ((m0.re * m0.re + m0.im * m0.im) + (m1.re * m1.re + m1.im * m1.im));
                 }
             }
-            S.kd[lane] = kdv;
+            S.jw[lane] = w;
+            if (kd_lane) S.kd[bp * 2 + ra] = kdv;
         }
         __syncwarp();
 
@@ -736,6 +729,19 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 }
                 __syncwarp();
                 for (int sq = 0; sq < 3; ++sq) {
+                    if constexpr (REAL_H) {
+                        // real symmetric D x D squaring on the DMMA pipe: fragments straight from shared memory
+#pragma unroll
+                        for (int I = 0; I < TL; ++I)
+#pragma unroll
+                            for (int J = 0; J < TL; ++J) {
+                                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                                for (int ks = 0; ks < KS; ++ks)
+                                    dmma(d0, d1, Ma[(8 * I + g) * D + 4 * ks + t], Ma[(4 * ks + t) * D + 8 * J + g]);
+                                *reinterpret_cast<double2*>(&Mb[(8 * I + g) * D + 8 * J + 2 * t]) = make_double2(d0, d1);
+                            }
+                    } else
                     for (int i = lane; i < D * D; i += 32) {
                         const int r = i / D, c = i % D;
                         double sre = 0.0, sim = 0.0;
