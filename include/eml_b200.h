@@ -22,7 +22,8 @@
  *     rho0, observables, times, targets).  eml_eval_batch() takes DEVICE pointers,
  *     allocates nothing, does not synchronise and launches on the caller's stream.
  *     eml_eval_batch_host() takes HOST pointers and stages through buffers owned by the
- *     plan (host<->device copies included), returning after the results are on the host.
+ *     plan (host<->device copies included), returning after the results are on the host;
+ *     page-locked caller buffers (cudaHostAlloc / cudaHostRegister) are used for the DMA directly.
  *   - a plan is bound to one device; calls on one plan must not overlap in time
  *     (different plans / devices are independent).
  */
@@ -93,8 +94,11 @@ typedef struct EmlOptions {
     double tol;          /* Taylor-series kernels: absolute per-element stopping tolerance (default 1e-11); the
                             Chebyshev kernels truncate at |J_k| < 1e-14 regardless */
     int32_t kernel;      /* EML_KERNEL_AUTO or a specific kernel, for tests/benchmarks */
-    int32_t reserved;
+    int32_t reserved;    /* flags; bit 0 (EML_FLAG_NO_SECTOR_REDUCTION): always evolve the whole density matrix, even when
+                            the parity-even half of rho0 is a steady state of the library (n_tls = 4 Chebyshev kernel) */
 } EmlOptions;
+
+#define EML_FLAG_NO_SECTOR_REDUCTION 1
 
 #define EML_KERNEL_AUTO 0
 #define EML_KERNEL_GENERIC 1 /* one CTA per model, rho in shared memory, FP64 FMA */
