@@ -296,9 +296,9 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
                           int* order_ws) {
     // counter_ws / order_ws: caller-owned work-fetch counter and ordering buffer (2 * 2^18 ints), so that several
     // evaluations of one plan can be in flight on different streams; NULL = the plan's own
+    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
     unsigned int* const counter = counter_ws ? counter_ws : plan->d_counter;
     int* const order = counter_ws ? order_ws : plan->d_order;
-    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
     if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
     if (n_models == 0) return EML_OK;
     if (!params && plan->P.n_params > 0) return fail(EML_ERR_INVALID_ARGUMENT, "params is NULL");
