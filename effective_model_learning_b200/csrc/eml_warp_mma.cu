@@ -33,6 +33,7 @@
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include "eml_common.cuh"
 #include "eml_cheb.cuh"
@@ -1208,6 +1209,24 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
     order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
 }
 
+// eml_order.cu
+const int* launch_packed_order(const DevProblem& P, long long n_models, const double* params, int* order_ws,
+                               const int* cost_hint, int slots, double zcap, int kcap, float fixed, float per_application,
+                               cudaStream_t stream);
+bool packed_order_applicable(const DevProblem& P, long long n_models, int slots);
+#ifndef EML_ORDER_PACK_DEFAULT
+#define EML_ORDER_PACK_DEFAULT 0
+#endif
+// 0: longest-first list; 1: packed list for cold batches; 2: also when the caller supplies measured costs.
+// The environment variable EML_ORDER_PACK overrides the build default (A/B measurements).
+static int order_pack_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("EML_ORDER_PACK");
+        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : EML_ORDER_PACK_DEFAULT;
+    }();
+    return mode;
+}
+
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }
@@ -1243,12 +1262,6 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = init_inv_table()) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-    // order buffer layout: [0] = work counter, [1 ...] = model order (LPT) when the batch is worth sorting
-    const int* use_order = nullptr;
-    if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {      // more than one model per resident warp
-        launch_model_order(P, n_models, params, order, cost_hint, stream);
-        use_order = order;
-    }
     const bool tl2 = (P.n_tls == 4);
     size_t smem = 0;
     const bool parity = parity_h && chebyshev && tl2;     // H block diagonal by parity: half the DMMAs (d = 16)
@@ -1270,7 +1283,22 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
     if (ctas > max_ctas) ctas = max_ctas;
-    const double zcap = chebyshev ? cheb_zcap_for(tl2 ? (sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1) : 0.0;
+    const int kcap = tl2 ? (sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1;
+    const double zcap = chebyshev ? cheb_zcap_for(kcap) : 0.0;
+    // Model order.  d = 16 Chebyshev kernel with a real H and a few models per warp slot: exact costs (or the caller's
+    // measured ones) packed onto the warp slots (eml_order.cu); otherwise a longest-first list when the batch is worth sorting.
+    const int* use_order = nullptr;
+    const int slots = (int)ctas * WARPS_PER_CTA;
+    const int pack_mode = order_pack_mode();
+    if (order != nullptr && tl2 && chebyshev && real_h && pack_mode >= (cost_hint != nullptr ? 2 : 1) &&
+        packed_order_applicable(P, n_models, slots)) {
+        // cost model in units of one generator application (ncu samples: set-up + epilogue, output phase per term)
+        const float fixed = sector ? 45.f : 25.f, per_application = sector ? 1.28f : 1.15f;
+        use_order = launch_packed_order(P, n_models, params, order, cost_hint, slots, zcap, kcap, fixed, per_application, stream);
+    } else if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {      // more than one model per resident warp
+        launch_model_order(P, n_models, params, order, cost_hint, stream);
+        use_order = order;
+    }
     kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
                                                               use_order, zcap);
     return cudaGetLastError();

@@ -92,11 +92,14 @@ if __name__ == '__main__':
     ap.add_argument('--warps', type=int, default=148 * 12)
     ap.add_argument('--fixed', type=float, default=47.0, help='set-up + epilogue in units of one application (ncu: ~12 %)')
     ap.add_argument('--output-share', type=float, default=0.27, help='output phase per application (ncu: ~17 %)')
+    ap.add_argument('--save', default='', help='write the application counts (int16 .npy), e.g. tests/golden/bench_application_counts.npy')
     a = ap.parse_args()
     ts = np.linspace(0.0, 2.5, 200)
     specs = [lo.random_library_spec(np.random.default_rng(1000 + b), 1, 3) for b in range(a.chains)]
     napp = np.array([plan_applications(s, ts, 540) for s in specs], float)
     proxy = np.array([proxy_cost(s) for s in specs])
+    if a.save:
+        np.save(a.save, napp.astype(np.int16))
     cost = a.fixed + (1.0 + a.output_share) * napp
     ideal = cost.sum() / a.warps
     print(f'{a.chains} models on {a.warps} warp slots: applications mean {napp.mean():.1f} (min {napp.min():.0f}, max {napp.max():.0f}), '
