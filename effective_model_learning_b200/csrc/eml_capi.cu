@@ -23,6 +23,7 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
+void set_order_pack_mode(int mode);
 }  // namespace eml
 
 #include "eml_plan.hpp"
@@ -55,6 +56,7 @@ extern "C" {
 int eml_version(void) { return EML_VERSION_MAJOR * 1000 + EML_VERSION_MINOR; }
 const char* eml_last_error_string(void) { return eml_last_error_ref().c_str(); }
 int64_t eml_launch_count(void) { return (int64_t)g_launches.load(); }
+void eml_set_order_pack_mode(int mode) { eml::set_order_pack_mode(mode); }
 
 int eml_device_count(int* count) {
     if (!count) return fail(EML_ERR_INVALID_ARGUMENT, "count is NULL");

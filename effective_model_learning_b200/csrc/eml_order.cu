@@ -18,20 +18,84 @@
 namespace eml {
 
 constexpr int COST_MODELS_PER_CTA = 8;      // 16 threads per model
+constexpr int COST_MAXP = 128;              // = MAXP of the warp kernel (plans with longer rows never reach it)
+constexpr int COST_MAX_TERMS = 192;         // term lists up to this length are staged in shared memory
+constexpr int COST_LD = 20;                 // row stride (floats) of the 16 x 16 matrices: rows are 16-byte aligned
+
+// FP32 copies of cheb_site_ranges / cheb_make_plan (eml_cheb.cuh): the same formulas, the plan is only used to COUNT terms
+__device__ __forceinline__ void cheb_site_ranges_f(const float* jw, const float* kd, const int n_sites, float& dlo, float& dhi,
+                                                   float& dasym) {
+    dlo = 0.f; dhi = 0.f; dasym = 0.f;
+    for (int bp = 0; bp < n_sites; ++bp) {
+        float slo = 3e38f, shi = -3e38f, sas = 0.f;
+#pragma unroll
+        for (int rc = 0; rc < 4; ++rc) {
+            const int ra = rc >> 1, ca = rc & 1;
+            const float dg = jw[bp * 8 + rc] - 0.5f * (kd[bp * 2 + ra] + kd[bp * 2 + ca]);
+            const float fa = jw[bp * 8 + 4 + rc], fb = jw[bp * 8 + 4 + (3 - rc)];
+            const float rad = 0.5f * fabsf(fa + fb);
+            slo = fminf(slo, dg - rad); shi = fmaxf(shi, dg + rad); sas = fmaxf(sas, 0.5f * fabsf(fa - fb));
+        }
+        dlo += slo; dhi += shi; dasym += sas;
+    }
+}
+
+struct ChebPlanF { float R, S, tau_max; };
+__device__ __forceinline__ ChebPlanF cheb_make_plan_f(const float spread, const float dlo, const float dhi, const float dasym,
+                                                      const float span, const float zcap, const int kcap) {
+    const float ah = 0.5f * (dhi - dlo), yext = spread + dasym;
+    float Rb = 1.f, Sb = 3e38f, Bb = 0.f;
+    bool have_ok = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float delta = (i == 0) ? 0.03f : (i == 1) ? 0.06f : (i == 2) ? 0.12f : (i == 3) ? 0.25f : (i == 4) ? 0.5f : 1.0f;
+        const float Rc = fmaxf(fmaxf(yext * (1.f + delta), ah), 1e-3f / fmaxf(span, 1e-30f));
+        const float cc = Rc * Rc - ah * ah - yext * yext, xr2 = ah * ah * Rc * Rc;
+        const float disc = sqrtf(cc * cc + 4.f * xr2);
+        const float u = (cc > 0.f) ? 2.f * xr2 / (cc + disc) : 0.5f * (disc - cc);
+        const float Bc = sqrtf(u), Ac = sqrtf(u + Rc * Rc);
+        const bool ok = span * Bc <= (float)CHEB_HUMP;
+        if ((ok && !have_ok) || (ok == have_ok && Ac + Bc < Sb)) { Rb = Rc; Sb = Ac + Bc; Bb = Bc; have_ok = ok; }
+    }
+    ChebPlanF pl;
+    pl.R = Rb; pl.S = Sb;
+    float tau_max = zcap / Sb;
+    if (Bb > 0.f) tau_max = fminf(tau_max, (float)CHEB_HUMP / Bb);
+    const float lnr = logf(Sb / Rb);
+    if (lnr * (float)kcap > 560.f) {
+        const float kall = 560.f / lnr;
+        tau_max = fminf(tau_max, fmaxf(kall - (float)CHEB_C1 * cbrtf(kall) - (float)CHEB_C0, 1.f) / Sb);
+    }
+    pl.tau_max = tau_max;
+    return pl;
+}
+__device__ __forceinline__ int cheb_terms_f(const float z) { return (int)ceilf(z + (float)CHEB_C1 * cbrtf(z) + (float)CHEB_C0); }
 
 __global__ void __launch_bounds__(16 * COST_MODELS_PER_CTA)
 cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restrict__ params, float* __restrict__ cost,
                    const double zcap, const int kcap, const float fixed, const float per_application) {
     constexpr int N = 4, D = 16;
-    __shared__ float Ma[COST_MODELS_PER_CTA][D][D + 1];
-    __shared__ float Mb[COST_MODELS_PER_CTA][D][D + 1];
-    __shared__ double jw[COST_MODELS_PER_CTA][32];
-    __shared__ double kd[COST_MODELS_PER_CTA][8];
+    __shared__ __align__(16) float Ma[COST_MODELS_PER_CTA][D][COST_LD];
+    __shared__ __align__(16) float Mb[COST_MODELS_PER_CTA][D][COST_LD];
+    __shared__ double spar[COST_MODELS_PER_CTA * COST_MAXP];
+    __shared__ EmlTerm sterms[COST_MAX_TERMS];
+    __shared__ float jw[COST_MODELS_PER_CTA][32];
+    __shared__ float kd[COST_MODELS_PER_CTA][8];
     const int ml = threadIdx.x >> 4, r = threadIdx.x & 15;
-    const int b_raw = blockIdx.x * COST_MODELS_PER_CTA + ml;
-    const bool valid = b_raw < n_models;
-    const long long b = valid ? b_raw : n_models - 1;
-    const double* par = params + b * P.n_params;
+    const long long b0 = (long long)blockIdx.x * COST_MODELS_PER_CTA;
+    const bool valid = b0 + ml < n_models;
+    const int np = P.n_params;
+
+    // ---- stage the parameter rows of the CTA's models (contiguous in HBM) and the term list
+    {
+        const long long rows = (n_models - b0 < COST_MODELS_PER_CTA) ? n_models - b0 : COST_MODELS_PER_CTA;
+        for (int i = threadIdx.x; i < (int)rows * np; i += blockDim.x) spar[i] = params[b0 * np + i];
+        if (P.n_terms <= COST_MAX_TERMS)
+            for (int i = threadIdx.x; i < P.n_terms; i += blockDim.x) sterms[i] = P.terms[i];
+    }
+    __syncthreads();
+    const EmlTerm* const terms = (P.n_terms <= COST_MAX_TERMS) ? sterms : P.terms;
+    const double* const par = spar + (valid ? ml : 0) * np;      // rows past the end of the batch reuse row 0 (never written back)
 
     // ---- one pass over the term list: row r of H (real: the plan guarantees real Hamiltonian terms; natural bit order,
     //      site s on bit N - 1 - s) and this thread's two real jump weights jw[site][type][ra][0..1] (the evaluator's
@@ -42,7 +106,7 @@ cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restr
     const int ja = jtype ? 1 - jra : jra;
     double w0 = 0.0, w1 = 0.0, kdv = 0.0;
     for (int ti = 0; ti < P.n_terms; ++ti) {
-        const EmlTerm tm = P.terms[ti];
+        const EmlTerm tm = terms[ti];
         const double v = par[tm.param];
         if (v == 0.0) continue;
         if (tm.kind == EML_TERM_LINDBLAD) {
@@ -74,9 +138,9 @@ cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restr
                 }
         }
     }
-    jw[ml][2 * r] = w0;
-    jw[ml][2 * r + 1] = w1;
-    if (jtype == 0) kd[ml][jbp * 2 + jra] = kdv;
+    jw[ml][2 * r] = (float)w0;
+    jw[ml][2 * r + 1] = (float)w1;
+    if (jtype == 0) kd[ml][jbp * 2 + jra] = (float)kdv;
     __syncwarp();
 
     // ---- Gershgorin spread and the mean of the diagonal (reductions over the 16 lanes of the model)
@@ -95,22 +159,27 @@ cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restr
     mu *= 1.f / D;
     Ma[ml][r][r] = ctr - mu;
     __syncwarp();
-    // ---- (H - mu)^8 by three squarings: thread r owns row r
-    float (*src)[D + 1] = Ma[ml];
-    float (*dst)[D + 1] = Mb[ml];
+    // ---- (H - mu)^8 by three squarings: thread r owns row r (the other rows are read as float4, broadcast to the 16 lanes)
+    float (*src)[COST_LD] = Ma[ml];
+    float (*dst)[COST_LD] = Mb[ml];
     for (int sq = 0; sq < 3; ++sq) {
-        float a[D], acc[D];
+        float acc[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) { a[k] = src[r][k]; acc[k] = 0.f; }
+        for (int c = 0; c < D; ++c) acc[c] = 0.f;
 #pragma unroll
-        for (int k = 0; k < D; ++k)
+        for (int k = 0; k < D; ++k) {
+            const float a = src[r][k];
 #pragma unroll
-            for (int c = 0; c < D; ++c) acc[c] = fmaf(a[k], src[k][c], acc[c]);
-        __syncwarp();
+            for (int c4 = 0; c4 < D; c4 += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&src[k][c4]);
+                acc[c4] = fmaf(a, s4.x, acc[c4]); acc[c4 + 1] = fmaf(a, s4.y, acc[c4 + 1]);
+                acc[c4 + 2] = fmaf(a, s4.z, acc[c4 + 2]); acc[c4 + 3] = fmaf(a, s4.w, acc[c4 + 3]);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < D; ++c) dst[r][c] = acc[c];
         __syncwarp();
-        float (*tmp)[D + 1] = src; src = dst; dst = tmp;
+        float (*tmp)[COST_LD] = src; src = dst; dst = tmp;
     }
     float cs = 0.f;
 #pragma unroll
@@ -119,43 +188,46 @@ cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restr
     for (int o = 8; o > 0; o >>= 1) cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
 
     if (r == 0 && valid) {
-        double spread = (double)hi - (double)lo;
-        spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt((double)cs))) * (1.0 + 1e-6));
-        double dlo, dhi, dasym;
-        cheb_site_ranges(jw[ml], kd[ml], N, dlo, dhi, dasym);
+        float spread = hi - lo;
+        spread = fminf(spread, 2.f * sqrtf(sqrtf(sqrtf(cs))) * (1.f + 1e-6f));
+        float dlo, dhi, dasym;
+        cheb_site_ranges_f(jw[ml], kd[ml], N, dlo, dhi, dasym);
         const int T = P.n_times;
         const double* times = P.times;
-        const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, times[T - 1] - times[0], zcap, kcap);
+        const ChebPlanF plan = cheb_make_plan_f(spread, dlo, dhi, dasym, (float)(times[T - 1] - times[0]), (float)zcap, kcap);
         // macro-step scan of the evaluator (the step ends are found by bisection; after 32 steps the rest is extrapolated)
-        double napp = 0.0;
+        float napp = 0.f;
         int kidx = 0, steps = 0;
         while (kidx < T - 1 && steps < 32) {
             const double t0 = times[kidx];
             int lo_i = kidx, hi_i = T - 1;      // largest index with times[i] - t0 <= tau_max
-            while (lo_i < hi_i) {
-                const int mid = (lo_i + hi_i + 1) >> 1;
-                if (times[mid] - t0 <= plan.tau_max) lo_i = mid; else hi_i = mid - 1;
-            }
+            if (!((float)(times[hi_i] - t0) <= plan.tau_max))
+                while (lo_i < hi_i) {
+                    const int mid = (lo_i + hi_i + 1) >> 1;
+                    if ((float)(times[mid] - t0) <= plan.tau_max) lo_i = mid; else hi_i = mid - 1;
+                }
+            else
+                lo_i = hi_i;
             int q = lo_i - kidx, nsub = 1;
             if (q == 0) {
-                const double ns = ceil((times[kidx + 1] - t0) / plan.tau_max);
-                nsub = (ns >= 1.0 && ns < 1e6) ? (int)ns : 1;
+                const float ns = ceilf((float)(times[kidx + 1] - t0) / plan.tau_max);
+                nsub = (ns >= 1.f && ns < 1e6f) ? (int)ns : 1;
                 q = 1;
             }
-            const double tau_end = (times[kidx + q] - t0) / nsub;
-            if (tau_end * plan.R >= 1e-40) {
-                int Kc = cheb_terms(tau_end * plan.S);
+            const float tau_end = (float)(times[kidx + q] - t0) / (float)nsub;
+            if (tau_end * plan.R >= 1e-30f) {
+                int Kc = cheb_terms_f(tau_end * plan.S);
                 if (!(Kc <= kcap)) Kc = kcap;
                 if (Kc < 0) Kc = 0;
-                napp += (double)nsub * (double)Kc;
+                napp += (float)nsub * (float)Kc;
             }
             kidx += q;
             ++steps;
         }
-        if (kidx < T - 1 && kidx > 0) napp *= (double)(T - 1) / (double)kidx;
-        float c = fixed + per_application * (float)napp;
+        if (kidx < T - 1 && kidx > 0) napp *= (float)(T - 1) / (float)kidx;
+        float c = fixed + per_application * napp;
         if (!(c >= 0.f && c < 1e30f)) c = 0.f;      // non-finite models are rejected by the evaluator at once
-        cost[b] = c;
+        cost[b0 + ml] = c;
     }
 }
 
@@ -221,13 +293,23 @@ pack_models_kernel(const int n_models, const float* cost, const int slots, const
             sorted[slot] = b;
         }
     __syncthreads();
-    // start key of every position of the sorted list; histogram of the keys
-    for (int j = 0; j < PACK_CLASSES; ++j)
-        for (int p = s_class[j] + tid; p < s_class[j + 1]; p += blockDim.x) {
-            const int key = pack_key_of(tab, j, p - s_class[j]);
+    // start key of every position of the sorted list; histogram of the keys.  Neighbouring positions mostly share a key
+    // (1776 of the 4096 models of the bench batch have key 0), so the counts are aggregated per warp before the atomic.
+    const int lane = tid & 31;
+    for (int p0 = 0; p0 < n_models; p0 += blockDim.x) {
+        const int p = p0 + tid;
+        int key = -1;
+        if (p < n_models) {
+            int j = 0;      // class of position p: largest j with s_class[j] <= p
+#pragma unroll
+            for (int step = PACK_CLASSES / 2; step > 0; step >>= 1)
+                if (s_class[j + step] <= p) j += step;
+            key = pack_key_of(tab, j, p - s_class[j]);
             keys[p] = key;
-            atomicAdd(&hist2[key], 1u);
         }
+        const unsigned int grp = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs((int)grp) - 1) atomicAdd(&hist2[key], (unsigned int)__popc(grp));
+    }
     __syncthreads();
     if (tid < 32) {     // exclusive scan of the cap + 2 key counts (in place): 33 entries per lane
         constexpr int PER = (PACK_LEVELS + 1 + 31) / 32;
@@ -249,9 +331,15 @@ pack_models_kernel(const int n_models, const float* cost, const int slots, const
         }
     }
     __syncthreads();
-    for (int p = tid; p < n_models; p += blockDim.x) {
-        const unsigned int slot = atomicAdd(&hist2[keys[p]], 1u);
-        out[slot] = sorted[p];
+    for (int p0 = 0; p0 < n_models; p0 += blockDim.x) {
+        const int p = p0 + tid;
+        const int key = (p < n_models) ? keys[p] : -1;
+        const unsigned int grp = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs((int)grp) - 1;
+        unsigned int base = 0;
+        if (key >= 0 && lane == leader) base = atomicAdd(&hist2[key], (unsigned int)__popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key >= 0) out[base + __popc(grp & ((1u << lane) - 1u))] = sorted[p];
     }
 }
 

@@ -32,6 +32,7 @@
 // (sigmax/y/z/p/m, exc, gnd, id2, mm all qualify).
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -1218,13 +1219,16 @@ bool packed_order_applicable(const DevProblem& P, long long n_models, int slots)
 #define EML_ORDER_PACK_DEFAULT 0
 #endif
 // 0: longest-first list; 1: packed list for cold batches; 2: also when the caller supplies measured costs.
-// The environment variable EML_ORDER_PACK overrides the build default (A/B measurements).
+// The environment variable EML_ORDER_PACK overrides the build default, eml_set_order_pack_mode overrides both (A/B measurements).
+static std::atomic<int> g_order_pack_override{-1};
+void set_order_pack_mode(int mode) { g_order_pack_override.store((mode >= 0 && mode <= 2) ? mode : -1); }
 static int order_pack_mode() {
     static const int mode = [] {
         const char* e = std::getenv("EML_ORDER_PACK");
         return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : EML_ORDER_PACK_DEFAULT;
     }();
-    return mode;
+    const int o = g_order_pack_override.load();
+    return o >= 0 ? o : mode;
 }
 
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {

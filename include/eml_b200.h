@@ -136,6 +136,10 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
 
 /* Number of kernels launched through this library since load (for bench accounting). */
 int64_t eml_launch_count(void);
+/* Order in which the persistent warps of the d = 16 Chebyshev kernel fetch the models of a launch (results do not depend
+ * on it): 0 longest-first list, 1 exact-cost packing for cold batches, 2 also with caller-measured costs (chain engine);
+ * any other value returns to the build default / the EML_ORDER_PACK environment variable.  Process-wide. */
+void eml_set_order_pack_mode(int mode);
 /* Name of the kernel the plan dispatches to ("generic", "warp_mma", ...). */
 const char* eml_plan_kernel_name(const EmlPlan* plan);
 /* FP64 microbenchmarks used to establish the roofline denominator (flops per second). */
