@@ -308,12 +308,13 @@ struct EmlChains {
     int* d_status = nullptr;
     // Large batches advance as two independent groups of chains on two streams: while the last (shortest) models
     // of one group's evaluation finish, the other group's next evaluation already fills the idle SMs.
+    static constexpr int MAX_GROUPS = 4;
     int n_groups = 1;
-    long long group_lo[2] = {0, 0}, group_hi[2] = {0, 0};
-    cudaStream_t gstream[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    unsigned int* g_counter[2] = {nullptr, nullptr};
-    int* g_order[2] = {nullptr, nullptr};
+    long long group_lo[MAX_GROUPS] = {}, group_hi[MAX_GROUPS] = {};
+    cudaStream_t gstream[MAX_GROUPS] = {};
+    cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {};
+    unsigned int* g_counter[MAX_GROUPS] = {};
+    int* g_order[MAX_GROUPS] = {};
 };
 
 template <typename T>
@@ -332,7 +333,7 @@ int eml_chains_destroy(EmlChains* ch) {
     cudaSetDevice(ch->plan->device);
     cudaDeviceSynchronize();
     for (void* p : ch->owned) cudaFree(p);
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < EmlChains::MAX_GROUPS; ++g) {
         if (ch->gstream[g]) cudaStreamDestroy(ch->gstream[g]);
         if (ch->join[g]) cudaEventDestroy(ch->join[g]);
     }
@@ -396,7 +397,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     ch->n_groups = (n_chains >= 2048) ? 2 : 1;
     if (const char* env = std::getenv("EML_CHAIN_GROUPS")) {       // A/B switch for measurements
         const int want = std::atoi(env);
-        if (want == 1 || (want == 2 && n_chains >= 2)) ch->n_groups = want;
+        if (want >= 1 && want <= EmlChains::MAX_GROUPS && n_chains >= want) ch->n_groups = want;
     }
     for (int g = 0; g < ch->n_groups; ++g) {
         ch->group_lo[g] = g * n_chains / ch->n_groups;

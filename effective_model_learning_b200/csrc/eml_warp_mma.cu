@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
 }
 
 template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (TL == 1) ? 4 : (SB ? CTAS_PER_SM_SB : CTAS_PER_SM))
+// resident warps per SM: 16 (d = 8), 12 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM* are quoted for four-warp CTAs
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4 * ((TL == 1) ? 4 : (SB ? CTAS_PER_SM_SB : CTAS_PER_SM)) / WARPS_PER_CTA)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
