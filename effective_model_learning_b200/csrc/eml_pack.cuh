@@ -62,9 +62,21 @@ EML_HD int pack_find_level(const unsigned int* mask, const int from, const int c
     return r <= cap ? r : -1;
 }
 
+EML_HD int pack_ctz(const unsigned int word) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)word) - 1;
+#else
+    return __builtin_ctz(word);
+#endif
+}
+
 // Best-fit decreasing over the class histogram n_class[PACK_CLASSES] into `slots` bins.  Sequential (one thread).
 // cleared: bins_at and mask are already zero (the kernel clears them with all its threads).
-EML_HD void pack_classes(const int* n_class, const int slots, const float eps, PackTables& t, const bool cleared = false) {
+// Capacities below 128 units (a few models per bin: the case the packing exists for) keep the level bitmask in four
+// registers, so that a step costs one dependent shared-memory load (bins_at[r]) instead of three or four;
+// `registers_path = false` forces the general path (the host test compares the two).
+EML_HD void pack_classes(const int* n_class, const int slots, const float eps, PackTables& t, const bool cleared = false,
+                         const bool registers_path = true) {
     long long total = 0;
     for (int j = 0; j < PACK_CLASSES; ++j) total += (long long)n_class[j] * (PACK_CLASSES - j);
     long long cap = (long long)((double)total * (1.0 + (double)eps) / (double)(slots > 0 ? slots : 1)) + 1;
@@ -76,8 +88,52 @@ EML_HD void pack_classes(const int* n_class, const int slots, const float eps, P
         for (int w = 0; w < PACK_MASK_WORDS; ++w) t.mask[w] = 0u;
     }
     t.bins_at[cap] = slots;
-    t.mask[cap >> 5] |= 1u << (cap & 31);
     int nchunks = 0;
+    if (registers_path && cap < 128) {
+        unsigned int m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;      // bit r of (m3 m2 m1 m0) set <=> bins_at[r] > 0
+        auto flip = [&](const int r, const bool on) {
+            const unsigned int bit = 1u << (r & 31);
+            const int w = r >> 5;
+            if (on) { m0 |= (w == 0) ? bit : 0u; m1 |= (w == 1) ? bit : 0u; m2 |= (w == 2) ? bit : 0u; m3 |= (w == 3) ? bit : 0u; }
+            else    { m0 &= (w == 0) ? ~bit : ~0u; m1 &= (w == 1) ? ~bit : ~0u; m2 &= (w == 2) ? ~bit : ~0u; m3 &= (w == 3) ? ~bit : ~0u; }
+        };
+        flip((int)cap, true);
+        for (int j = 0; j < PACK_CLASSES; ++j) {
+            t.cbeg[j] = nchunks;
+            const int c = PACK_CLASSES - j;
+            const int cw = c >> 5;
+            const unsigned int high = 0xffffffffu << (c & 31);
+            int rem = n_class[j], placed = 0;
+            while (rem > 0 && nchunks < PACK_MAX_CHUNKS) {
+                // lowest set bit at or above c
+                const unsigned int w0 = (cw == 0) ? (m0 & high) : 0u;
+                const unsigned int w1 = (cw == 1) ? (m1 & high) : (cw < 1 ? m1 : 0u);
+                const unsigned int w2 = (cw == 2) ? (m2 & high) : (cw < 2 ? m2 : 0u);
+                const unsigned int w3 = (cw == 3) ? (m3 & high) : (cw < 3 ? m3 : 0u);
+                int r;
+                if (w0) r = pack_ctz(w0);
+                else if (w1) r = 32 + pack_ctz(w1);
+                else if (w2) r = 64 + pack_ctz(w2);
+                else if (w3) r = 96 + pack_ctz(w3);
+                else break;
+                const int have = t.bins_at[r];
+                const int m = rem < have ? rem : have;
+                placed += m;
+                t.chunk_key[nchunks] = (unsigned short)(t.cap - r);
+                t.chunk_end[nchunks] = placed;
+                ++nchunks;
+                if (have == m) flip(r, false);
+                t.bins_at[r] = have - m;
+                t.bins_at[r - c] += m;
+                flip(r - c, true);
+                rem -= m;
+            }
+        }
+        t.mask[0] = m0; t.mask[1] = m1; t.mask[2] = m2; t.mask[3] = m3;
+        t.cbeg[PACK_CLASSES] = nchunks;
+        return;
+    }
+    t.mask[cap >> 5] |= 1u << (cap & 31);
     for (int j = 0; j < PACK_CLASSES; ++j) {
         t.cbeg[j] = nchunks;
         const int c = PACK_CLASSES - j;

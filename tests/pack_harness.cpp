@@ -5,6 +5,20 @@
 
 #include "eml_pack.cuh"
 
+// the two paths of pack_classes (level bitmask in registers / in memory) on one class histogram: 1 if all tables agree
+extern "C" int pack_paths_agree(const int* n_class, int slots, float eps) {
+    using namespace eml;
+    static PackTables a, b;
+    pack_classes(n_class, slots, eps, a, false, true);
+    pack_classes(n_class, slots, eps, b, false, false);
+    if (a.cap != b.cap) return 0;
+    for (int j = 0; j <= PACK_CLASSES; ++j) if (a.cbeg[j] != b.cbeg[j]) return 0;
+    for (int k = 0; k < a.cbeg[PACK_CLASSES]; ++k) if (a.chunk_key[k] != b.chunk_key[k] || a.chunk_end[k] != b.chunk_end[k]) return 0;
+    for (int r = 0; r < PACK_LEVELS; ++r) if (a.bins_at[r] != b.bins_at[r]) return 0;
+    for (int w = 0; w < PACK_MASK_WORDS; ++w) if (a.mask[w] != b.mask[w]) return 0;
+    return a.cap < 128 ? 2 : 1;      // 2: the register path was taken
+}
+
 extern "C" int pack_order_host(int n, const float* cost, int slots, float eps, int* order_out, int* keys_out) {
     using namespace eml;
     float mx = 0.f;

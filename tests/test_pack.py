@@ -90,3 +90,26 @@ def test_packing_beats_the_longest_first_list_on_the_bench_batch(lib):
     noisy = cost * (1.0 + 0.03 * np.random.default_rng(0).standard_normal(len(cost)))
     order, _, _ = pack(lib, cost, slots)
     assert busy_fraction(noisy, order, slots) > busy_fraction(noisy, np.argsort(-cost, kind='stable'), slots) + 0.05
+
+
+def test_register_and_memory_paths_of_the_packing_agree(lib):
+    """pack_classes keeps the level bitmask in registers for capacities below 128 units: same tables as the general path."""
+    rng = np.random.default_rng(11)
+    took_registers = 0
+    for trial in range(400):
+        n = int(rng.integers(1, 6000))
+        slots = int(rng.integers(1, 2500))
+        shape = rng.choice(['bench', 'flat', 'two', 'one'])
+        if shape == 'bench':
+            q = np.clip((bench_costs()[rng.integers(0, 4096, n)] / 720.0 * 63).astype(int), 0, 63)
+        elif shape == 'flat':
+            q = rng.integers(0, 64, n)
+        elif shape == 'two':
+            q = rng.choice([3, 60], n)
+        else:
+            q = np.full(n, int(rng.integers(0, 64)))
+        n_class = np.bincount(63 - q, minlength=64).astype(np.int32)      # class 0 = most expensive
+        res = lib.pack_paths_agree(n_class.ctypes.data_as(ctypes.c_void_p), slots, ctypes.c_float(float(rng.uniform(0, 0.2))))
+        assert res in (1, 2), (trial, n, slots, shape)
+        took_registers += res == 2
+    assert 50 < took_registers < 400
