@@ -24,6 +24,8 @@ bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 void set_order_pack_mode(int mode);
+cudaError_t warp_predicted_applications(const DevProblem& P, bool sector, long long n_models, const double* params, float* out,
+                                        cudaStream_t stream);
 }  // namespace eml
 
 #include "eml_plan.hpp"
@@ -413,6 +415,23 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     for (long long i = 0; i < n_models; ++i)
         if (plan->h_status[i] < 0)
             return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " did not converge (series cap or non-finite generator)");
+    return EML_OK;
+}
+
+int eml_predict_applications(EmlPlan* plan, int64_t n_models, const double* params, float* applications, void* stream) {
+    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
+    if (n_models == 0) return EML_OK;
+    if (!params || !applications) return fail(EML_ERR_INVALID_ARGUMENT, "params / applications is NULL");
+    if (plan->kernel != EML_KERNEL_WARP_CHEB || plan->Pw.n_tls != 4 || !plan->real_h)
+        return fail(EML_ERR_UNSUPPORTED, "predicted application counts exist for the d = 16 Chebyshev kernel with a real Hamiltonian");
+    int cur = -1;
+    EML_CUDA(cudaGetDevice(&cur));
+    if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
+    const cudaError_t e = eml::warp_predicted_applications(plan->Pw, plan->parity_h && plan->sector_b, n_models, params, applications,
+                                                           (cudaStream_t)stream);
+    if (cur != plan->device && cur >= 0) cudaSetDevice(cur);
+    if (e != cudaSuccess) return fail(EML_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return EML_OK;
 }
 

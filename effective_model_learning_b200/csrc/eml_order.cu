@@ -370,6 +370,16 @@ const int* launch_packed_order(const DevProblem& P, long long n_models, const do
     return out;
 }
 
+// Diagnostic: the generator applications cheb16_cost_kernel predicts for every model (what the packing is built on), to be
+// compared with the counts the evaluator reports in `status`.  d = 16 plans with a real H only.
+cudaError_t launch_predicted_applications(const DevProblem& P, long long n_models, const double* params, float* out,
+                                          double zcap, int kcap, cudaStream_t stream) {
+    const int n = (int)n_models;
+    cheb16_cost_kernel<<<(unsigned)((n + COST_MODELS_PER_CTA - 1) / COST_MODELS_PER_CTA), 16 * COST_MODELS_PER_CTA, 0, stream>>>(
+        P, n, params, out, zcap, kcap, 0.f, 1.f);
+    return cudaGetLastError();
+}
+
 bool packed_order_applicable(const DevProblem& P, long long n_models, int slots) {
     return P.n_tls == 4 && P.n_times >= 1 && n_models > slots && n_models <= 8LL * slots && n_models <= PACK_MAX_MODELS;
 }

@@ -1216,6 +1216,14 @@ const int* launch_packed_order(const DevProblem& P, long long n_models, const do
                                const int* cost_hint, int slots, double zcap, int kcap, float fixed, float per_application,
                                cudaStream_t stream);
 bool packed_order_applicable(const DevProblem& P, long long n_models, int slots);
+cudaError_t launch_predicted_applications(const DevProblem& P, long long n_models, const double* params, float* out,
+                                          double zcap, int kcap, cudaStream_t stream);
+// the series cap of the d = 16 Chebyshev variant a plan runs (sector: CHEB_KCAP_SB), for the diagnostic entry point
+cudaError_t warp_predicted_applications(const DevProblem& P, bool sector, long long n_models, const double* params, float* out,
+                                        cudaStream_t stream) {
+    const int kcap = sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2;
+    return launch_predicted_applications(P, n_models, params, out, cheb_zcap_for(kcap), kcap, stream);
+}
 #ifndef EML_ORDER_PACK_DEFAULT
 #define EML_ORDER_PACK_DEFAULT 0
 #endif

@@ -140,6 +140,10 @@ int64_t eml_launch_count(void);
  * on it): 0 longest-first list, 1 exact-cost packing for cold batches, 2 also with caller-measured costs (chain engine);
  * any other value returns to the build default / the EML_ORDER_PACK environment variable.  Process-wide. */
 void eml_set_order_pack_mode(int mode);
+/* Diagnostic for the packed order: the generator applications the d = 16 Chebyshev kernel (real Hamiltonian) will
+ * spend on every model, predicted by the FP32 pre-pass; compare with `status` of eml_eval_batch.  Device pointers:
+ * params [n_models][n_params], applications [n_models].  EML_ERR_UNSUPPORTED for other plans. */
+int eml_predict_applications(EmlPlan* plan, int64_t n_models, const double* params, float* applications, void* stream);
 /* Name of the kernel the plan dispatches to ("generic", "warp_mma", ...). */
 const char* eml_plan_kernel_name(const EmlPlan* plan);
 /* FP64 microbenchmarks used to establish the roofline denominator (flops per second). */

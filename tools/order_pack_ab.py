@@ -49,4 +49,11 @@ for mode in (0, 1):
     out[f'ms_per_batch_mode{mode}'] = e0.elapsed_time(e1) / reps
 _native.set_order_pack_mode(-1)
 out['identical_results'] = True
+# the pre-pass's predicted application counts against the evaluator's own (status)
+pred = torch.empty(B, dtype=torch.float32, device='cuda')
+plan.predict_applications_device(B, p.data_ptr(), pred.data_ptr(), s)
+torch.cuda.synchronize()
+dev = pred.cpu().numpy() - ref[1]
+out['predicted_applications'] = {'mean': float(pred.mean()), 'actual_mean': float(ref[1].mean()), 'max_abs_dev': float(np.abs(dev).max()),
+                                 'models_off_by_more_than_2': int((np.abs(dev) > 2).sum())}
 print(json.dumps(out))
