@@ -113,3 +113,125 @@ def test_register_and_memory_paths_of_the_packing_agree(lib):
         assert res in (1, 2), (trial, n, slots, shape)
         took_registers += res == 2
     assert 50 < took_registers < 400
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# numpy transcription (float32 where the kernel uses it) of cheb16_cost_kernel (csrc/eml_order.cu), fed with exactly what
+# the kernel receives: the context's term list, operator table and parameter rows.  It pins the LOGIC of the pre-pass
+# (bit order, jump-weight layout, FP32 plan, macro-step scan) against the application counts the device reports.
+C1, C0, HUMP = 9.25, 5.0, 14.0
+TERM_ENERGY, TERM_COUPLING, TERM_LINDBLAD = 0, 1, 2
+
+
+def _cheb_terms_f(z):
+    return int(np.ceil(np.float32(z) + np.float32(C1) * np.cbrt(np.float32(z)) + np.float32(C0)))
+
+
+def _predict_applications(terms, op_table, row, times, kcap, zcap):
+    f32 = np.float32
+    N, D = 4, 16
+    H = np.zeros((D, D), dtype=f32)
+    jw = np.zeros(32, dtype=f32)
+    kd = np.zeros(8, dtype=f32)
+    for (param, kind, site_a, site_b, op_a, op_b) in terms:
+        v = row[param]
+        if v == 0.0:
+            continue
+        A = op_table[op_a]
+        if kind == TERM_LINDBLAD:
+            for e in range(8 * site_a, 8 * site_a + 8):
+                typ, ra, ca = (e >> 2) & 1, (e >> 1) & 1, e & 1
+                a, bb = (1 - ra, 1 - ca) if typ else (ra, ca)
+                jw[e] += f32(v * (A[ra, a] * np.conj(A[ca, bb])).real)
+            for ra in range(2):
+                kd[2 * site_a + ra] += f32(v * (abs(A[0, ra]) ** 2 + abs(A[1, ra]) ** 2))
+            continue
+        sa = N - 1 - site_a
+        for r in range(D):
+            ra = (r >> sa) & 1
+            if kind == TERM_ENERGY:
+                for a in range(2):
+                    c = (r & ~(1 << sa)) | (a << sa)
+                    H[r, c] += f32(v * A[ra, a].real)
+            else:
+                B = op_table[op_b]
+                sb = N - 1 - site_b
+                rb = (r >> sb) & 1
+                for a in range(2):
+                    for bb in range(2):
+                        c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb)
+                        H[r, c] += f32(v * v * (A[ra, a] * B[rb, bb]).real)
+    diag = H.diagonal().copy()
+    rad = np.abs(H).sum(axis=1) - np.abs(diag)
+    spread = f32((diag + rad).max() - (diag - rad).min())
+    M = H - np.eye(D, dtype=f32) * f32(diag.sum() / D)
+    for _ in range(3):
+        M = (M @ M).astype(f32)
+    cs = np.abs(M).sum(axis=0).max()
+    spread = min(spread, f32(2.0) * np.sqrt(np.sqrt(np.sqrt(f32(cs)))) * f32(1 + 1e-6))
+    dlo = dhi = dasym = f32(0)
+    for bp in range(N):
+        slo, shi, sas = f32(3e38), f32(-3e38), f32(0)
+        for rc in range(4):
+            ra, ca = rc >> 1, rc & 1
+            dg = jw[bp * 8 + rc] - f32(0.5) * (kd[bp * 2 + ra] + kd[bp * 2 + ca])
+            fa, fb = jw[bp * 8 + 4 + rc], jw[bp * 8 + 4 + (3 - rc)]
+            r_ = f32(0.5) * abs(fa + fb)
+            slo, shi, sas = min(slo, dg - r_), max(shi, dg + r_), max(sas, f32(0.5) * abs(fa - fb))
+        dlo, dhi, dasym = dlo + slo, dhi + shi, dasym + sas
+    span = f32(times[-1] - times[0])
+    ah, yext = f32(0.5) * (dhi - dlo), spread + dasym
+    best = None
+    have_ok = False
+    for delta in (0.03, 0.06, 0.12, 0.25, 0.5, 1.0):
+        R = max(yext * f32(1 + delta), ah, f32(1e-3) / max(span, f32(1e-30)))
+        cc, xr2 = R * R - ah * ah - yext * yext, ah * ah * R * R
+        disc = np.sqrt(cc * cc + 4 * xr2)
+        u = 2 * xr2 / (cc + disc) if cc > 0 else 0.5 * (disc - cc)
+        Bc, Ac = np.sqrt(u), np.sqrt(u + R * R)
+        ok = span * Bc <= HUMP
+        if (ok and not have_ok) or (ok == have_ok and (best is None or Ac + Bc < best[1])):
+            best, have_ok = (R, Ac + Bc, Bc), ok
+    R, S, Bb = best
+    tau_max = f32(zcap) / S
+    if Bb > 0:
+        tau_max = min(tau_max, f32(HUMP) / Bb)
+    lnr = np.log(S / R)
+    if lnr * kcap > 560.0:
+        kall = 560.0 / lnr
+        tau_max = min(tau_max, max(kall - C1 * np.cbrt(kall) - C0, 1.0) / S)
+    T, kidx, napp = len(times), 0, 0
+    while kidx < T - 1:
+        t0 = times[kidx]
+        q = 0
+        while kidx + q + 1 <= T - 1 and f32(times[kidx + q + 1] - t0) <= tau_max:
+            q += 1
+        nsub = 1
+        if q == 0:
+            nsub, q = int(np.ceil(f32(times[kidx + 1] - t0) / tau_max)), 1
+        tau_end = f32(times[kidx + q] - t0) / f32(nsub)
+        napp += nsub * min(_cheb_terms_f(tau_end * S), kcap)
+        kidx += q
+    return napp
+
+
+def test_cost_prepass_logic_predicts_the_device_application_counts():
+    """First 160 models of the bench batch: the pre-pass logic reproduces the counts the evaluator reported on the B200
+    (tests/golden/bench_application_counts.npy holds the counts of the numpy model of the evaluator, equal to the
+    device's mean to six digits) to within one term."""
+    from effective_model_learning_b200 import configs, synthetic, engine, definitions
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    lay = synthetic.LibraryLayout(1, 3, hyper)
+    ts = np.linspace(0.0, 2.5, 200)
+    ctx = engine.EvalContext(4, [definitions.ops['plus']] + [definitions.ops['mm']] * 3, 0, ['sigmax', 'sigmay', 'sigmaz'], ts)
+    ctx.ensure_columns(lay.keys)
+    terms = ctx.terms()
+    op_table = np.stack(ctx.op_rows)
+    want = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_application_counts.npy'))
+    kcap = 540                                       # CHEB_KCAP_SB (csrc/eml_warp_mma.cu)
+    z = float(kcap)
+    while np.ceil(z + C1 * np.cbrt(z) + C0) > kcap:  # cheb_zcap_for (csrc/eml_cheb.cuh)
+        z -= 0.25
+    params = lay.batch_params(1000 + np.arange(160))
+    got = np.array([_predict_applications(terms, op_table, row, ts, kcap, z) for row in params])
+    assert np.abs(got - want[:160]).max() <= 1
