@@ -236,7 +236,8 @@ cheb16_cost_kernel(const DevProblem P, const int n_models, const double* __restr
 constexpr int ORDER_KEYS_AT = 1 << 17;
 
 __global__ void __launch_bounds__(1024)
-pack_models_kernel(const int n_models, const float* cost, const int slots, const float eps, int* order_ws, int* out) {
+pack_models_kernel(const int n_models, const float* cost, const int slots, const float eps, const float tail_fraction,
+                   int* order_ws, int* out) {
     __shared__ unsigned int hist[PACK_BINS];
     __shared__ unsigned int start[PACK_BINS];
     __shared__ int n_class[PACK_CLASSES];
@@ -286,7 +287,7 @@ pack_models_kernel(const int n_models, const float* cost, const int slots, const
     if (tid == 0) s_class[PACK_CLASSES] = n_models;
     __syncthreads();
     // the packing (one thread) runs while the others scatter the models into the sorted list
-    if (tid == 0) pack_classes(n_class, slots, eps, tab, true);
+    if (tid == 0) pack_classes(n_class, slots, eps, tab, true, true, tail_fraction);
     if (tid >= 32)
         for (int b = tid - 32; b < n_models; b += blockDim.x - 32) {
             const unsigned int slot = atomicAdd(&start[pack_bin_of(cost[b], scale)], 1u);
@@ -366,7 +367,8 @@ const int* launch_packed_order(const DevProblem& P, long long n_models, const do
         cheb16_cost_kernel<<<(unsigned)((n + COST_MODELS_PER_CTA - 1) / COST_MODELS_PER_CTA), 16 * COST_MODELS_PER_CTA, 0, stream>>>(
             P, n, params, cost, zcap, kcap, fixed, per_application);
     int* out = order_ws + (1 << 18);      // the cost scratch is dead once the models are sorted
-    pack_models_kernel<<<1, 1024, 0, stream>>>(n, cost, slots, 0.05f, order_ws, out);
+    // capacity 5 % above the mean load of the packed models; the cheapest 10 % of the models form the greedy tail
+    pack_models_kernel<<<1, 1024, 0, stream>>>(n, cost, slots, 0.05f, 0.10f, order_ws, out);
     return out;
 }
 

@@ -75,10 +75,18 @@ EML_HD int pack_ctz(const unsigned int word) {
 // Capacities below 128 units (a few models per bin: the case the packing exists for) keep the level bitmask in four
 // registers, so that a step costs one dependent shared-memory load (bins_at[r]) instead of three or four;
 // `registers_path = false` forces the general path (the host test compares the two).
+// tail_fraction: the cheapest classes holding at most this fraction of the models are NOT packed; they stay at the end of
+// the list (longest first) and are fetched greedily, which absorbs the run-time noise of the packed part
+// (tools/schedule_model.py: with 5 % noise 0.87 busy without a tail, 0.90 with 10 %).
 EML_HD void pack_classes(const int* n_class, const int slots, const float eps, PackTables& t, const bool cleared = false,
-                         const bool registers_path = true) {
+                         const bool registers_path = true, const float tail_fraction = 0.f) {
+    int n_all = 0;
+    for (int j = 0; j < PACK_CLASSES; ++j) n_all += n_class[j];
+    int j_cut = PACK_CLASSES, n_tail = 0;                // classes j_cut .. PACK_CLASSES - 1 form the greedy tail
+    const int tail_max = (int)(tail_fraction * (float)n_all);
+    while (j_cut > 1 && n_tail + n_class[j_cut - 1] <= tail_max) { --j_cut; n_tail += n_class[j_cut]; }
     long long total = 0;
-    for (int j = 0; j < PACK_CLASSES; ++j) total += (long long)n_class[j] * (PACK_CLASSES - j);
+    for (int j = 0; j < j_cut; ++j) total += (long long)n_class[j] * (PACK_CLASSES - j);
     long long cap = (long long)((double)total * (1.0 + (double)eps) / (double)(slots > 0 ? slots : 1)) + 1;
     if (cap < PACK_CLASSES) cap = PACK_CLASSES;          // the most expensive model fits an empty bin
     if (cap > PACK_LEVELS - 1) cap = PACK_LEVELS - 1;
@@ -103,7 +111,7 @@ EML_HD void pack_classes(const int* n_class, const int slots, const float eps, P
             const int c = PACK_CLASSES - j;
             const int cw = c >> 5;
             const unsigned int high = 0xffffffffu << (c & 31);
-            int rem = n_class[j], placed = 0;
+            int rem = (j < j_cut) ? n_class[j] : 0, placed = 0;
             while (rem > 0 && nchunks < PACK_MAX_CHUNKS) {
                 // lowest set bit at or above c
                 const unsigned int w0 = (cw == 0) ? (m0 & high) : 0u;
@@ -137,7 +145,7 @@ EML_HD void pack_classes(const int* n_class, const int slots, const float eps, P
     for (int j = 0; j < PACK_CLASSES; ++j) {
         t.cbeg[j] = nchunks;
         const int c = PACK_CLASSES - j;
-        int rem = n_class[j], placed = 0;
+        int rem = (j < j_cut) ? n_class[j] : 0, placed = 0;
         while (rem > 0 && nchunks < PACK_MAX_CHUNKS) {
             const int r = pack_find_level(t.mask, c, t.cap);
             if (r < 0) break;

@@ -6,11 +6,11 @@
 #include "eml_pack.cuh"
 
 // the two paths of pack_classes (level bitmask in registers / in memory) on one class histogram: 1 if all tables agree
-extern "C" int pack_paths_agree(const int* n_class, int slots, float eps) {
+extern "C" int pack_paths_agree(const int* n_class, int slots, float eps, float tail_fraction) {
     using namespace eml;
     static PackTables a, b;
-    pack_classes(n_class, slots, eps, a, false, true);
-    pack_classes(n_class, slots, eps, b, false, false);
+    pack_classes(n_class, slots, eps, a, false, true, tail_fraction);
+    pack_classes(n_class, slots, eps, b, false, false, tail_fraction);
     if (a.cap != b.cap) return 0;
     for (int j = 0; j <= PACK_CLASSES; ++j) if (a.cbeg[j] != b.cbeg[j]) return 0;
     for (int k = 0; k < a.cbeg[PACK_CLASSES]; ++k) if (a.chunk_key[k] != b.chunk_key[k] || a.chunk_end[k] != b.chunk_end[k]) return 0;
@@ -19,7 +19,7 @@ extern "C" int pack_paths_agree(const int* n_class, int slots, float eps) {
     return a.cap < 128 ? 2 : 1;      // 2: the register path was taken
 }
 
-extern "C" int pack_order_host(int n, const float* cost, int slots, float eps, int* order_out, int* keys_out) {
+extern "C" int pack_order_host(int n, const float* cost, int slots, float eps, float tail_fraction, int* order_out, int* keys_out) {
     using namespace eml;
     float mx = 0.f;
     for (int b = 0; b < n; ++b) mx = std::max(mx, cost[b]);
@@ -37,7 +37,7 @@ extern "C" int pack_order_host(int n, const float* cost, int slots, float eps, i
     }
     s_class[PACK_CLASSES] = n;
     static PackTables t;
-    pack_classes(n_class, slots, eps, t);
+    pack_classes(n_class, slots, eps, t, false, true, tail_fraction);
     std::vector<int> key(n), hist2(t.cap + 2, 0), start2(t.cap + 2, 0);
     for (int j = 0; j < PACK_CLASSES; ++j)
         for (int p = s_class[j]; p < s_class[j + 1]; ++p) {

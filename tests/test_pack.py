@@ -25,12 +25,12 @@ def lib(tmp_path_factory):
     return ctypes.CDLL(out)
 
 
-def pack(lib, cost, slots, eps=0.05):
+def pack(lib, cost, slots, eps=0.05, tail=0.0):
     n = len(cost)
     c = np.ascontiguousarray(cost, dtype=np.float32)
     order = np.full(n, -1, dtype=np.int32)
     keys = np.full(n, -1, dtype=np.int32)
-    cap = lib.pack_order_host(n, c.ctypes.data_as(ctypes.c_void_p), slots, ctypes.c_float(eps),
+    cap = lib.pack_order_host(n, c.ctypes.data_as(ctypes.c_void_p), slots, ctypes.c_float(eps), ctypes.c_float(tail),
                               order.ctypes.data_as(ctypes.c_void_p), keys.ctypes.data_as(ctypes.c_void_p))
     return order, keys, cap
 
@@ -86,6 +86,18 @@ def test_packing_beats_the_longest_first_list_on_the_bench_batch(lib):
         napp = (cost - 45.0) / 1.28
         order, _, _ = pack(lib, fixed + per * napp, slots)
         assert busy_fraction(cost, order, slots) > 0.89
+    # the greedy tail (cheapest 10 % of the models left unpacked) buys robustness against run-time noise
+    rng = np.random.default_rng(3)
+    order_tail, keys_tail, cap_tail = pack(lib, cost, slots, tail=0.10)
+    assert 0.05 * len(cost) < (keys_tail == cap_tail + 1).sum() <= 0.13 * len(cost)      # the tail plus what did not fit
+    order_plain, _, _ = pack(lib, cost, slots)
+    assert busy_fraction(cost, order_tail, slots) > 0.92
+    plain = tailed = 0.0
+    for _ in range(4):
+        noisy5 = cost * (1.0 + 0.05 * rng.standard_normal(len(cost)))
+        plain += busy_fraction(noisy5, order_plain, slots) / 4
+        tailed += busy_fraction(noisy5, order_tail, slots) / 4
+    assert tailed > plain + 0.02 and tailed > 0.90
     # and against 3 % noise of the real run times
     noisy = cost * (1.0 + 0.03 * np.random.default_rng(0).standard_normal(len(cost)))
     order, _, _ = pack(lib, cost, slots)
@@ -109,7 +121,8 @@ def test_register_and_memory_paths_of_the_packing_agree(lib):
         else:
             q = np.full(n, int(rng.integers(0, 64)))
         n_class = np.bincount(63 - q, minlength=64).astype(np.int32)      # class 0 = most expensive
-        res = lib.pack_paths_agree(n_class.ctypes.data_as(ctypes.c_void_p), slots, ctypes.c_float(float(rng.uniform(0, 0.2))))
+        res = lib.pack_paths_agree(n_class.ctypes.data_as(ctypes.c_void_p), slots, ctypes.c_float(float(rng.uniform(0, 0.2))),
+                                   ctypes.c_float(float(rng.choice([0.0, 0.1, 0.3]))))
         assert res in (1, 2), (trial, n, slots, shape)
         took_registers += res == 2
     assert 50 < took_registers < 400
