@@ -418,12 +418,13 @@ def run_b200(args):
 
     # ---- second headline metric: RJMCMC steps/s of the batched chain engine (propose -> evaluate -> accept on device)
     if not args.no_chains:
-        from effective_model_learning_b200 import BatchedChains, configs
+        from effective_model_learning_b200 import BatchedChains, configs, definitions
         cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[CONFIG_INDEX])
         rj = {}
         for label, init in (('from_initial_model', None), ('from_library_models', params_host)):
             eng = BatchedChains(ts, targets, OBS3, n_chains=B, n_defects=args.defects, n_qubits=args.qubits,
-                                seed=1000 + rank, device=local, initial_params=init, **cfg)
+                                seed=1000 + rank, device=local, initial_params=init,
+                                defect_initial_state=definitions.ops['mm'], **cfg)
             eng.run(max(2, args.warmup), stream=stream)
             barrier()
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

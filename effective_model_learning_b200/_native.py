@@ -23,9 +23,9 @@ FLAG_NO_SECTOR_REDUCTION = 1     # EmlOptions.reserved bit 0: evolve the whole d
 
 # every symbol include/eml_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
-           'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count', 'eml_set_order_pack_mode', 'eml_predict_applications',
+           'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count', 'eml_debug_phase_clocks', 'eml_set_order_pack_mode', 'eml_predict_applications',
            'eml_plan_kernel_name', 'eml_measure_fp64_peak', 'eml_chains_create', 'eml_chains_destroy',
-           'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device', 'eml_chains_state_bytes',
+           'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device', 'eml_chains_bad_evaluations', 'eml_chains_state_bytes',
            'eml_chains_export', 'eml_chains_import')
 CHAIN_STATS = 8
 COL_DEFECT_ENERGY, COL_Q2D_COUPLING, COL_D2D_COUPLING, COL_QUBIT_L, COL_DEFECT_L, COL_FIXED = range(6)
@@ -97,6 +97,7 @@ def load():
         lib.eml_chains_stats_device.argtypes = [vp]
         lib.eml_chains_stats_device.restype = vp
         lib.eml_chains_state_bytes.argtypes = [vp]
+        lib.eml_chains_bad_evaluations.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         lib.eml_chains_state_bytes.restype = C.c_size_t
         lib.eml_chains_export.argtypes = [vp, vp]
         lib.eml_chains_import.argtypes = [vp, vp]
@@ -108,7 +109,13 @@ def last_error() -> str:
     return load().eml_last_error_string().decode()
 
 
+class NotConvergedError(RuntimeError):
+    """EML_ERR_NOT_CONVERGED: at least one model of the batch hit the series cap or the step-count / overflow guard."""
+
+
 def check(rc: int, what: str):
+    if rc == EML_ERR_NOT_CONVERGED:
+        raise NotConvergedError(f'{what} failed ({rc}): {last_error()}')
     if rc != EML_OK:
         raise RuntimeError(f'{what} failed ({rc}): {last_error()}')
 

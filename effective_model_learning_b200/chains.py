@@ -41,7 +41,12 @@ class BatchedChains:
     n_chains chains for a model family of `n_qubits` qubits + `n_defects` defects.
 
     target_datasets: [K][T] (shared by all chains) or [S][K][T] with `target_set[n_chains]` choosing one per chain.
-    Hyperparameters take the names and meaning of LearningChain's (configs.py dictionaries can be passed as **config).
+    Hyperparameters take the names, meaning AND DEFAULTS of LearningChain's (configs.py dictionaries can be passed as
+    **config): qubits start in `plus`, defects in `gnd` (basic_model.py:259-281) -- the reference's production runs pass
+    defect_initial_state=ops['mm'] explicitly (execute_learning_full.py:151-164), and so must callers of this class;
+    jump lengths and step options fall back to LearningChain.Defaults.  The one exception is params_bounds, which is
+    required: the device-side proposal kernel samples new processes uniformly inside the bounds
+    (process_handling.py:98-103) and has no gamma-prior branch.
     Chain c uses the random stream of global chain number first_chain + c.
     """
 
@@ -65,14 +70,21 @@ class BatchedChains:
         targets = np.asarray(target_datasets, dtype=np.complex128)
         if targets.ndim == 1:
             targets = targets[None]
+        from .learning_chain import LearningChain
+        defaults = LearningChain.Defaults
+        if qubit_initial_state is None or qubit_initial_state is False:
+            qubit_initial_state = definitions.ops['plus']
+        if defect_initial_state is None or defect_initial_state is False:
+            defect_initial_state = definitions.ops['gnd']
         self.ctx = self.layout.context(np.asarray(target_times, dtype=np.float64), obs,
                                        qubit_state=qubit_initial_state, defect_state=defect_initial_state, device=device)
         self.ctx.set_targets(targets)
-        plan = self.ctx.plan
+        plan = self.ctx.pin_plan()      # the native engine keeps a pointer to the plan: it must outlive the engine
+        self._pinned = True
 
-        steps = dict(chain_step_options or {})
-        jumps = params_handler_hyperparams or {}
-        ji = jumps.get('initial_jump_lengths', {'couplings': 0.001, 'energies': 0.01, 'Ls': 0.00001})
+        steps = dict(chain_step_options or defaults.chain_step_options)
+        jumps = params_handler_hyperparams or defaults.params_handler_hyperparams
+        ji = jumps.get('initial_jump_lengths', defaults.params_handler_hyperparams['initial_jump_lengths'])
         ja = jumps.get('annealed_jump_lengths', ji)
         cls = column_classes(self.layout)
         self._cls = cls
@@ -110,10 +122,14 @@ class BatchedChains:
         lib = _native.load()
         self._lib = lib
         handle = C.c_void_p()
-        _native.check(lib.eml_chains_create(plan.handle, C.byref(h), self.n_chains,
-                                            initial_params.ctypes.data_as(C.POINTER(C.c_double)),
-                                            ts.ctypes.data_as(C.POINTER(C.c_int32)) if ts is not None else None,
-                                            C.c_uint64(seed & (2 ** 64 - 1)), int(first_chain), C.byref(handle)), 'eml_chains_create')
+        try:
+            _native.check(lib.eml_chains_create(plan.handle, C.byref(h), self.n_chains,
+                                                initial_params.ctypes.data_as(C.POINTER(C.c_double)),
+                                                ts.ctypes.data_as(C.POINTER(C.c_int32)) if ts is not None else None,
+                                                C.c_uint64(seed & (2 ** 64 - 1)), int(first_chain), C.byref(handle)), 'eml_chains_create')
+        except Exception:
+            self._unpin()
+            raise
         self._h = handle
         self.steps_done = 0
 
@@ -174,10 +190,27 @@ class BatchedChains:
             out.append(m)
         return out
 
+    def bad_evaluations(self):
+        """
+        (per-chain counts, total) of proposals that were rejected because their evaluation did not converge or gave a
+        non-finite loss (the reference's mesolve would have evaluated them; DESIGN.md, deviations).
+        """
+        per = np.zeros(self.n_chains, dtype=np.int32)
+        tot = C.c_int64(0)
+        _native.check(self._lib.eml_chains_bad_evaluations(self._h, per.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(tot)),
+                      'eml_chains_bad_evaluations')
+        return per, int(tot.value)
+
+    def _unpin(self):
+        if getattr(self, '_pinned', False):
+            self._pinned = False
+            self.ctx.unpin_plan()
+
     def close(self):
         if getattr(self, '_h', None):
             self._lib.eml_chains_destroy(self._h)
             self._h = None
+        self._unpin()
 
     def __del__(self):
         try:

@@ -24,6 +24,7 @@ bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 void set_order_pack_mode(int mode);
+cudaError_t read_phase_clocks(unsigned long long* out, bool reset);
 cudaError_t warp_predicted_applications(const DevProblem& P, bool sector, long long n_models, const double* params, float* out,
                                         cudaStream_t stream);
 }  // namespace eml
@@ -58,6 +59,13 @@ extern "C" {
 int eml_version(void) { return EML_VERSION_MAJOR * 1000 + EML_VERSION_MINOR; }
 const char* eml_last_error_string(void) { return eml_last_error_ref().c_str(); }
 int64_t eml_launch_count(void) { return (int64_t)g_launches.load(); }
+int eml_debug_phase_clocks(uint64_t* out8, int reset) {
+    if (!out8) return fail(EML_ERR_INVALID_ARGUMENT, "out8 is NULL");
+    unsigned long long tmp[8];
+    EML_CUDA(eml::read_phase_clocks(tmp, reset != 0));
+    for (int i = 0; i < 8; ++i) out8[i] = tmp[i];
+    return EML_OK;
+}
 void eml_set_order_pack_mode(int mode) { eml::set_order_pack_mode(mode); }
 
 int eml_device_count(int* count) {

@@ -5,6 +5,8 @@
 // ProcessHandler add/remove moves (process_handling.py:60-602).
 #include <cmath>
 #include <new>
+#include <string>
+#include <vector>
 
 #include <cstdlib>
 #include "eml_plan.hpp"
@@ -45,6 +47,7 @@ struct ChainState {
     int* counters;      // [C][4] tot_RJ, acc_RJ, tot_tweak, acc_tweak
     int* annealed;      // [C]
     double* last_ratio; // [C] last window acceptance ratio
+    int* bad_evals;     // [C] proposals rejected because their evaluation did not converge / gave a non-finite loss
 };
 
 // ---- counter-based RNG: splitmix64 of (key ^ counter * golden); mirrored in tests/chain_reference.py
@@ -168,6 +171,16 @@ __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S,
     for (int m = 0; m < N_MOVES; ++m) wsum += H.priority[m] * ways[m];
     const double u = rng.uniform();
     int mv = N_MOVES - 1;
+    if (!(wsum > 0.0)) {
+        // no move with a non-zero priority is available (e.g. only jump moves enabled and none applicable): re-propose the
+        // current model with acceptance probability 0 -- the step is counted, the chain does not move
+        for (int p = 0; p < P; ++p) prop[p] = cur[p];
+        S.log_ratio[c] = 0.0;
+        S.move[c] = MV_TWEAK;
+        S.counters[c * 4 + 2] += 1;
+        S.rng_ctr[c] = rng.ctr;
+        return;
+    }
     {
         double cdf = 0.0;
         for (int m = 0; m < N_MOVES; ++m) {
@@ -231,7 +244,8 @@ __global__ void chains_propose_kernel(const ChainHyperDev H, const ChainState S,
     S.rng_ctr[c] = rng.ctr;
 }
 
-__global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo, const long long c_hi,
+__global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, const int* __restrict__ eval_status,
+                                     const long long c_lo, const long long c_hi,
                                      const unsigned long long seed, const long long first_chain, double* hist_loss,
                                      double* hist_aprob, int* hist_code, double* hist_params) {
     const long long c = c_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,7 +254,12 @@ __global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, 
     Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
     const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
     const double a = exp(-1.0 / S.temp[c] * (Lp - Lc)) * S.log_ratio[c];     // learning_chain.py:802-805
-    const bool accept = rng.uniform() < a;
+    // a proposal whose evaluation did not converge (status < 0: series cap, overflow guard, non-finite generator) still
+    // carries a finite-looking loss: it must never be accepted or become the best model.  The uniform draw is consumed
+    // either way so that the random stream does not depend on it.
+    const bool usable = eval_status[c] >= 0 && isfinite(Lp);
+    const bool accept = (rng.uniform() < a) && usable;
+    if (!usable) S.bad_evals[c] += 1;
     const int mv = S.move[c];
     if (accept) {
         for (int p = 0; p < P; ++p) S.cur[c * P + p] = S.prop[c * P + p];
@@ -281,7 +300,7 @@ __global__ void chains_init_kernel(const ChainHyperDev H, const ChainState S, co
     S.best_loss[c] = S.prop_loss[c];
     for (int k = 0; k < 3; ++k) S.jump[c * 3 + k] = H.jump_initial[k];
     S.rng_ctr[c] = 0; S.window_bits[c] = 0; S.step[c] = 0; S.kwin[c] = 0; S.move[c] = 0; S.annealed[c] = 0;
-    S.last_ratio[c] = 0.0;
+    S.last_ratio[c] = 0.0; S.bad_evals[c] = 0;
     for (int k = 0; k < 4; ++k) S.counters[c * 4 + k] = 0;
     int n_proc = 0;
     for (int p = 0; p < P; ++p) {
@@ -306,6 +325,7 @@ struct EmlChains {
     std::vector<void*> owned;
     int* d_target_set = nullptr;
     int* d_status = nullptr;
+    std::vector<int> h_col_class;
     // Large batches advance as two independent groups of chains on two streams: while the last (shortest) models
     // of one group's evaluation finish, the other group's next evaluation already fills the idle SMs.
     static constexpr int MAX_GROUPS = 4;
@@ -375,6 +395,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     CH_TRY(dalloc(ch, &d_cls, (size_t)P));
     if (cudaMemcpy(d_cls, h->col_class, sizeof(int) * P, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy col_class"); }
     H.col_class = d_cls;
+    ch->h_col_class.assign(h->col_class, h->col_class + P);
     eml::ChainState& S = ch->S;
     const size_t C = (size_t)n_chains;
     CH_TRY(dalloc(ch, &S.cur, C * P)); CH_TRY(dalloc(ch, &S.prop, C * P)); CH_TRY(dalloc(ch, &S.best, C * P));
@@ -383,6 +404,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     CH_TRY(dalloc(ch, &S.stats, C * EML_CHAIN_STATS)); CH_TRY(dalloc(ch, &S.rng_ctr, C)); CH_TRY(dalloc(ch, &S.window_bits, C));
     CH_TRY(dalloc(ch, &S.step, C)); CH_TRY(dalloc(ch, &S.kwin, C)); CH_TRY(dalloc(ch, &S.move, C));
     CH_TRY(dalloc(ch, &S.counters, C * 4)); CH_TRY(dalloc(ch, &S.annealed, C)); CH_TRY(dalloc(ch, &S.last_ratio, C));
+    CH_TRY(dalloc(ch, &S.bad_evals, C));
     CH_TRY(dalloc(ch, &ch->d_status, C));
     if (target_set) {
         for (int64_t i = 0; i < n_chains; ++i)
@@ -393,6 +415,20 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     if (cudaMemcpy(S.cur, initial_params, sizeof(double) * C * P, cudaMemcpyHostToDevice) != cudaSuccess) { eml_chains_destroy(ch); return fail(EML_ERR_CUDA, "memcpy initial params"); }
     // loss of the initial models (LearningChain.__init__, learning_chain.py:298)
     CH_TRY(eml_eval_batch(plan, n_chains, S.cur, ch->d_target_set, nullptr, S.prop_loss, ch->d_status, nullptr));
+    {   // a chain cannot start from a model whose evaluation failed: its acceptance probabilities would all be NaN
+        std::vector<int> st(C);
+        std::vector<double> l0(C);
+        if (cudaMemcpy(st.data(), ch->d_status, sizeof(int) * C, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(l0.data(), S.prop_loss, sizeof(double) * C, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            eml_chains_destroy(ch);
+            return fail(EML_ERR_CUDA, "memcpy initial status");
+        }
+        for (size_t i = 0; i < C; ++i)
+            if (st[i] < 0 || !std::isfinite(l0[i])) {
+                eml_chains_destroy(ch);
+                return fail(EML_ERR_NOT_CONVERGED, "the initial model of chain " + std::to_string(i) + " could not be evaluated (series cap, overflow guard or non-finite parameters)");
+            }
+    }
     // groups: two halves when every half still has several models per resident warp
     ch->n_groups = (n_chains >= 2048) ? 2 : 1;
     if (const char* env = std::getenv("EML_CHAIN_GROUPS")) {       // A/B switch for measurements
@@ -441,7 +477,7 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
                                            nullptr, ch->S.prop_loss + lo, ch->d_status + lo, gs, ch->d_status + lo,
                                            ch->g_counter[g], ch->g_order[g]);
             if (rc != EML_OK) return rc;
-            eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain,
+            eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
                                                              hist_loss ? hist_loss + i * ch->n : nullptr,
                                                              hist_aprob ? hist_aprob + i * ch->n : nullptr,
                                                              hist_code ? hist_code + i * ch->n : nullptr,
@@ -472,6 +508,18 @@ int eml_chains_read(EmlChains* ch, double* current_params, double* current_loss,
 
 const double* eml_chains_stats_device(EmlChains* ch) { return ch ? ch->S.stats : nullptr; }
 
+int eml_chains_bad_evaluations(EmlChains* ch, int32_t* per_chain, int64_t* total) {
+    if (!ch) return fail(EML_ERR_INVALID_ARGUMENT, "chains is NULL");
+    EML_CUDA(cudaSetDevice(ch->plan->device));
+    EML_CUDA(cudaDeviceSynchronize());
+    std::vector<int> host((size_t)ch->n);
+    EML_CUDA(cudaMemcpy(host.data(), ch->S.bad_evals, sizeof(int) * (size_t)ch->n, cudaMemcpyDeviceToHost));
+    long long sum = 0;
+    for (size_t i = 0; i < host.size(); ++i) { sum += host[i]; if (per_chain) per_chain[i] = host[i]; }
+    if (total) *total = sum;
+    return EML_OK;
+}
+
 // ---- checkpoint / resume: every per-chain array, in a fixed order
 struct Segment { void* ptr; size_t bytes; };
 static std::vector<Segment> state_segments(const EmlChains* ch) {
@@ -479,13 +527,31 @@ static std::vector<Segment> state_segments(const EmlChains* ch) {
     const eml::ChainState& S = ch->S;
     return {{S.cur, C * P * 8}, {S.best, C * P * 8}, {S.cur_loss, C * 8}, {S.best_loss, C * 8}, {S.jump, C * 3 * 8},
             {S.stats, C * EML_CHAIN_STATS * 8}, {S.rng_ctr, C * 8}, {S.window_bits, C * 8}, {S.step, C * 8},
-            {S.last_ratio, C * 8}, {S.kwin, C * 4}, {S.counters, C * 4 * 4}, {S.annealed, C * 4}, {ch->d_status, C * 4}};
+            {S.last_ratio, C * 8}, {S.kwin, C * 4}, {S.counters, C * 4 * 4}, {S.annealed, C * 4}, {ch->d_status, C * 4},
+            {S.bad_evals, C * 4}};
 }
-static const unsigned long long kBlobMagic = 0x454d4c4348413031ull;   // "EMLCHA01"
+static const unsigned long long kBlobMagic = 0x454d4c4348413032ull;   // "EMLCHA02"
+constexpr int kBlobHead = 6;      // magic, n_chains, n_params, seed, first_chain, layout hash
+// FNV-1a over everything a checkpoint silently depends on: column classes, bounds, priorities, jump lengths, window ...
+static unsigned long long layout_hash(const EmlChains* ch, const std::vector<int>& col_class) {
+    unsigned long long h = 0xcbf29ce484222325ull;
+    auto mix = [&h](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
+    };
+    const eml::ChainHyperDev& H = ch->H;
+    mix(col_class.data(), col_class.size() * sizeof(int));
+    mix(&H.window, sizeof(H.window)); mix(H.priority, sizeof(H.priority));
+    mix(&H.temperature, sizeof(double)); mix(&H.temperature_scale, sizeof(double)); mix(&H.complexity_factor, sizeof(double));
+    mix(H.lo, sizeof(H.lo)); mix(H.hi, sizeof(H.hi)); mix(H.jump_initial, sizeof(H.jump_initial)); mix(H.jump_annealed, sizeof(H.jump_annealed));
+    mix(&H.jump_rescale, sizeof(double)); mix(&H.acc_target, sizeof(double)); mix(&H.acc_band, sizeof(double));
+    mix(&H.shock_anneal_at, sizeof(H.shock_anneal_at));
+    return h;
+}
 
 size_t eml_chains_state_bytes(const EmlChains* ch) {
     if (!ch) return 0;
-    size_t total = 4 * sizeof(unsigned long long);
+    size_t total = kBlobHead * sizeof(unsigned long long);
     for (const Segment& s : state_segments(ch)) total += s.bytes;
     return total;
 }
@@ -496,7 +562,8 @@ int eml_chains_export(EmlChains* ch, void* blob) {
     EML_CUDA(cudaDeviceSynchronize());
     unsigned long long* head = (unsigned long long*)blob;
     head[0] = kBlobMagic; head[1] = (unsigned long long)ch->n; head[2] = (unsigned long long)ch->H.n_params; head[3] = ch->seed;
-    char* out = (char*)(head + 4);
+    head[4] = (unsigned long long)ch->first_chain; head[5] = layout_hash(ch, ch->h_col_class);
+    char* out = (char*)(head + kBlobHead);
     for (const Segment& s : state_segments(ch)) {
         EML_CUDA(cudaMemcpy(out, s.ptr, s.bytes, cudaMemcpyDeviceToHost));
         out += s.bytes;
@@ -509,10 +576,14 @@ int eml_chains_import(EmlChains* ch, const void* blob) {
     const unsigned long long* head = (const unsigned long long*)blob;
     if (head[0] != kBlobMagic || head[1] != (unsigned long long)ch->n || head[2] != (unsigned long long)ch->H.n_params)
         return fail(EML_ERR_INVALID_ARGUMENT, "checkpoint does not match this engine (magic / n_chains / n_params)");
+    if (head[4] != (unsigned long long)ch->first_chain)
+        return fail(EML_ERR_INVALID_ARGUMENT, "checkpoint was written for a different first_chain (chain partition)");
+    if (head[5] != layout_hash(ch, ch->h_col_class))
+        return fail(EML_ERR_INVALID_ARGUMENT, "checkpoint was written under a different parameter layout or different chain hyperparameters");
     EML_CUDA(cudaSetDevice(ch->plan->device));
     EML_CUDA(cudaDeviceSynchronize());
-    ch->seed = head[3];
-    const char* in = (const char*)(head + 4);
+    ch->seed = head[3];     // the random streams continue from the checkpoint's seed and counters
+    const char* in = (const char*)(head + kBlobHead);
     for (const Segment& s : state_segments(ch)) {
         EML_CUDA(cudaMemcpy(s.ptr, in, s.bytes, cudaMemcpyHostToDevice));
         in += s.bytes;

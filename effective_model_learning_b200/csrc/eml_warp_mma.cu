@@ -34,6 +34,7 @@
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include "eml_common.cuh"
@@ -73,8 +74,15 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 #endif                             // -2.3 % with the parity-blocked variant (was +1 % when the kernel was FP64-pipe bound)
 constexpr int CHEB_KCAP_TL2 = EML_CHEB_KCAP_TL2, CHEB_KCAP_TL1 = 256;
 constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
-constexpr int CHEB_KCAP_SB = 540;      // sector variant: 12 warps per SM, two trace values per term
-constexpr int CTAS_PER_SM_SB = 3;
+#ifndef EML_CHEB_KCAP_SB
+#define EML_CHEB_KCAP_SB 396
+#endif
+#ifndef EML_WARPS_PER_SM_SB
+#define EML_WARPS_PER_SM_SB 16
+#endif
+constexpr int CHEB_KCAP_SB = EML_CHEB_KCAP_SB;      // sector variant: 16 warps per SM (<= 128 regs, 14 KB shared memory per warp), two trace values per term
+constexpr int WARPS_PER_SM_SB = EML_WARPS_PER_SM_SB;
+static_assert(WARPS_PER_SM_SB % EML_WARPS_PER_CTA == 0, "resident warps per SM must be a whole number of CTAs");
 
 template <int TL, bool CHEB, bool SB = false>
 struct alignas(16) WarpScratch {
@@ -91,12 +99,30 @@ struct alignas(16) WarpScratch {
     double colsum[16];
     double misc[4];
     static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
+    // SB: one 8 x 8 complex tile, (re, im) interleaved, two buffers (256 doubles in xt_re; xt_im unused)
     alignas(16) double xt_re[XT];
-    alignas(16) double xt_im[XT];   // X' staged column-major (swizzled) for the conjugate transpose
+    alignas(16) double xt_im[SB ? 2 : XT];   // X' staged column-major (swizzled) for the conjugate transpose
     alignas(16) double tr[(KCAP + 1) * NTR];                      // partial traces of the Chebyshev terms
 };
 static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_SB + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
-static_assert((CHEB_KCAP_SB + 1) * 2 >= 4 * 16 * 16, "the trace table doubles as scratch for the spread bound");
+static_assert((CHEB_KCAP_SB + 1) * 2 >= 2 * 16 * 16, "the trace table doubles as scratch for the spread bound");
+
+// Phase clocks (profiling builds only, -DEML_PROFILE_PHASES): warp-cycles spent in set-up, recurrence, outputs, epilogue,
+// summed over all warps, plus the cycles between a warp's last model and the end of the launch are NOT included.
+__device__ unsigned long long g_phase_clk[8];
+#ifdef EML_PROFILE_PHASES
+#define PHASE_MARK(slot) do { const long long _now = clock64(); if (lane == 0) atomicAdd(&g_phase_clk[slot], (unsigned long long)(_now - phase_t)); phase_t = _now; } while (0)
+#else
+#define PHASE_MARK(slot) do { } while (0)
+#endif
+cudaError_t read_phase_clocks(unsigned long long* out, bool reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(g_phase_clk));
+    if (e == cudaSuccess && reset) {
+        const unsigned long long zero[8] = {0};
+        e = cudaMemcpyToSymbol(g_phase_clk, zero, sizeof(zero));
+    }
+    return e;
+}
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -188,8 +214,8 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
 }
 
 template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
-// resident warps per SM: 16 (d = 8), 12 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM* are quoted for four-warp CTAs
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4 * ((TL == 1) ? 4 : (SB ? CTAS_PER_SM_SB : CTAS_PER_SM)) / WARPS_PER_CTA)
+// resident warps per SM: 16 (d = 8), 16 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM is quoted for four-warp CTAs
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (SB ? WARPS_PER_SM_SB : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
@@ -243,6 +269,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 
     for (;;) {
         // ---- dynamic model fetch (one atomic per warp)
+#ifdef EML_PROFILE_PHASES
+        long long phase_t = clock64();
+#endif
         unsigned int bidx = 0;
         if (lane == 0) bidx = atomicAdd(counter, 1u);
         bidx = __shfl_sync(0xffffffffu, bidx, 0);
@@ -724,7 +753,10 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
                 mu *= 1.0 / D;
                 double* Ma = S.tr;                                   // [re | im] planes of D x D
-                double* Mb = S.tr + 2 * D * D;
+                // second buffer: behind the first one when the trace table is large enough, else (sector variant: 16 warps
+                // per SM, small table) packed for a real H, or over G (dead once Ma is filled) for a complex H
+                constexpr bool ROOMY = (Scratch::KCAP + 1) * NTR >= 4 * D * D;
+                double* Mb = ROOMY ? S.tr + 2 * D * D : (REAL_H ? S.tr + D * D : &S.G_re[0][0]);
                 for (int i = lane; i < D * D; i += 32) {
                     const int r = i / D, c = i % D;
                     Ma[i] = -S.G_im[r][c] - ((r == c) ? mu : 0.0);
@@ -775,10 +807,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             }
             cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
         }
+        PHASE_MARK(0);      // assembly, norm bound, fragments, spread bound, site ranges
         const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, P.times[T - 1] - P.times[0], cheb_zcap, Scratch::KCAP);
         const double Rb = plan.R, Sb = plan.S, ac = plan.ac, tau_max = plan.tau_max;
         {   // generator -> 2 (L + ac) / R  (stencil weights are stored halved)
             const double sc = 2.0 / Rb;
+            const double sw = SB ? 2.0 * sc : sc;      // the sector variant applies J(v) in one piece: weights unhalved
 #pragma unroll
             for (int I = 0; I < TL; ++I) {
 #pragma unroll
@@ -786,11 +820,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll
                 for (int J = 0; J < TL; ++J) {
 #pragma unroll
-                    for (int e = 0; e < FE; ++e) F3[I][J][e] *= sc;
-                    W0[I][J][0] = (W0[I][J][0] + 0.5 * ac) * sc; W0[I][J][1] = (W0[I][J][1] + 0.5 * ac) * sc;
+                    for (int e = 0; e < FE; ++e) F3[I][J][e] *= sw;
+                    W0[I][J][0] = (W0[I][J][0] + 0.5 * ac) * sw; W0[I][J][1] = (W0[I][J][1] + 0.5 * ac) * sw;
                 }
             }
-            f2 *= sc; f1 *= sc; f0[0] *= sc; f0[1] *= sc;
+            f2 *= sw; f1 *= sw; f0[0] *= sw; f0[1] *= sw;
         }
         // 2x2 partial trace of a term straight into shared memory (dst[0..3] = rho00, rho11, Re rho01, Im rho01).  d = 16:
         // only the 8 lanes 4g + (g >> 1) hold partial-trace elements; a 3-stage reduce-scatter among exactly those lanes
@@ -805,18 +839,22 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }"
                          :: "r"(tr_base + (unsigned)(kterm * NTR * 8)), "d"(val), "r"((int)tr_lane) : "memory");
         };
+        // SB: only rho01 of the observed site moves.  It lives in tile (p, 1 ^ p), p = parity of the (equal) low bits of row
+        // and column; tile (1,0) is the conjugate transpose of tile (0,1) and a partial-trace element sits on the diagonal
+        // of its tile, so tile (0,1) alone supplies it (conjugated where p = 1); dst[0..1]
+        auto trace_store_sb = [&](const double (&mr)[2], const double (&mi)[2], const int kterm) {
+            const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
+            const double a2 = gp ? mr[1] : mr[0], a3 = gp ? mi[1] : mi[0];
+            const double v2 = a2, v3 = pl ? neg(a3) : a3;
+            const bool hb = g & 4;
+            double kk = (hb ? v3 : v2) + shfl(hb ? v2 : v3, dl4);
+            kk += shfl(kk, dl2);
+            kk += shfl(kk, dl1);
+            tr_put(kterm, kk);
+        };
         auto trace_store = [&](const double (&xr)[TL][TL][2], const double (&xi)[TL][TL][2], const int kterm) {
             if constexpr (SB) {
-                // only rho01 of the observed site moves: tile (p, 1 ^ p), p = parity of the (equal) low bits; dst[0..1]
-                const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
-                const double a2 = gp ? xr[0][1][1] : xr[0][1][0], a3 = gp ? xi[0][1][1] : xi[0][1][0];
-                const double b2 = gp ? xr[1][0][1] : xr[1][0][0], b3 = gp ? xi[1][0][1] : xi[1][0][0];
-                const double v2 = pl ? b2 : a2, v3 = pl ? b3 : a3;
-                const bool hb = g & 4;
-                double kk = (hb ? v3 : v2) + shfl(hb ? v2 : v3, dl4);
-                kk += shfl(kk, dl2);
-                kk += shfl(kk, dl1);
-                tr_put(kterm, kk);
+                trace_store_sb(xr[0][1], xi[0][1], kterm);
             } else if constexpr (TL == 2) {
                 double v0 = gp ? xr[0][0][1] : xr[0][0][0], v1 = gp ? xr[1][1][1] : xr[1][1][0];
                 double v2 = gp ? xr[0][1][1] : xr[0][1][0], v3 = gp ? xi[0][1][1] : xi[0][1][0];
@@ -886,6 +924,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             for (int sub = 0; UNI(sub < nsub); ++sub) {
                 const bool last = (sub == nsub - 1);
                 const bool need_acc = UNI(!(final_step && last));     // the state at the step end is needed
+                PHASE_MARK(1);      // plan, rescaling, first output, step scan
                 double cscale = 0.0;
                 if (need_acc) {
                     // J_k(tau_end R), k = 0..Kc: Miller's backward recurrence, every lane redundantly, normalised by
@@ -903,30 +942,188 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     cscale = exp(-ac * tau_end) / (2.0 * ssum + jn);
                     __syncwarp();
                 }
-                double v_re[TL][TL][2], v_im[TL][TL][2], ph_re[TL][TL][2], ph_im[TL][TL][2];
-#pragma unroll
-                for (int I = 0; I < TL; ++I)
-#pragma unroll
-                    for (int J = 0; J < TL; ++J)
+                if constexpr (SB) {
+                // ---- sector variant: the STATE is tile (0,1) alone (m); tile (1,0) = m^dag (n) is kept only as an operand:
+                //      w01 = J(v)01 + G00 m + m G11^dag + (previous term).  Every site flip maps tile (0,1) <-> (1,0) in the
+                //      parity coordinates, so the flip stencils read n; G00 m takes B = conj(n) from the lane's own registers,
+                //      m G11^dag takes A = m from the lane's own registers (k index permuted as for G's A fragments, whose
+                //      registers are also the B fragments of G11^dag).  No X' + X'^dag pass, half the stencil work, weights
+                //      unhalved; the new n = w01^dag goes through a double-buffered 1 KB tile in shared memory.
+                double m_re[2] = {acc_re[0][1][0], acc_re[0][1][1]}, m_im[2] = {acc_im[0][1][0], acc_im[0][1][1]};
+                double n_re[2], nn_im[2], p_re[2] = {0.0, 0.0}, p_im[2] = {0.0, 0.0};      // n = n_re - i nn_im
+                acc_re[0][1][0] = acc_re[0][1][1] = acc_im[0][1][0] = acc_im[0][1][1] = 0.0;
+                // transposition tile: element (R, C) of a plane at 2 pi + (R & 1), pi = 8 h + (a & 1) + 2 ((C >> 1) ^ h),
+                // a = R >> 1, h = 2 (C & 1) + (a >> 1): the STS.64 of the accumulator fragments (R = g, C = 2t + e) and the
+                // LDS.128 of the transposed pairs (R = 2t, 2t + 1; C = g) are both bank-conflict free.  Planes re | im of 64
+                // doubles, two buffers (term k uses buffer k & 1, so one __syncwarp per application suffices).
+                auto xt_addr = [](const int R, const int C) {
+                    const int a = R >> 1, h = 2 * (C & 1) + (a >> 1);
+                    return 2 * (8 * h + (a & 1) + 2 * ((C >> 1) ^ h)) + (R & 1);
+                };
+                double* const xs0 = S.xt_re + xt_addr(g, 2 * t), * const xs1 = S.xt_re + xt_addr(g, 2 * t + 1);
+                const double* const xl = S.xt_re + xt_addr(2 * t, g);
+                auto transpose_conj = [&](const int buf) {      // n = m^dag
+                    xs0[buf * 128] = m_re[0]; xs1[buf * 128] = m_re[1];
+                    xs0[buf * 128 + 64] = m_im[0]; xs1[buf * 128 + 64] = m_im[1];
+                    __syncwarp();
+                    const double2 cr = *reinterpret_cast<const double2*>(xl + buf * 128);
+                    const double2 ci = *reinterpret_cast<const double2*>(xl + buf * 128 + 64);
+                    n_re[0] = cr.x; n_re[1] = cr.y; nn_im[0] = ci.x; nn_im[1] = ci.y;
+                };
+                __syncwarp();
+                transpose_conj(1);
+                auto application = [&](const int k, auto na_tag, auto first_tag) {
+                    constexpr bool NA = decltype(na_tag)::value, FIRST = decltype(first_tag)::value;
+                    trace_store_sb(m_re, m_im, k);
+                    if constexpr (NA) {
+                        const double c = cJ[k] * cscale;
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            if (!live(I, J)) continue;
-                            v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e];
-                            ph_re[I][J][e] = 0.0; ph_im[I][J][e] = 0.0;
-                            acc_re[I][J][e] = 0.0; acc_im[I][J][e] = 0.0;
+                            acc_re[0][1][e] = fma(c, m_re[e], acc_re[0][1][e]);
+                            acc_im[0][1][e] = fma(c, m_im[e], acc_im[0][1][e]);
                         }
-                // Iteration 0 takes v = phi_0 with nothing added and gives 2 phi_1; from then on the stored input is halved
-                // (exponent decrement on the integer pipe) to supply phi_{k-1} / 2 ... so every term k >= 1 is carried
-                // DOUBLED, which is exactly the factor 2 of the series: the weights are plain J_k for all k.
-                auto run_terms = [&](auto na_tag) {
-                    constexpr bool NA = decltype(na_tag)::value;     // accumulate the state at the step end
-                    int hsub = 0;
-                    [[maybe_unused]] double hmul = 1.0;
+                    }
+                    double x_re[2], x_im[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x_re[e] = fma(W0[0][1][e], m_re[e], p_re[e]);
+                        x_im[e] = fma(W0[0][1][e], m_im[e], p_im[e]);
+                    }
+                    // m G11^dag: A = m (own registers), B = conj of G11's A fragment -- independent of n, issued first
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        if (!REAL_H) {
+                            dmma(x_re[0], x_re[1], m_re[ks], a_re[1][ks]);
+                            dmma(x_im[0], x_im[1], m_im[ks], a_re[1][ks]);
+                        }
+                        dmma(x_re[0], x_re[1], m_im[ks], a_im[1][ks]);
+                        dmma(x_im[0], x_im[1], m_re[ks], -a_im[1][ks]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x_re[e] = fma(F3[0][1][e], n_re[e], x_re[e]);
+                        x_im[e] = fma(F3[0][1][e], -nn_im[e], x_im[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x_re[e] = fma(f2, __shfl_xor_sync(0xffffffffu, n_re[e], 18), x_re[e]);
+                        x_im[e] = fma(f2, -__shfl_xor_sync(0xffffffffu, nn_im[e], 18), x_im[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x_re[e] = fma(f1, __shfl_xor_sync(0xffffffffu, n_re[e], 9), x_re[e]);
+                        x_im[e] = fma(f1, -__shfl_xor_sync(0xffffffffu, nn_im[e], 9), x_im[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x_re[e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, n_re[e ^ 1], 4), x_re[e]);
+                        x_im[e] = fma(f0[e], -__shfl_xor_sync(0xffffffffu, nn_im[e ^ 1], 4), x_im[e]);
+                    }
+                    // G00 m: B = conj(n) from the lane's own registers
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        if (!REAL_H) {
+                            dmma(x_re[0], x_re[1], a_re[0][ks], n_re[ks]);
+                            dmma(x_im[0], x_im[1], a_re[0][ks], nn_im[ks]);
+                        }
+                        dmma(x_re[0], x_re[1], a_im[0][ks], -nn_im[ks]);
+                        dmma(x_im[0], x_im[1], a_im[0][ks], n_re[ks]);
+                    }
+                    // T_2 = (2 At) T_1 + 2 T_0, afterwards T_{k+1} = (2 At) T_k + T_{k-1}
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        p_re[e] = FIRST ? 2.0 * m_re[e] : m_re[e]; p_im[e] = FIRST ? 2.0 * m_im[e] : m_im[e];
+                        m_re[e] = x_re[e]; m_im[e] = x_im[e];
+                    }
+                    transpose_conj(k & 1);
+                };
+                auto run_terms_sb = [&](auto na_tag) {
+                    application(0, na_tag, std::true_type{});
+#pragma unroll 2
+                    for (int k = 1; UNI(k < Kc); ++k) application(k, na_tag, std::false_type{});
+                    trace_store_sb(m_re, m_im, Kc);          // the last term
+                    if constexpr (decltype(na_tag)::value) {
+                        const double c = cJ[Kc] * cscale;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            acc_re[0][1][e] = fma(c, m_re[e], acc_re[0][1][e]);
+                            acc_im[0][1][e] = fma(c, m_im[e], acc_im[0][1][e]);
+                        }
+                    }
+                };
+                if (need_acc) run_terms_sb(std::true_type{}); else run_terms_sb(std::false_type{});
+                {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
+                    const double chk = fabs(m_re[0]) + fabs(m_im[0]) + fabs(m_re[1]);
+                    if (!UNI(chk < 1e300)) capped = true;
+                }
+                } else {
+                    double v_re[TL][TL][2], v_im[TL][TL][2], ph_re[TL][TL][2], ph_im[TL][TL][2];
+#pragma unroll
+                    for (int I = 0; I < TL; ++I)
+#pragma unroll
+                        for (int J = 0; J < TL; ++J)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                if (!live(I, J)) continue;
+                                v_re[I][J][e] = acc_re[I][J][e]; v_im[I][J][e] = acc_im[I][J][e];
+                                ph_re[I][J][e] = 0.0; ph_im[I][J][e] = 0.0;
+                                acc_re[I][J][e] = 0.0; acc_im[I][J][e] = 0.0;
+                            }
+                    // Iteration 0 takes v = phi_0 with nothing added and gives 2 phi_1; from then on the stored input is halved
+                    // (exponent decrement on the integer pipe) to supply phi_{k-1} / 2 ... so every term k >= 1 is carried
+                    // DOUBLED, which is exactly the factor 2 of the series: the weights are plain J_k for all k.
+                    auto run_terms = [&](auto na_tag) {
+                        constexpr bool NA = decltype(na_tag)::value;     // accumulate the state at the step end
+                        int hsub = 0;
+                        [[maybe_unused]] double hmul = 1.0;
 #pragma unroll CHEB_UNROLL
-                    for (int k = 0; UNI(k < Kc); ++k) {
-                        trace_store(v_re, v_im, k);       // partial trace of term k (overlaps the DMMAs below)
+                        for (int k = 0; UNI(k < Kc); ++k) {
+                            trace_store(v_re, v_im, k);       // partial trace of term k (overlaps the DMMAs below)
+                            if constexpr (NA) {
+                                const double c = cJ[k] * cscale;
+#pragma unroll
+                                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                                    for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                        for (int e = 0; e < 2; ++e) {
+                                            if (!live(I, J)) continue;
+                                            acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
+                                            acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
+                                        }
+                            }
+                            double x_re[TL][TL][2], x_im[TL][TL][2], w_re[TL][TL][2], w_im[TL][TL][2];
+#pragma unroll
+                            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                                for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        if (!live(I, J)) continue;
+                                        x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
+                                        x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
+                                    }
+                            apply_rest(v_re, v_im, x_re, x_im);
+                            symmetrise(x_re, x_im, w_re, w_im);       // (2 At) v + (previous term)
+#pragma unroll
+                            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                                for (int J = 0; J < TL; ++J)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        if (!live(I, J)) continue;
+                                        if constexpr (EML_HALVE_ON_FP64 == 1 || (EML_HALVE_ON_FP64 == 2 && PARITY)) {
+                                            ph_re[I][J][e] = hmul * v_re[I][J][e]; ph_im[I][J][e] = hmul * v_im[I][J][e];
+                                        } else {
+                                            ph_re[I][J][e] = scale_pow2(v_re[I][J][e], hsub); ph_im[I][J][e] = scale_pow2(v_im[I][J][e], hsub);
+                                        }
+                                        v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
+                                    }
+                            hsub = 0x00100000; hmul = 0.5;
+                        }
+                        trace_store(v_re, v_im, Kc);          // the last term
                         if constexpr (NA) {
-                            const double c = cJ[k] * cscale;
+                            const double c = cJ[Kc] * cscale;
 #pragma unroll
                             for (int I = 0; I < TL; ++I)
 #pragma unroll
@@ -938,57 +1135,16 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                                         acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
                                     }
                         }
-                        double x_re[TL][TL][2], x_im[TL][TL][2], w_re[TL][TL][2], w_im[TL][TL][2];
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    if (!live(I, J)) continue;
-                                    x_re[I][J][e] = fma(W0[I][J][e], v_re[I][J][e], ph_re[I][J][e]);
-                                    x_im[I][J][e] = fma(W0[I][J][e], v_im[I][J][e], ph_im[I][J][e]);
-                                }
-                        apply_rest(v_re, v_im, x_re, x_im);
-                        symmetrise(x_re, x_im, w_re, w_im);       // (2 At) v + (previous term)
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    if (!live(I, J)) continue;
-                                    if constexpr (EML_HALVE_ON_FP64 == 1 || (EML_HALVE_ON_FP64 == 2 && PARITY)) {
-                                        ph_re[I][J][e] = hmul * v_re[I][J][e]; ph_im[I][J][e] = hmul * v_im[I][J][e];
-                                    } else {
-                                        ph_re[I][J][e] = scale_pow2(v_re[I][J][e], hsub); ph_im[I][J][e] = scale_pow2(v_im[I][J][e], hsub);
-                                    }
-                                    v_re[I][J][e] = w_re[I][J][e]; v_im[I][J][e] = w_im[I][J][e];
-                                }
-                        hsub = 0x00100000; hmul = 0.5;
+                    };
+                    if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
+                    {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
+                        const double chk = fabs(v_re[0][TL - 1][0]) + fabs(v_im[0][TL - 1][0]) + fabs(v_re[TL - 1][0][1]);
+                        if (!UNI(chk < 1e300)) capped = true;
                     }
-                    trace_store(v_re, v_im, Kc);          // the last term
-                    if constexpr (NA) {
-                        const double c = cJ[Kc] * cscale;
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    if (!live(I, J)) continue;
-                                    acc_re[I][J][e] = fma(c, v_re[I][J][e], acc_re[I][J][e]);
-                                    acc_im[I][J][e] = fma(c, v_im[I][J][e], acc_im[I][J][e]);
-                                }
-                    }
-                };
-                if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
-                {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
-                    const double chk = fabs(v_re[0][TL - 1][0]) + fabs(v_im[0][TL - 1][0]) + fabs(v_re[TL - 1][0][1]);
-                    if (!UNI(chk < 1e300)) capped = true;
                 }
                 n_apply += Kc;
                 __syncwarp();
+                PHASE_MARK(2);      // recurrence (and the coefficient table of a non-final step)
                 if (UNI(last)) {
                     // ---- outputs of the step, 32 per round, Bessel weights by backward recurrence.  A round costs as many
                     //      iterations as its LATEST output needs terms, so the rounds are cut from the end of the list: the
@@ -1034,6 +1190,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         if (act) finish_output(kidx + 1 + p, r);
                     }
                     __syncwarp();
+                    PHASE_MARK(3);      // Bessel-weighted output sums, observables, loss terms
                 }
             }
             kidx += q;
@@ -1184,6 +1341,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             if (status != nullptr) status[b] = capped ? -1 : n_apply;
         }
         __syncwarp();
+        if constexpr (CHEB) { PHASE_MARK(4); }     // loss reduction, result stores
     }
 }
 
@@ -1292,6 +1450,9 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem)) != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (dev < 64) per_sm_cache[dev][variant] = per_sm;
+        if (std::getenv("EML_B200_DEBUG") != nullptr)
+            fprintf(stderr, "eml: warp kernel variant %d: %d CTAs of %d warps per SM, %zu B shared memory per CTA\n", variant, per_sm,
+                    WARPS_PER_CTA, smem);
     }
     long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models

@@ -99,6 +99,7 @@ class EvalContext:
         self.op_rows: list[np.ndarray] = []
         self.targets = None
         self._plan = None
+        self._pins = 0      # live native objects (BatchedChains engines) that hold this context's plan
 
     # -- library management
     def _op(self, name: str) -> int:
@@ -121,8 +122,20 @@ class EvalContext:
 
     def _drop_plan(self):
         if self._plan is not None:
+            if self._pins:
+                raise RuntimeError('the native plan of this context is in use by a live BatchedChains engine: close the '
+                                   'engine before growing the process library or clearing the targets')
             self._plan.close()
             self._plan = None
+
+    def pin_plan(self) -> '_native.Plan':
+        """The plan, kept alive until unpin_plan(): anything that would destroy it raises instead."""
+        plan = self.plan
+        self._pins += 1
+        return plan
+
+    def unpin_plan(self):
+        self._pins = max(0, self._pins - 1)
 
     def terms(self) -> list[tuple]:
         """Flat EmlTerm list (param, kind, site_a, site_b, op_a, op_b) of the current library."""
@@ -184,18 +197,16 @@ def context_for(model, obs_names, times, device=None) -> EvalContext:
         else:
             ctx = EvalContext(len(model.TLSs), states, q, obs_names, times, device)
         _contexts[key] = ctx
-        while len(_contexts) > _MAX_CONTEXTS:
-            _, old = _contexts.popitem(last=False)
-            old._drop_plan()
+        for old_key in [k for k, c in _contexts.items() if not c._pins][:max(0, len(_contexts) - _MAX_CONTEXTS)]:
+            _contexts.pop(old_key)._drop_plan()
     else:
         _contexts.move_to_end(key)
     return ctx
 
 
 def clear_contexts():
-    for ctx in _contexts.values():
-        ctx._drop_plan()
-    _contexts.clear()
+    for key in [k for k, c in _contexts.items() if not c._pins]:
+        _contexts.pop(key)._drop_plan()
 
 
 def is_hermitian(a: np.ndarray) -> bool:

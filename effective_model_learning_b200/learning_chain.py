@@ -13,18 +13,23 @@ What differs on purpose:
   * with no custom_function_on_dynamics_return the observables never leave the device: the
     kernel reduces them against the targets and returns only the loss;
   * class Defaults.params_priors / params_bounds are plain dicts (the reference's trailing
-    commas make them 1-tuples, learning_chain.py:119,125).
+    commas make them 1-tuples, learning_chain.py:119,125);
+  * a model the kernels refuse to integrate (norm bound x time span >= 1e5, or a capped series) gets loss +inf,
+    i.e. the proposal is rejected with a RuntimeWarning, where the reference's mesolve (nsteps = 1e9) would grind
+    through it; such models are counted in `unconverged_evaluations`.
 """
 from __future__ import annotations
 
 import copy
 import time
+import warnings
 
 import numpy as np
 import scipy as sp
 import scipy.special
 import scipy.stats
 
+from . import _native
 from . import engine
 from . import learning_model
 from . import params_handling
@@ -386,7 +391,17 @@ class LearningChain:
             raise RuntimeError('Hamiltonian not defined -- cannot calculate dynamics')
         ctx = self._context(model)
         params = ctx.params_of([engine.model_processes(model)])
-        _, loss = ctx.evaluate(params, want_expect=False, want_loss=True)
+        try:
+            _, loss = ctx.evaluate(params, want_expect=False, want_loss=True)
+        except _native.NotConvergedError as err:
+            # The kernels refuse a generator whose norm bound times the time span exceeds 1e5 (and report a capped
+            # series); the reference's mesolve (nsteps = 1e9, basic_model.py:386) would grind through such a model.
+            # Deviation: the proposal gets an infinite loss, i.e. it is rejected, and the chain carries on -- the same
+            # outcome BatchedChains gives it (forced reject).  Counted in self.unconverged_evaluations.
+            self.unconverged_evaluations = getattr(self, 'unconverged_evaluations', 0) + 1
+            warnings.warn(f'model evaluation did not converge, loss set to +inf (proposal will be rejected): {err}',
+                          RuntimeWarning, stacklevel=2)
+            return float('inf')
         return float(loss[0])
 
     def acceptance_probability(self, current, proposal, there, back, params_priors_ratio: float = 1) -> float:

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from effective_model_learning_b200 import configs, dist, output, synthetic  # noqa: E402
+from effective_model_learning_b200 import configs, definitions, dist, output, synthetic  # noqa: E402
 from effective_model_learning_b200.multiset import MultisetSweep  # noqa: E402
 
 experiment_name = sys.argv[1] if len(sys.argv) > 1 else 'multiset-demo'
@@ -45,7 +45,8 @@ for D_truth in (1, 2):
     dataset_names.append(f'sim-D{D_truth}')
     datasets.append((ts, data, measurement_observables))
 
-sweep = MultisetSweep(datasets, config_numbers, defects_numbers, [repetitions_number], seed=2024, device=local)
+sweep = MultisetSweep(datasets, config_numbers, defects_numbers, [repetitions_number], seed=2024, device=local,
+                      qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'])
 done = 0
 while done < iterations_number:
     n = min(checkpoint_every, iterations_number - done)

@@ -136,6 +136,10 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
 
 /* Number of kernels launched through this library since load (for bench accounting). */
 int64_t eml_launch_count(void);
+/* Profiling builds only (-DEML_PROFILE_PHASES; zeros otherwise): warp-cycles the d <= 16 Chebyshev evaluator spent per
+ * phase since the last reset, summed over warps -- [0] assembly + bounds, [1] plan + first output, [2] recurrence,
+ * [3] output sums, [4] epilogue.  Current device. */
+int eml_debug_phase_clocks(uint64_t* out8, int reset);
 /* Order in which the persistent warps of the d = 16 Chebyshev kernel fetch the models of a launch (results do not depend
  * on it): 0 longest-first list, 1 exact-cost packing for cold batches, 2 also with caller-measured costs (chain engine);
  * any other value returns to the build default / the EML_ORDER_PACK environment variable.  Process-wide. */
@@ -211,6 +215,11 @@ int eml_chains_read(EmlChains* chains, double* current_params, double* current_l
 /* Device pointer of the per-chain statistics table [n_chains][EML_CHAIN_STATS] (refreshed by every run), for
  * the checkpoint all_gather. */
 const double* eml_chains_stats_device(EmlChains* chains);
+/* Proposals that were force-rejected because their evaluation did not converge (status < 0) or gave a non-finite loss
+ * (synchronises): per_chain [n_chains] and / or the total; either may be NULL.  Such a proposal is never accepted and never
+ * becomes a chain's best model; the reference (qutip.mesolve with nsteps = 1e9, basic_model.py:386) would have
+ * integrated it -- a documented deviation. */
+int eml_chains_bad_evaluations(EmlChains* chains, int32_t* per_chain, int64_t* total);
 /* Checkpoint / resume: the complete chain state (models, losses, jump lengths, acceptance windows, counters,
  * random-stream positions) as one opaque host blob.  Importing it into an engine created with the same plan layout,
  * hyperparameters, n_chains, seed and first_chain continues the chains exactly where they were. */

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from effective_model_learning_b200 import BatchedChains, configs, engine
+from effective_model_learning_b200 import BatchedChains, configs, definitions, engine
 from oracle import lindblad_oracle as lo
 from tests.chain_reference import ReferenceChain, MOVES
 from tests.helpers import OBS3
@@ -22,7 +22,7 @@ def _setup(D, n_chains, steps_cfg=None, temperature=0.002):
     truth = lo.random_library_spec(np.random.default_rng(20260000 + 10 + D), 1, D)
     targets = np.array([np.asarray(e) for e in lo.expect_exact(truth, ts, OBS3)])
     targets = targets + np.random.default_rng(5).normal(0, 0.01, targets.shape)
-    eng = BatchedChains(ts, targets, OBS3, n_chains=n_chains, n_defects=D, seed=1234, **cfg)
+    eng = BatchedChains(ts, targets, OBS3, n_chains=n_chains, n_defects=D, seed=1234, defect_initial_state=definitions.ops['mm'], **cfg)
     return cfg, ts, targets, eng
 
 
@@ -101,7 +101,7 @@ def test_results_do_not_depend_on_how_chains_are_split_over_engines():
     whole.close()
     parts = []
     for lo_, hi_ in ((0, 24), (24, 64)):
-        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=2, seed=1234, first_chain=lo_, **cfg)
+        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=2, seed=1234, first_chain=lo_, defect_initial_state=definitions.ops['mm'], **cfg)
         eng.run(25)
         parts.append(eng.read())
         eng.close()
@@ -117,7 +117,7 @@ def test_two_group_pipelining_gives_the_same_chains():
     whole.close()
     parts = []
     for lo_, hi_ in ((0, 1000), (1000, 2304)):
-        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=1, seed=1234, first_chain=lo_, **cfg)
+        eng = BatchedChains(ts, targets, OBS3, n_chains=hi_ - lo_, n_defects=1, seed=1234, first_chain=lo_, defect_initial_state=definitions.ops['mm'], **cfg)
         eng.run(12)
         parts.append(eng.read())
         eng.close()
@@ -132,7 +132,7 @@ def test_checkpoint_resume_continues_exactly():
     a.run(30)
     want = a.read()
     a.close()
-    b = BatchedChains(ts, targets, OBS3, n_chains=40, n_defects=2, seed=1234, **cfg)
+    b = BatchedChains(ts, targets, OBS3, n_chains=40, n_defects=2, seed=1234, defect_initial_state=definitions.ops['mm'], **cfg)
     b.import_state(blob)
     b.run(30)
     got = b.read()
@@ -140,5 +140,5 @@ def test_checkpoint_resume_continues_exactly():
     for key in want:
         assert np.array_equal(want[key], got[key]), key
     with pytest.raises(RuntimeError):
-        c = BatchedChains(ts, targets, OBS3, n_chains=41, n_defects=2, seed=1234, **cfg)
+        c = BatchedChains(ts, targets, OBS3, n_chains=41, n_defects=2, seed=1234, defect_initial_state=definitions.ops['mm'], **cfg)
         c.import_state(blob)

@@ -2,7 +2,7 @@
 import json, sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
-from effective_model_learning_b200 import BatchedChains, configs, synthetic
+from effective_model_learning_b200 import BatchedChains, configs, definitions, synthetic
 OBS3 = ['sigmax', 'sigmay', 'sigmaz']
 cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
 ts = np.linspace(0, 2.5, 200)
@@ -13,7 +13,8 @@ for D, C, steps in SHAPES:
     ctx = lay.context(ts, OBS3)
     ex, _ = ctx.evaluate(lay.random_params(np.random.default_rng(20260000 + 10 + D))[None], want_expect=True)
     targets = ex[0].real + np.random.default_rng(1).normal(0, 0.01, (3, 200))
-    eng = BatchedChains(ts, targets, OBS3, n_chains=C, n_defects=D, seed=5, initial_params=lay.batch_params(1000 + np.arange(C)), **cfg)
+    eng = BatchedChains(ts, targets, OBS3, n_chains=C, n_defects=D, seed=5, initial_params=lay.batch_params(1000 + np.arange(C)),
+                        defect_initial_state=definitions.ops['mm'], **cfg)
     eng.run(5)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -2,7 +2,7 @@
 import sys, time
 import numpy as np
 sys.path.insert(0, '.')
-from effective_model_learning_b200 import BatchedChains, configs, synthetic
+from effective_model_learning_b200 import BatchedChains, configs, definitions, synthetic
 OBS3 = ['sigmax', 'sigmay', 'sigmaz']
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
@@ -15,7 +15,7 @@ truth = lay.random_params(np.random.default_rng(20260000 + 10 + D), p_present=0.
 ctx = lay.context(ts, OBS3)
 ex, _ = ctx.evaluate(truth[None], want_expect=True)
 targets = ex[0].real + np.random.default_rng(1).normal(0, 0.01, (3, 200))
-eng = BatchedChains(ts, targets, OBS3, n_chains=C, n_defects=D, seed=11, **cfg)
+eng = BatchedChains(ts, targets, OBS3, n_chains=C, n_defects=D, seed=11, defect_initial_state=definitions.ops['mm'], **cfg)
 t0 = time.time()
 for chunk in range(5):
     eng.run(steps // 5)

@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 sys.path.insert(0, '.')
-from effective_model_learning_b200 import _native, configs, synthetic, BatchedChains
+from effective_model_learning_b200 import _native, configs, definitions, synthetic, BatchedChains
 
 OBS3 = ['sigmax', 'sigmay', 'sigmaz']
 hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
@@ -16,7 +16,7 @@ for Q, D, kernel, B in ((1, 1, _native.KERNEL_AUTO, 5), (1, 2, _native.KERNEL_AU
     print(Q, D, ctx.plan.kernel_name, float(loss.sum()))
 cfg = dict(hyper)
 cfg['shock_anneal_at'] = 2
-eng = BatchedChains(ts, np.zeros((3, len(ts))), OBS3, n_chains=8, n_defects=3, seed=1, **cfg)
+eng = BatchedChains(ts, np.zeros((3, len(ts))), OBS3, n_chains=8, n_defects=3, seed=1, defect_initial_state=definitions.ops['mm'], **cfg)
 eng.run(4)
 print(eng.read()['stats'][:, :2].sum())
 eng.close()
