@@ -23,7 +23,7 @@ FLAG_NO_SECTOR_REDUCTION = 1     # EmlOptions.reserved bit 0: evolve the whole d
 
 # every symbol include/eml_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ('eml_version', 'eml_last_error_string', 'eml_device_count', 'eml_plan_create', 'eml_plan_destroy',
-           'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count', 'eml_debug_phase_clocks', 'eml_set_order_pack_mode', 'eml_predict_applications',
+           'eml_plan_set_targets', 'eml_eval_batch', 'eml_eval_batch_host', 'eml_launch_count', 'eml_debug_phase_clocks',
            'eml_plan_kernel_name', 'eml_measure_fp64_peak', 'eml_chains_create', 'eml_chains_destroy',
            'eml_chains_run', 'eml_chains_read', 'eml_chains_stats_device', 'eml_chains_bad_evaluations', 'eml_chains_state_bytes',
            'eml_chains_export', 'eml_chains_import')
@@ -84,9 +84,6 @@ def load():
         lib.eml_eval_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp]
         lib.eml_eval_batch_host.argtypes = [vp, C.c_int64, dp, ip, dp, dp]
         lib.eml_launch_count.restype = C.c_int64
-        lib.eml_set_order_pack_mode.argtypes = [C.c_int]
-        lib.eml_set_order_pack_mode.restype = None
-        lib.eml_predict_applications.argtypes = [vp, C.c_int64, vp, vp, vp]
         lib.eml_plan_kernel_name.argtypes = [vp]
         lib.eml_plan_kernel_name.restype = C.c_char_p
         lib.eml_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, dp]
@@ -128,11 +125,6 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(load().eml_launch_count())
-
-
-def set_order_pack_mode(mode: int) -> None:
-    """0 longest-first model list, 1 packed list for cold batches, 2 also for the chain engine; -1 = build default."""
-    load().eml_set_order_pack_mode(C.c_int(int(mode)))
 
 
 def measure_fp64_peak(device: int = 0, use_mma=False, seconds: float = 0.5) -> float:
@@ -239,12 +231,6 @@ class Plan:
                                       C.c_void_p(expect_ptr or None), C.c_void_p(loss_ptr or None),
                                       C.c_void_p(status_ptr or None), C.c_void_p(stream or None))
         check(rc, 'eml_eval_batch')
-
-    def predict_applications_device(self, n_models, params_ptr, out_ptr, stream=0):
-        """Diagnostic (d = 16 Chebyshev kernel, real H): predicted generator applications per model into a float32 device array."""
-        rc = self._lib.eml_predict_applications(self._h, int(n_models), C.c_void_p(params_ptr), C.c_void_p(out_ptr),
-                                                C.c_void_p(stream or None))
-        check(rc, 'eml_predict_applications')
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:

@@ -15,7 +15,8 @@ cudaError_t launch_generic(const DevProblem& P, long long n_models, const double
 size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h, bool chebyshev,
-                            bool parity_h, bool sector_b, const int* cost_hint, cudaStream_t stream);
+                            bool parity_h, bool sector_b, const int* cost_hint, double* prep_ws, long long prep_cap, cudaStream_t stream);
+size_t warp_prep_bytes_per_model(const DevProblem& P, bool real_h, bool chebyshev, bool parity_h, bool sector_b);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
@@ -23,10 +24,7 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
-void set_order_pack_mode(int mode);
 cudaError_t read_phase_clocks(unsigned long long* out, bool reset);
-cudaError_t warp_predicted_applications(const DevProblem& P, bool sector, long long n_models, const double* params, float* out,
-                                        cudaStream_t stream);
 }  // namespace eml
 
 #include "eml_plan.hpp"
@@ -66,7 +64,6 @@ int eml_debug_phase_clocks(uint64_t* out8, int reset) {
     for (int i = 0; i < 8; ++i) out8[i] = tmp[i];
     return EML_OK;
 }
-void eml_set_order_pack_mode(int mode) { eml::set_order_pack_mode(mode); }
 
 int eml_device_count(int* count) {
     if (!count) return fail(EML_ERR_INVALID_ARGUMENT, "count is NULL");
@@ -83,6 +80,7 @@ int eml_plan_destroy(EmlPlan* plan) {
     cudaSetDevice(plan->device);
     for (void* p : plan->owned) cudaFree(p);
     if (plan->d_targets) cudaFree(plan->d_targets);
+    if (plan->d_prep) cudaFree(plan->d_prep);
     cudaFree(plan->d_params); cudaFree(plan->d_expect); cudaFree(plan->d_loss); cudaFree(plan->d_tset); cudaFree(plan->d_status);
     cudaFreeHost(plan->h_params); cudaFreeHost(plan->h_expect); cudaFreeHost(plan->h_loss); cudaFreeHost(plan->h_tset); cudaFreeHost(plan->h_status);
     if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -302,12 +300,36 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
 
 }  // extern "C"
 
+// bytes of prepare-kernel workspace one model needs under this plan (0: the plan's kernel has no prepare pass)
+size_t eml_plan_prep_bytes_per_model(const EmlPlan* plan) {
+    if (!plan || plan->kernel != EML_KERNEL_WARP_CHEB) return 0;
+    return eml::warp_prep_bytes_per_model(plan->Pw, plan->real_h, true, plan->parity_h, plan->sector_b);
+}
+
+// The plan's own prepare workspace grows to the largest batch seen (capped; larger batches run in chunks): the first call
+// with a larger batch than any before pays one cudaMalloc, steady-state calls allocate nothing.
+static const long long kPrepMaxModels = 1 << 16;
+static int ensure_prep(EmlPlan* plan, long long n_models) {
+    const size_t per = eml_plan_prep_bytes_per_model(plan);
+    if (per == 0) return EML_OK;
+    long long want = n_models < 1024 ? 1024 : n_models;
+    if (want > kPrepMaxModels) want = kPrepMaxModels;
+    if (want <= plan->prep_cap) return EML_OK;
+    if (plan->d_prep) { EML_CUDA(cudaFree(plan->d_prep)); plan->d_prep = nullptr; plan->prep_cap = 0; }   // cudaFree waits for work in flight
+    void* p = nullptr;
+    EML_CUDA(cudaMalloc(&p, per * (size_t)want));
+    plan->d_prep = (double*)p;
+    plan->prep_cap = want;
+    return EML_OK;
+}
+
 // internal entry point: eml_eval_batch plus an optional measured cost per model for the longest-first ordering
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                           double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,
-                          int* order_ws) {
-    // counter_ws / order_ws: caller-owned work-fetch counter and ordering buffer (2 * 2^18 ints), so that several
-    // evaluations of one plan can be in flight on different streams; NULL = the plan's own
+                          int* order_ws, double* prep_ws, long long prep_cap) {
+    // counter_ws / order_ws / prep_ws: caller-owned work-fetch counter, ordering buffer (2 * 2^18 ints) and prepare
+    // workspace (prep_cap models x eml_plan_prep_bytes_per_model), so that several evaluations of one plan can be in
+    // flight on different streams; NULL = the plan's own
     if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
     unsigned int* const counter = counter_ws ? counter_ws : plan->d_counter;
     int* const order = counter_ws ? order_ws : plan->d_order;
@@ -318,10 +340,16 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     int cur = -1;
     EML_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
+    if (plan->kernel == EML_KERNEL_WARP_CHEB && !counter_ws) {
+        const int rc = ensure_prep(plan, n_models);
+        if (rc != EML_OK) { if (cur != plan->device && cur >= 0) cudaSetDevice(cur); return rc; }
+        prep_ws = plan->d_prep; prep_cap = plan->prep_cap;
+    }
     cudaError_t e;
     if (plan->kernel == EML_KERNEL_WARP_MMA || plan->kernel == EML_KERNEL_WARP_CHEB)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
-                                 plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, plan->sector_b, cost_hint, (cudaStream_t)stream);
+                                 plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, plan->sector_b, cost_hint, prep_ws, prep_cap,
+                                 (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
                                 plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
@@ -337,7 +365,7 @@ extern "C" {
 
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                    double* loss, int32_t* status, void* stream) {
-    return eml_eval_batch_hinted(plan, n_models, params, target_set, expect, loss, status, stream, nullptr, nullptr, nullptr);
+    return eml_eval_batch_hinted(plan, n_models, params, target_set, expect, loss, status, stream, nullptr, nullptr, nullptr, nullptr, 0);
 }
 
 }  // extern "C"
@@ -423,23 +451,6 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     for (long long i = 0; i < n_models; ++i)
         if (plan->h_status[i] < 0)
             return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " did not converge (series cap or non-finite generator)");
-    return EML_OK;
-}
-
-int eml_predict_applications(EmlPlan* plan, int64_t n_models, const double* params, float* applications, void* stream) {
-    if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
-    if (n_models < 0 || n_models > 0x7fffffffLL) return fail(EML_ERR_INVALID_ARGUMENT, "n_models out of range");
-    if (n_models == 0) return EML_OK;
-    if (!params || !applications) return fail(EML_ERR_INVALID_ARGUMENT, "params / applications is NULL");
-    if (plan->kernel != EML_KERNEL_WARP_CHEB || plan->Pw.n_tls != 4 || !plan->real_h)
-        return fail(EML_ERR_UNSUPPORTED, "predicted application counts exist for the d = 16 Chebyshev kernel with a real Hamiltonian");
-    int cur = -1;
-    EML_CUDA(cudaGetDevice(&cur));
-    if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
-    const cudaError_t e = eml::warp_predicted_applications(plan->Pw, plan->parity_h && plan->sector_b, n_models, params, applications,
-                                                           (cudaStream_t)stream);
-    if (cur != plan->device && cur >= 0) cudaSetDevice(cur);
-    if (e != cudaSuccess) return fail(EML_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return EML_OK;
 }
 

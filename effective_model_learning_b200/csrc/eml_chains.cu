@@ -335,6 +335,7 @@ struct EmlChains {
     cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {};
     unsigned int* g_counter[MAX_GROUPS] = {};
     int* g_order[MAX_GROUPS] = {};
+    double* g_prep[MAX_GROUPS] = {};     // prepare-kernel workspace of each group (its own: the groups run concurrently)
 };
 
 template <typename T>
@@ -440,6 +441,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
         ch->group_hi[g] = (g + 1) * n_chains / ch->n_groups;
         CH_TRY(dalloc(ch, &ch->g_counter[g], 1));
         CH_TRY(dalloc(ch, &ch->g_order[g], (size_t)2 * (1 << 18)));
+        CH_TRY(dalloc(ch, &ch->g_prep[g], eml_plan_prep_bytes_per_model(plan) / sizeof(double) * (size_t)(ch->group_hi[g] - ch->group_lo[g])));
         if (cudaStreamCreateWithFlags(&ch->gstream[g], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ch->join[g], cudaEventDisableTiming) != cudaSuccess) {
             eml_chains_destroy(ch);
@@ -475,7 +477,7 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
             // the generator applications each chain's previous proposal needed order this step's models (longest first)
             int rc = eml_eval_batch_hinted(ch->plan, cnt, ch->S.prop + lo * P, ch->d_target_set ? ch->d_target_set + lo : nullptr,
                                            nullptr, ch->S.prop_loss + lo, ch->d_status + lo, gs, ch->d_status + lo,
-                                           ch->g_counter[g], ch->g_order[g]);
+                                           ch->g_counter[g], ch->g_order[g], ch->g_prep[g], cnt);
             if (rc != EML_OK) return rc;
             eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
                                                              hist_loss ? hist_loss + i * ch->n : nullptr,

@@ -38,8 +38,11 @@ struct EmlPlan {
     size_t targets_bytes = 0;
     unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
     int* d_order = nullptr;             // LPT model order (capacity 2^18 models) followed by the float cost scratch
+    double* d_prep = nullptr;           // records of the prepare kernel (Chebyshev warp kernels), prep_cap models
+    long long prep_cap = 0;
 };
 
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                           double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,
-                          int* order_ws);
+                          int* order_ws, double* prep_ws, long long prep_cap);
+size_t eml_plan_prep_bytes_per_model(const EmlPlan* plan);

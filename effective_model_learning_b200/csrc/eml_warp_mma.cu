@@ -75,7 +75,10 @@ constexpr int MAXP = 128;       // parameter-vector cap for this kernel
 constexpr int CHEB_KCAP_TL2 = EML_CHEB_KCAP_TL2, CHEB_KCAP_TL1 = 256;
 constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
 #ifndef EML_CHEB_KCAP_SB
-#define EML_CHEB_KCAP_SB 396
+#define EML_CHEB_KCAP_SB 488
+#endif
+#ifndef EML_OUTPUT_CHAINS
+#define EML_OUTPUT_CHAINS 1        // output times per lane and pass of the Bessel-weighted sums (measured: 2 chains +-0, 4 chains -6 %, 8 chains -22 %: the phase is bound by the FP64 pipe it shares with the recurrences of the other warps, not by the latency of its dependent FMA chain)
 #endif
 #ifndef EML_WARPS_PER_SM_SB
 #define EML_WARPS_PER_SM_SB 16
@@ -84,13 +87,14 @@ constexpr int CHEB_KCAP_SB = EML_CHEB_KCAP_SB;      // sector variant: 16 warps 
 constexpr int WARPS_PER_SM_SB = EML_WARPS_PER_SM_SB;
 static_assert(WARPS_PER_SM_SB % EML_WARPS_PER_CTA == 0, "resident warps per SM must be a whole number of CTAs");
 
+// Per-warp shared memory.  The Taylor variants assemble the generator themselves (G, parameters, norm-bound scratch);
+// the Chebyshev variants receive it from the prepare kernel and keep the trace table, the coefficient table of a
+// non-final macro step and the transposition tile instead.
 template <int TL, bool CHEB, bool SB = false>
-struct alignas(16) WarpScratch {
-    static constexpr int D = 8 * TL;
-    static constexpr int KCAP = CHEB ? (TL == 2 ? (SB ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1) : 0;
-    static constexpr int NTR = SB ? 2 : 4;      // partial-trace values kept per term
-    // G_re, G_im, par are contiguous: dead once the A fragments are in registers, the Chebyshev path reuses them
-    // for the coefficient table of the step end (KCAP + 1 <= 2 D (D + 1) + MAXP doubles)
+struct alignas(16) WarpScratch;
+template <int TL>
+struct alignas(16) WarpScratch<TL, false, false> {
+    static constexpr int D = 8 * TL, KCAP = 0, NTR = 4;
     double G_re[D][D + 1];
     double G_im[D][D + 1];
     double par[MAXP];
@@ -99,13 +103,39 @@ struct alignas(16) WarpScratch {
     double colsum[16];
     double misc[4];
     static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
-    // SB: one 8 x 8 complex tile, (re, im) interleaved, two buffers (256 doubles in xt_re; xt_im unused)
+    alignas(16) double xt_re[XT];
+    alignas(16) double xt_im[XT];   // X' staged column-major (swizzled) for the conjugate transpose
+    alignas(16) double tr[4];
+};
+template <int TL, bool SB>
+struct alignas(16) WarpScratch<TL, true, SB> {
+    static constexpr int D = 8 * TL;
+    static constexpr int KCAP = TL == 2 ? (SB ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1;
+    static constexpr int NTR = SB ? 2 : 4;      // partial-trace values kept per term
+    double jw[32];      // [bitpos][type(0 diag,1 flip)][ra][ca]          (from the prepare kernel's record)
+    double gdiag[16];   // real H: diagonal of G.re = -1/2 sum c^dag c     (contiguous with plan: one record read)
+    double plan[4];     // R, S, ac, tau_max
+    double half_tr[2];  // sector variant: Tr(rho0) / 2 (rho00 = rho11 of the observed site never move)
+    static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
+    // SB: one 8 x 8 complex tile, planes re | im of 64 doubles, two buffers (256 doubles in xt_re; xt_im unused)
     alignas(16) double xt_re[XT];
     alignas(16) double xt_im[SB ? 2 : XT];   // X' staged column-major (swizzled) for the conjugate transpose
-    alignas(16) double tr[(KCAP + 1) * NTR];                      // partial traces of the Chebyshev terms
+    double cj[KCAP + 2];                     // Bessel coefficients of the step end (non-final macro steps only)
+    alignas(16) double tr[(KCAP + 4) * NTR]; // partial traces of the Chebyshev terms (+3 zero entries: groups of four)
 };
-static_assert(CHEB_KCAP_TL2 + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_SB + 1 <= 2 * 16 * 17 + MAXP && CHEB_KCAP_TL1 + 1 <= 2 * 8 * 9 + MAXP, "coefficient table alias");
-static_assert((CHEB_KCAP_SB + 1) * 2 >= 2 * 16 * 16, "the trace table doubles as scratch for the spread bound");
+// The prepare kernel's per-warp scratch: generator, parameters, and the two matrices of the spread-bound squarings.
+template <int TL, bool REAL_H>
+struct alignas(16) PrepScratch {
+    static constexpr int D = 8 * TL;
+    double G_re[D][D + 1];
+    double G_im[D][D + 1];
+    double par[MAXP];
+    double jw[32];
+    double kd[8];
+    double colsum[16];
+    double misc[4];
+    alignas(16) double mat[(REAL_H ? 2 : 4) * D * D];
+};
 
 // Phase clocks (profiling builds only, -DEML_PROFILE_PHASES): warp-cycles spent in set-up, recurrence, outputs, epilogue,
 // summed over all warps, plus the cycles between a warp's last model and the end of the launch are NOT included.
@@ -213,13 +243,246 @@ __global__ void __launch_bounds__(1024) order_models_kernel(const int n_models, 
     }
 }
 
+// ---- K1 (reference basic_model.py:152-255): G = -iH - 1/2 sum c^dag c of one model into shared memory (lane r < D owns row r),
+//      the real jump weights jw (one entry per lane) and, for the Chebyshev enclosure, the diagonal of sum rate * A^dag A per
+//      site; returns the norm bound  nu >= ||L||_1.  Shared by the prepare kernel and the Taylor evaluators.
+template <int TL, bool WANT_KD, class SC>
+__device__ __forceinline__ double assemble_generator(SC& S, const DevProblem& P, const double* __restrict__ prow, const int lane) {
+    constexpr int N = 2 + TL, D = 8 * TL;
+    const int obs_site = P.obs_site;
+    auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
+    // ---- parameters, clear G
+    for (int i = lane; i < P.n_params; i += 32) S.par[i] = prow[i];
+    for (int i = lane; i < D * (D + 1); i += 32) { (&S.G_re[0][0])[i] = 0.0; (&S.G_im[0][0])[i] = 0.0; }
+    __syncwarp();
+
+    // ---- K1: assemble G (lane r < 16 owns row r) and the real jump weights (one entry per lane)
+    if (lane < D) {
+        const int r = lane;
+        for (int ti = 0; ti < P.n_terms; ++ti) {
+            const EmlTerm tm = P.terms[ti];
+            const double v = S.par[tm.param];
+            if (v == 0.0) continue;
+            const int sa = pos(tm.site_a);
+            const int ra = (r >> sa) & 1;
+            if (tm.kind == EML_TERM_ENERGY) {
+                for (int a = 0; a < 2; ++a) {
+                    const cplx A = ld_op(P.op_table, tm.op_a, ra, a);
+                    const int c = (r & ~(1 << sa)) | (a << sa);
+                    S.G_re[r][c] += v * A.im;        // -i h
+                    S.G_im[r][c] -= v * A.re;
+                }
+            } else if (tm.kind == EML_TERM_COUPLING) {
+                const int sb = pos(tm.site_b);
+                const int rb = (r >> sb) & 1;
+                const double v2 = v * v;
+                for (int a = 0; a < 2; ++a)
+                    for (int bb = 0; bb < 2; ++bb) {
+                        const cplx AB = cmul(ld_op(P.op_table, tm.op_a, ra, a), ld_op(P.op_table, tm.op_b, rb, bb));
+                        const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
+                        S.G_re[r][c] += v2 * AB.im;
+                        S.G_im[r][c] -= v2 * AB.re;
+                    }
+            } else {
+                for (int a = 0; a < 2; ++a) {
+                    cplx M = {0.0, 0.0};
+                    for (int z = 0; z < 2; ++z) {
+                        const cplx m = cmul(cconj(ld_op(P.op_table, tm.op_a, z, ra)), ld_op(P.op_table, tm.op_a, z, a));
+                        M.re += m.re; M.im += m.im;
+                    }
+                    const int c = (r & ~(1 << sa)) | (a << sa);
+                    S.G_re[r][c] -= 0.5 * v * M.re;
+                    S.G_im[r][c] -= 0.5 * v * M.im;
+                }
+            }
+        }
+    }
+    {
+        const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
+        const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
+        // the lanes (type 0, ca 0) also collect the diagonal of sum rate * A^dag A of their site and row bit (the
+        // anticommutator part of the site generator, needed by the Chebyshev enclosure)
+        const bool kd_lane = WANT_KD && type == 0 && ca == 0;
+        double w = 0.0, kdv = 0.0;
+        for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
+            const EmlTerm tm = P.terms[ti];
+            if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
+            const double v = S.par[tm.param];
+            if (v == 0.0) continue;
+            const cplx x = cmul(ld_op(P.op_table, tm.op_a, ra, a), cconj(ld_op(P.op_table, tm.op_a, ca, bb)));
+            w += v * x.re;
+            if (kd_lane) {
+                const cplx m0 = ld_op(P.op_table, tm.op_a, 0, ra), m1 = ld_op(P.op_table, tm.op_a, 1, ra);
+                kdv += v * ((m0.re * m0.re + m0.im * m0.im) + (m1.re * m1.re + m1.im * m1.im));
+            }
+        }
+        S.jw[lane] = w;
+        if (kd_lane) S.kd[bp * 2 + ra] = kdv;
+    }
+    __syncwarp();
+
+    // ---- norm bound: 2 * max column sum |G| (G^dag supplies the row-sum term) + sum_s ||S_s||_1
+    if (lane < D) {
+        double cs = 0.0;
+        for (int i = 0; i < D; ++i) cs += hypot(S.G_re[i][lane], S.G_im[i][lane]);
+        S.colsum[lane] = cs;   // vec(rho G^dag) = (conj(G) (x) I) vec(rho) has the same 1-norm: factor 2 below
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double mc = 0.0;
+        double poison = 0.0;     // fmax drops NaNs: carry them into nu explicitly
+        for (int i = 0; i < D; ++i) { mc = fmax(mc, S.colsum[i]); poison += S.colsum[i]; }
+        double nu = 2.0 * mc + 0.0 * poison;
+        for (int bp = 0; bp < N; ++bp) {
+            double best = 0.0;
+            for (int a = 0; a < 2; ++a)
+                for (int bb = 0; bb < 2; ++bb)
+                    best = fmax(best, fabs(S.jw[bp * 8 + a * 2 + bb]) + fabs(S.jw[bp * 8 + 4 + (1 - a) * 2 + (1 - bb)]));
+            nu += best;
+        }
+        S.misc[0] = nu;
+    }
+    __syncwarp();
+    return S.misc[0];
+}
+
+// ---- prepare kernel (Chebyshev variants): one warp per model, high occupancy.  Assembles the generator, bounds its spectrum
+//      (Gershgorin and 2 ||(H - mean diag)^8||_1^(1/8) for the commutator, per-site ranges for the dissipator), chooses the
+//      Chebyshev plan and writes ONE RECORD per model for the evaluator:
+//        [NA][32]  A fragments of G per lane (im plane, then re plane for a complex H), k index permuted as the evaluator
+//                  multiplies them;  [32] jw;  [16] diagonal of G.re;  [4] R, S, ac, tau_max  (R = NaN: not evaluable)
+//      and the number of generator applications the evaluation will need (exact for a single macro step) -- the cost the
+//      persistent warps of the evaluator are ordered by.
+template <int TL, bool REAL_H, bool PARITY>
+__host__ __device__ constexpr int prep_fragments() { return (REAL_H ? 1 : 2) * TL * (PARITY ? 2 : 2 * TL); }
+template <int TL, bool REAL_H, bool PARITY>
+__host__ __device__ constexpr int prep_record_doubles() { return prep_fragments<TL, REAL_H, PARITY>() * 32 + 32 + 16 + 4; }
+constexpr int PREP_WARPS = 4;
+
+template <int TL, bool REAL_H, bool PARITY>
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+prepare_models_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params, double* __restrict__ rec,
+                      float* __restrict__ cost, const double cheb_zcap, const int kcap) {
+    constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL, KSE = PARITY ? 2 : KS;
+    constexpr int NA = prep_fragments<TL, REAL_H, PARITY>(), REC = prep_record_doubles<TL, REAL_H, PARITY>();
+    auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Scratch = PrepScratch<TL, REAL_H>;
+    Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const long long b = (long long)blockIdx.x * PREP_WARPS + (threadIdx.x >> 5);
+    if (b >= n_models) return;
+    double* const R = rec + (size_t)b * REC;
+    const int T = P.n_times;
+    const double span = P.times[T - 1] - P.times[0];
+    const double nu = assemble_generator<TL, true>(S, P, params + b * P.n_params, lane);
+    // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
+    if (!(nu * span < 1e5)) {
+        if (lane < 4) R[NA * 32 + 48 + lane] = nan("");
+        if (lane == 0 && cost != nullptr) cost[b] = 0.f;
+        return;
+    }
+    // ---- record: A fragments with the permuted k index (PARITY: only the diagonal tiles, kept in ks = 0, 1), weights
+#pragma unroll
+    for (int I = 0; I < TL; ++I)
+#pragma unroll
+        for (int ks = 0; ks < KSE; ++ks) {
+            const int k = PARITY ? 8 * I + 2 * t + (ks & 1) : 8 * (ks >> 1) + 2 * t + (ks & 1);
+            R[((0 * TL + I) * KSE + ks) * 32 + lane] = S.G_im[phys(8 * I + g)][phys(k)];
+            if (!REAL_H) R[((1 * TL + I) * KSE + ks) * 32 + lane] = S.G_re[phys(8 * I + g)][phys(k)];
+        }
+    R[NA * 32 + lane] = S.jw[lane];
+    if (lane < 16) R[NA * 32 + 32 + lane] = (lane < D) ? S.G_re[lane][lane] : 0.0;
+    // ---- spectral enclosure
+    double spread, dlo, dhi, dasym;
+    {
+        double hi = -1e300, lo = 1e300;
+        if (lane < D) {
+            double rad = 0.0;
+            for (int c = 0; c < D; ++c)
+                if (c != lane) rad += REAL_H ? fabs(S.G_im[lane][c]) : hypot(S.G_re[lane][c], S.G_im[lane][c]);
+            const double ctr = -S.G_im[lane][lane];
+            hi = ctr + rad; lo = ctr - rad;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        }
+        spread = hi - lo;
+        // Gershgorin overestimates the spread by ~1.5x at d = 16; the spectral radius of Hc = H - mean(diag) is bounded far
+        // more tightly by ||Hc^8||_1^(1/8) (three squarings): lambda_max - lambda_min <= 2 rho(Hc), measured 1.09x the true
+        // spread on the benchmark library.
+        double mu = (lane < D) ? -S.G_im[lane][lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        mu *= 1.0 / D;
+        double* Ma = S.mat;                                   // [re | im] planes of D x D (real H: re only)
+        double* Mb = S.mat + (REAL_H ? 1 : 2) * D * D;
+        for (int i = lane; i < D * D; i += 32) {
+            const int r = i / D, c = i % D;
+            Ma[i] = -S.G_im[r][c] - ((r == c) ? mu : 0.0);
+            if (!REAL_H) Ma[D * D + i] = (r == c) ? 0.0 : S.G_re[r][c];
+        }
+        __syncwarp();
+        for (int sq = 0; sq < 3; ++sq) {
+            if constexpr (REAL_H) {
+                // real symmetric D x D squaring on the DMMA pipe: fragments straight from shared memory
+#pragma unroll
+                for (int I = 0; I < TL; ++I)
+#pragma unroll
+                    for (int J = 0; J < TL; ++J) {
+                        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks)
+                            dmma(d0, d1, Ma[(8 * I + g) * D + 4 * ks + t], Ma[(4 * ks + t) * D + 8 * J + g]);
+                        *reinterpret_cast<double2*>(&Mb[(8 * I + g) * D + 8 * J + 2 * t]) = make_double2(d0, d1);
+                    }
+            } else
+            for (int i = lane; i < D * D; i += 32) {
+                const int r = i / D, c = i % D;
+                double sre = 0.0, sim = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < D; ++k) {
+                    const double are = Ma[r * D + k], bre = Ma[k * D + c];
+                    const double aim = Ma[D * D + r * D + k], bim = Ma[D * D + k * D + c];
+                    sre = fma(are, bre, fma(-aim, bim, sre));
+                    sim = fma(are, bim, fma(aim, bre, sim));
+                }
+                Mb[i] = sre;
+                Mb[D * D + i] = sim;
+            }
+            __syncwarp();
+            double* tmp = Ma; Ma = Mb; Mb = tmp;
+        }
+        double cs = 0.0;
+        if (lane < D)
+            for (int r = 0; r < D; ++r)
+                cs += REAL_H ? fabs(Ma[r * D + lane]) : hypot(Ma[r * D + lane], Ma[D * D + r * D + lane]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
+        spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
+        cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
+    }
+    const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, span, cheb_zcap, kcap);
+    if (lane == 0) {
+        R[NA * 32 + 48] = plan.R; R[NA * 32 + 49] = plan.S; R[NA * 32 + 50] = plan.ac; R[NA * 32 + 51] = plan.tau_max;
+        if (cost != nullptr) {
+            // generator applications: one macro step when the span fits (exact), else about span / tau_max full steps
+            const double steps = ceil(span / plan.tau_max);
+            const int k1 = min(cheb_terms(fmin(span, plan.tau_max) * plan.S), kcap);
+            cost[b] = (float)(fmax(steps, 1.0) * (double)k1);
+        }
+    }
+}
+
 template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
 // resident warps per SM: 16 (d = 8), 16 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM is quoted for four-warp CTAs
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (SB ? WARPS_PER_SM_SB : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
-                     const double cheb_zcap) {
+                     const double* __restrict__ prep) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
     static_assert(!PARITY || (CHEB && TL == 2), "the parity-blocked variant exists for the d = 16 Chebyshev kernel");
@@ -278,121 +541,57 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         if (UNI((long long)bidx >= n_models)) break;
         const long long b = (order != nullptr) ? order[bidx] : bidx;
 
-        // ---- parameters, clear G
-        for (int i = lane; i < P.n_params; i += 32) S.par[i] = params[b * P.n_params + i];
-        for (int i = lane; i < D * (D + 1); i += 32) { (&S.G_re[0][0])[i] = 0.0; (&S.G_im[0][0])[i] = 0.0; }
-        __syncwarp();
-
-        // ---- K1: assemble G (lane r < 16 owns row r) and the real jump weights (one entry per lane)
-        if (lane < D) {
-            const int r = lane;
-            for (int ti = 0; ti < P.n_terms; ++ti) {
-                const EmlTerm tm = P.terms[ti];
-                const double v = S.par[tm.param];
-                if (v == 0.0) continue;
-                const int sa = pos(tm.site_a);
-                const int ra = (r >> sa) & 1;
-                if (tm.kind == EML_TERM_ENERGY) {
-                    for (int a = 0; a < 2; ++a) {
-                        const cplx A = ld_op(P.op_table, tm.op_a, ra, a);
-                        const int c = (r & ~(1 << sa)) | (a << sa);
-                        S.G_re[r][c] += v * A.im;        // -i h
-                        S.G_im[r][c] -= v * A.re;
-                    }
-                } else if (tm.kind == EML_TERM_COUPLING) {
-                    const int sb = pos(tm.site_b);
-                    const int rb = (r >> sb) & 1;
-                    const double v2 = v * v;
-                    for (int a = 0; a < 2; ++a)
-                        for (int bb = 0; bb < 2; ++bb) {
-                            const cplx AB = cmul(ld_op(P.op_table, tm.op_a, ra, a), ld_op(P.op_table, tm.op_b, rb, bb));
-                            const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
-                            S.G_re[r][c] += v2 * AB.im;
-                            S.G_im[r][c] -= v2 * AB.re;
-                        }
-                } else {
-                    for (int a = 0; a < 2; ++a) {
-                        cplx M = {0.0, 0.0};
-                        for (int z = 0; z < 2; ++z) {
-                            const cplx m = cmul(cconj(ld_op(P.op_table, tm.op_a, z, ra)), ld_op(P.op_table, tm.op_a, z, a));
-                            M.re += m.re; M.im += m.im;
-                        }
-                        const int c = (r & ~(1 << sa)) | (a << sa);
-                        S.G_re[r][c] -= 0.5 * v * M.re;
-                        S.G_im[r][c] -= 0.5 * v * M.im;
-                    }
+        double a_re[TL][KS], a_im[TL][KS];
+        if constexpr (CHEB) {
+            // ---- the prepare kernel's record of this model: A fragments (coalesced), weights and plan through shared memory
+            constexpr int KSE = PARITY ? 2 : KS;
+            constexpr int NA = prep_fragments<TL, REAL_H, PARITY>(), REC = prep_record_doubles<TL, REAL_H, PARITY>();
+            const double* const R = prep + (size_t)b * REC;
+#pragma unroll
+            for (int I = 0; I < TL; ++I)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    a_im[I][ks] = (ks < KSE) ? R[((0 * TL + I) * KSE + ks) * 32 + lane] : 0.0;
+                    a_re[I][ks] = (!REAL_H && ks < KSE) ? R[((1 * TL + I) * KSE + ks) * 32 + lane] : 0.0;
                 }
-            }
-        }
-        {
-            const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
-            const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
-            // the lanes (type 0, ca 0) also collect the diagonal of sum rate * A^dag A of their site and row bit (the
-            // anticommutator part of the site generator, needed by the Chebyshev enclosure)
-            const bool kd_lane = CHEB && type == 0 && ca == 0;
-            double w = 0.0, kdv = 0.0;
-            for (int ti = 0; ti < P.n_terms && bp < N; ++ti) {
-                const EmlTerm tm = P.terms[ti];
-                if (tm.kind != EML_TERM_LINDBLAD || pos(tm.site_a) != bp) continue;
-                const double v = S.par[tm.param];
-                if (v == 0.0) continue;
-                const cplx x = cmul(ld_op(P.op_table, tm.op_a, ra, a), cconj(ld_op(P.op_table, tm.op_a, ca, bb)));
-                w += v * x.re;
-                if (kd_lane) {
-                    const cplx m0 = ld_op(P.op_table, tm.op_a, 0, ra), m1 = ld_op(P.op_table, tm.op_a, 1, ra);
-                    kdv += v * ((m0.re * m0.re + m0.im * m0.im) + (m1.re * m1.re + m1.im * m1.im));
-                }
-            }
-            S.jw[lane] = w;
-            if (kd_lane) S.kd[bp * 2 + ra] = kdv;
-        }
-        __syncwarp();
-
-        // ---- norm bound: 2 * max column sum |G| (G^dag supplies the row-sum term) + sum_s ||S_s||_1
-        if (lane < D) {
-            double cs = 0.0;
-            for (int i = 0; i < D; ++i) cs += hypot(S.G_re[i][lane], S.G_im[i][lane]);
-            S.colsum[lane] = cs;   // vec(rho G^dag) = (conj(G) (x) I) vec(rho) has the same 1-norm: factor 2 below
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double mc = 0.0;
-            double poison = 0.0;     // fmax drops NaNs: carry them into nu explicitly
-            for (int i = 0; i < D; ++i) { mc = fmax(mc, S.colsum[i]); poison += S.colsum[i]; }
-            double nu = 2.0 * mc + 0.0 * poison;
-            for (int bp = 0; bp < N; ++bp) {
-                double best = 0.0;
-                for (int a = 0; a < 2; ++a)
-                    for (int bb = 0; bb < 2; ++bb)
-                        best = fmax(best, fabs(S.jw[bp * 8 + a * 2 + bb]) + fabs(S.jw[bp * 8 + 4 + (1 - a) * 2 + (1 - bb)]));
-                nu += best;
-            }
-            S.misc[0] = nu;
-        }
-        __syncwarp();
-        const double nu = S.misc[0];
-        // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
-        if (UNI(!(nu * (P.times[T - 1] - P.times[0]) < 1e5))) {
-            if (lane == 0) {
-                if (loss != nullptr) loss[b] = nan("");
-                if (status != nullptr) status[b] = -1;
-            }
+            S.jw[lane] = R[NA * 32 + lane];
+            if (lane < 20) S.gdiag[lane] = R[NA * 32 + 32 + lane];      // gdiag[16] and plan[4] are contiguous
             __syncwarp();
-            continue;
+            // not evaluable (non-finite parameters or an absurd step count): reported, not attempted
+            if (UNI(!(S.plan[0] == S.plan[0]))) {
+                if (lane == 0) {
+                    if (loss != nullptr) loss[b] = nan("");
+                    if (status != nullptr) status[b] = -1;
+                }
+                __syncwarp();
+                continue;
+            }
+        } else {
+            const double nu_ = assemble_generator<TL, false>(S, P, params + b * P.n_params, lane);
+            // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
+            if (UNI(!(nu_ * (P.times[T - 1] - P.times[0]) < 1e5))) {
+                if (lane == 0) {
+                    if (loss != nullptr) loss[b] = nan("");
+                    if (status != nullptr) status[b] = -1;
+                }
+                __syncwarp();
+                continue;
+            }
         }
-
+        [[maybe_unused]] double nu = 0.0;
+        if constexpr (!CHEB) nu = S.misc[0];
         // ---- A fragments of G with the permuted k index.  REAL_H: H is real, so G.re = -K/2 is diagonal and is
         //      folded into the diagonal stencil weight; only G.im = -H goes through the DMMA pipe.
-        double a_re[TL][KS], a_im[TL][KS];
+        if constexpr (!CHEB) {
 #pragma unroll
-        for (int I = 0; I < TL; ++I)
+            for (int I = 0; I < TL; ++I)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                // PARITY: only the diagonal tile K' = I is non-zero; it is kept in ks = 0, 1
-                const int k = PARITY ? 8 * I + 2 * t + (ks & 1) : 8 * (ks >> 1) + 2 * t + (ks & 1);
-                a_re[I][ks] = REAL_H ? 0.0 : S.G_re[phys(8 * I + g)][phys(k)];
-                a_im[I][ks] = S.G_im[phys(8 * I + g)][phys(k)];
-            }
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+                    a_re[I][ks] = REAL_H ? 0.0 : S.G_re[8 * I + g][k];
+                    a_im[I][ks] = S.G_im[8 * I + g][k];
+                }
+        }
         // Stencil weights are stored HALVED: the DMMA accumulators start from J(v)/2, so that
         // X' + X'^dag = G v + v G^dag + J(v)  (J(v) is Hermitian).
         double W0[TL][TL][2];
@@ -409,7 +608,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     double w = S.jw[2 * 8 + (g >> 2) * 2 + (t >> 1)] + S.jw[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] +
                                S.jw[0 * 8 + (g & 1) * 2 + e];
                     if (TL == 2) w += S.jw[3 * 8 + r3 * 2 + c3];
-                    if (REAL_H) w += S.G_re[row][row] + S.G_re[col][col];
+                    if constexpr (REAL_H) {
+                        if constexpr (CHEB) w += S.gdiag[row] + S.gdiag[col]; else w += S.G_re[row][row] + S.G_re[col][col];
+                    }
                     W0[I][J][e] = 0.5 * w;
                     if (e < FE) F3[I][J][e] = (TL == 2) ? 0.5 * S.jw[3 * 8 + 4 + r3 * 2 + c3] : 0.0;
                 }
@@ -728,88 +929,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // range: Gershgorin on H for the commutator, per-site Gershgorin for the dissipator (real range [dlo, dhi],
         // centred by the shift ac; antisymmetric part added to the imaginary extent); the series is truncated for
         // the confocal ellipse (semi-axes A along the imaginary axis, B real) through the corner of that rectangle.
-        double spread, dlo, dhi, dasym;
-        {
-            double hi = -1e300, lo = 1e300;
-            if (lane < D) {
-                double rad = 0.0;
-                for (int c = 0; c < D; ++c)
-                    if (c != lane) rad += REAL_H ? fabs(S.G_im[lane][c]) : hypot(S.G_re[lane][c], S.G_im[lane][c]);
-                const double ctr = -S.G_im[lane][lane];
-                hi = ctr + rad; lo = ctr - rad;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-                lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            }
-            spread = hi - lo;
-            {
-                // Gershgorin overestimates the spread by ~1.5x at d = 16; the spectral radius of Hc = H - mean(diag) is
-                // bounded far more tightly by ||Hc^8||_1^(1/8) (three squarings in the still-unused trace buffer):
-                // lambda_max - lambda_min <= 2 rho(Hc), measured 1.09x the true spread on the benchmark library.
-                double mu = (lane < D) ? -S.G_im[lane][lane] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
-                mu *= 1.0 / D;
-                double* Ma = S.tr;                                   // [re | im] planes of D x D
-                // second buffer: behind the first one when the trace table is large enough, else (sector variant: 16 warps
-                // per SM, small table) packed for a real H, or over G (dead once Ma is filled) for a complex H
-                constexpr bool ROOMY = (Scratch::KCAP + 1) * NTR >= 4 * D * D;
-                double* Mb = ROOMY ? S.tr + 2 * D * D : (REAL_H ? S.tr + D * D : &S.G_re[0][0]);
-                for (int i = lane; i < D * D; i += 32) {
-                    const int r = i / D, c = i % D;
-                    Ma[i] = -S.G_im[r][c] - ((r == c) ? mu : 0.0);
-                    if (!REAL_H) Ma[D * D + i] = (r == c) ? 0.0 : S.G_re[r][c];
-                }
-                __syncwarp();
-                for (int sq = 0; sq < 3; ++sq) {
-                    if constexpr (REAL_H) {
-                        // real symmetric D x D squaring on the DMMA pipe: fragments straight from shared memory
-#pragma unroll
-                        for (int I = 0; I < TL; ++I)
-#pragma unroll
-                            for (int J = 0; J < TL; ++J) {
-                                double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                                for (int ks = 0; ks < KS; ++ks)
-                                    dmma(d0, d1, Ma[(8 * I + g) * D + 4 * ks + t], Ma[(4 * ks + t) * D + 8 * J + g]);
-                                *reinterpret_cast<double2*>(&Mb[(8 * I + g) * D + 8 * J + 2 * t]) = make_double2(d0, d1);
-                            }
-                    } else
-                    for (int i = lane; i < D * D; i += 32) {
-                        const int r = i / D, c = i % D;
-                        double sre = 0.0, sim = 0.0;
-#pragma unroll 4
-                        for (int k = 0; k < D; ++k) {
-                            const double are = Ma[r * D + k], bre = Ma[k * D + c];
-                            sre = fma(are, bre, sre);
-                            if (!REAL_H) {
-                                const double aim = Ma[D * D + r * D + k], bim = Ma[D * D + k * D + c];
-                                sre = fma(-aim, bim, sre);
-                                sim = fma(are, bim, fma(aim, bre, sim));
-                            }
-                        }
-                        Mb[i] = sre;
-                        if (!REAL_H) Mb[D * D + i] = sim;
-                    }
-                    __syncwarp();
-                    double* tmp = Ma; Ma = Mb; Mb = tmp;
-                }
-                double cs = 0.0;
-                if (lane < D)
-                    for (int r = 0; r < D; ++r)
-                        cs += REAL_H ? fabs(Ma[r * D + lane]) : hypot(Ma[r * D + lane], Ma[D * D + r * D + lane]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
-                spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
-                __syncwarp();
-            }
-            cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
-        }
-        PHASE_MARK(0);      // assembly, norm bound, fragments, spread bound, site ranges
-        const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, P.times[T - 1] - P.times[0], cheb_zcap, Scratch::KCAP);
-        const double Rb = plan.R, Sb = plan.S, ac = plan.ac, tau_max = plan.tau_max;
+        PHASE_MARK(0);      // record of the prepare kernel, stencil weights, initial state
+        // the plan (R, S, ac, tau_max) and Tr(rho0)/2 stay in shared memory and are re-read where they are needed, so that
+        // none of them occupies registers across the recurrence loop
+#define Rb (S.plan[0])
+#define Sb (S.plan[1])
+#define ac (S.plan[2])
+#define tau_max (S.plan[3])
         {   // generator -> 2 (L + ac) / R  (stencil weights are stored halved)
             const double sc = 2.0 / Rb;
             const double sw = SB ? 2.0 * sc : sc;      // the sector variant applies J(v) in one piece: weights unhalved
@@ -876,16 +1002,17 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 tr_put(kterm, trv);
             }
         };
-        double* const cJ = &S.G_re[0][0];     // coefficient table of the step end (G and par are dead by now)
+        double* const cJ = S.cj;     // coefficient table of the step end
 
         // SB: rho00 = rho11 = Tr(rho0) / 2 of the observed site never move
-        double half_tr = 0.0;
         if constexpr (SB) {
-            half_tr = (lane < D) ? P.rho0[2 * (lane * D + lane)] : 0.0;
+            double h = (lane < D) ? P.rho0[2 * (lane * D + lane)] : 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) half_tr += __shfl_xor_sync(0xffffffffu, half_tr, o);
-            half_tr *= 0.5;
+            for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+            if (lane == 0) S.half_tr[0] = 0.5 * h;
+            __syncwarp();
         }
+#define half_tr (S.half_tr[0])
         {   // the first output time carries the initial state
             trace_store(acc_re, acc_im, 0);
             __syncwarp();
@@ -1143,51 +1270,87 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                 }
                 n_apply += Kc;
+                if (lane < 3 * NTR) S.tr[(Kc + 1) * NTR + lane] = 0.0;      // the output sums read the table in groups of four terms
                 __syncwarp();
                 PHASE_MARK(2);      // recurrence (and the coefficient table of a non-final step)
                 if (UNI(last)) {
-                    // ---- outputs of the step, 32 per round, Bessel weights by backward recurrence.  A round costs as many
-                    //      iterations as its LATEST output needs terms, so the rounds are cut from the end of the list: the
-                    //      partial round is the one with the earliest (cheapest) output times.
-                    for (int pbase = 0; UNI(pbase < q); pbase += 32) {
-                        const int p = q - 1 - pbase - lane;
-                        const bool act = p >= 0;
-                        const double tau = act ? ((nsub == 1) ? P.times[kidx + 1 + p] - t0 : tau_end) : 0.0;
-                        const double z = tau * Rb;
-                        const bool direct = !(z >= 1e-40);
-                        int Kp = 0;
-                        if (act && !direct) { Kp = cheb_terms(tau * Sb); if (Kp > Kc) Kp = Kc; }
-                        const int kmax = __reduce_max_sync(0xffffffffu, Kp);
-                        const double tz = direct ? 0.0 : 2.0 / z;
-                        double a0 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
-                        double kd = (double)kmax;
-#pragma unroll 2
-                        for (int k = kmax; k >= 1; --k, kd -= 1.0) {
-                            if (k == Kp) jn = 1.0;
-                            if constexpr (SB) {
-                                const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 2]);
-                                a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
-                            } else {
-                                const double2 ta = *reinterpret_cast<const double2*>(&S.tr[k * 4]);
-                                const double2 tb = *reinterpret_cast<const double2*>(&S.tr[k * 4 + 2]);
-                                a0 = fma(jn, ta.x, a0); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
-                            }
-                            if (!(k & 1)) ssum += jn;
-                            const double jm = fma(kd * tz, jn, -jn1);
-                            jn1 = jn; jn = jm;
+                    // ---- outputs of the step: Bessel weights J_k(tau_p R) by Miller's backward recurrence, NCH independent
+                    //      output times per lane (the recurrence is one dependent FMA chain per output: several chains in
+                    //      flight hide its latency; all chains of a pass share the loads of the trace table).  A pass costs
+                    //      as many terms as its LATEST output needs, so the passes are cut from the end of the list: the
+                    //      partial pass is the one with the earliest (cheapest) output times.  Terms go in groups of four,
+                    //      k a multiple of 4 (the table is zero beyond Kc): the multipliers 2k/z of a group cost one product
+                    //      and three subtractions, the even terms of the normalisation sum J_0 + 2 sum J_2k = 1 are known
+                    //      statically, and the test "this chain starts here" is only needed down to the smallest start index
+                    //      of the pass (a chain that has not started carries exact zeros).
+                    constexpr int NCH = EML_OUTPUT_CHAINS;
+                    const double t0o = P.times[kidx], tau_e = (P.times[kidx + q] - t0o) / nsub;
+                    for (int pbase = 0; UNI(pbase < q); pbase += 32 * NCH) {
+                        int Kp[NCH], pidx[NCH];
+                        double tz[NCH], tau[NCH];
+                        bool direct[NCH];
+                        int kmax = 0, kmin = 0x7fffffff;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            pidx[c] = q - 1 - pbase - 32 * c - lane;
+                            const bool act = pidx[c] >= 0;
+                            tau[c] = act ? ((nsub == 1) ? P.times[kidx + 1 + pidx[c]] - t0o : tau_e) : 0.0;
+                            const double z = tau[c] * Rb;
+                            direct[c] = !(z >= 1e-40);
+                            Kp[c] = 0;
+                            if (act && !direct[c]) { Kp[c] = cheb_terms(tau[c] * Sb); if (Kp[c] > Kc) Kp[c] = Kc; kmin = min(kmin, Kp[c]); }
+                            kmax = max(kmax, Kp[c]);
+                            tz[c] = direct[c] ? 0.0 : 2.0 / z;
                         }
+                        kmax = __reduce_max_sync(0xffffffffu, kmax);
+                        kmin = __reduce_min_sync(0xffffffffu, kmin);
+                        double a0[NCH], a2[NCH], a3[NCH], ssum[NCH], jn[NCH], jn1[NCH];
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) { a0[c] = a2[c] = a3[c] = ssum[c] = jn[c] = jn1[c] = 0.0; }
+                        int k = (kmax + 3) & ~3;
+                        double kd = (double)k;
+                        auto four_terms = [&](auto chk_tag) {
+                            constexpr bool CHK = decltype(chk_tag)::value;
+                            double cm[NCH];
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) cm[c] = kd * tz[c];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int kk = k - j;
+                                double2 ta = make_double2(0.0, 0.0);
+                                if constexpr (!SB) ta = *reinterpret_cast<const double2*>(&S.tr[kk * NTR]);
+                                const double2 tb = *reinterpret_cast<const double2*>(&S.tr[kk * NTR + NTR - 2]);
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) {
+                                    if constexpr (CHK)      // jn is exactly 0.0 before the start: setting the high word makes it 1.0
+                                        jn[c] = __hiloint2double(kk == Kp[c] ? 0x3ff00000 : __double2hiint(jn[c]), __double2loint(jn[c]));
+                                    if constexpr (!SB) a0[c] = fma(jn[c], ta.x, a0[c]);
+                                    a2[c] = fma(jn[c], tb.x, a2[c]); a3[c] = fma(jn[c], tb.y, a3[c]);
+                                    if (!(j & 1)) ssum[c] += jn[c];
+                                    const double jm = fma(cm[c], jn[c], -jn1[c]);
+                                    jn1[c] = jn[c]; jn[c] = jm;
+                                    if (j < 3) cm[c] -= tz[c];
+                                }
+                            }
+                            k -= 4; kd -= 4.0;
+                        };
+                        while (UNI(k >= 4 && k >= kmin)) four_terms(std::true_type{});
+                        while (UNI(k >= 4)) four_terms(std::false_type{});
                         const double2 ta = SB ? make_double2(half_tr, half_tr) : *reinterpret_cast<const double2*>(&S.tr[0]);
                         const double2 tb = *reinterpret_cast<const double2*>(&S.tr[NTR - 2]);
-                        double r[4];
-                        if (direct) {
-                            r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
-                        } else {
-                            const double nrm = exp(-ac * tau) / (2.0 * ssum + jn);
-                            // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
-                            r[0] = SB ? half_tr : fma(jn, ta.x, a0) * nrm; r[1] = (ta.x + ta.y) - r[0];
-                            r[2] = fma(jn, tb.x, a2) * nrm; r[3] = fma(jn, tb.y, a3) * nrm;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            double r[4];
+                            if (direct[c]) {
+                                r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
+                            } else {
+                                const double nrm = exp(-ac * tau[c]) / (2.0 * ssum[c] + jn[c]);
+                                // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
+                                r[0] = SB ? half_tr : fma(jn[c], ta.x, a0[c]) * nrm; r[1] = (ta.x + ta.y) - r[0];
+                                r[2] = fma(jn[c], tb.x, a2[c]) * nrm; r[3] = fma(jn[c], tb.y, a3[c]) * nrm;
+                            }
+                            if (pidx[c] >= 0) finish_output(kidx + 1 + pidx[c], r);
                         }
-                        if (act) finish_output(kidx + 1 + p, r);
                     }
                     __syncwarp();
                     PHASE_MARK(3);      // Bessel-weighted output sums, observables, loss terms
@@ -1195,6 +1358,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             }
             kidx += q;
         }
+#undef Rb
+#undef Sb
+#undef ac
+#undef tau_max
+#undef half_tr
         } else {
         int kidx = 0;
         while (UNI(kidx < T - 1)) {
@@ -1345,7 +1513,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-#define EML_WARP_INST(TL, RH, CH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA, SB>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+#define EML_WARP_INST(TL, RH, CH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA, SB>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
 EML_WARP_INST(1, true, false, false, false) EML_WARP_INST(1, false, false, false, false) EML_WARP_INST(2, true, false, false, false) EML_WARP_INST(2, false, false, false, false)
 EML_WARP_INST(1, true, true, false, false) EML_WARP_INST(1, false, true, false, false) EML_WARP_INST(2, true, true, false, false) EML_WARP_INST(2, false, true, false, false)
 EML_WARP_INST(2, true, true, true, false) EML_WARP_INST(2, false, true, true, false)
@@ -1369,35 +1537,6 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
     order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
 }
 
-// eml_order.cu
-const int* launch_packed_order(const DevProblem& P, long long n_models, const double* params, int* order_ws,
-                               const int* cost_hint, int slots, double zcap, int kcap, float fixed, float per_application,
-                               cudaStream_t stream);
-bool packed_order_applicable(const DevProblem& P, long long n_models, int slots);
-cudaError_t launch_predicted_applications(const DevProblem& P, long long n_models, const double* params, float* out,
-                                          double zcap, int kcap, cudaStream_t stream);
-// the series cap of the d = 16 Chebyshev variant a plan runs (sector: CHEB_KCAP_SB), for the diagnostic entry point
-cudaError_t warp_predicted_applications(const DevProblem& P, bool sector, long long n_models, const double* params, float* out,
-                                        cudaStream_t stream) {
-    const int kcap = sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2;
-    return launch_predicted_applications(P, n_models, params, out, cheb_zcap_for(kcap), kcap, stream);
-}
-#ifndef EML_ORDER_PACK_DEFAULT
-#define EML_ORDER_PACK_DEFAULT 0
-#endif
-// 0: longest-first list; 1: packed list for cold batches; 2: also when the caller supplies measured costs.
-// The environment variable EML_ORDER_PACK overrides the build default, eml_set_order_pack_mode overrides both (A/B measurements).
-static std::atomic<int> g_order_pack_override{-1};
-void set_order_pack_mode(int mode) { g_order_pack_override.store((mode >= 0 && mode <= 2) ? mode : -1); }
-static int order_pack_mode() {
-    static const int mode = [] {
-        const char* e = std::getenv("EML_ORDER_PACK");
-        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : EML_ORDER_PACK_DEFAULT;
-    }();
-    const int o = g_order_pack_override.load();
-    return o >= 0 ? o : mode;
-}
-
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }
@@ -1416,66 +1555,105 @@ static cudaError_t init_inv_table() {
 }
 
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
-                          unsigned int*, const int*, const double);
+                          unsigned int*, const int*, const double*);
+using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, const double, const int);
 
-template <int TL, bool CH, bool PA, bool SB = false>
-static WarpKern pick_kernel(bool real_h, size_t& smem) {
-    smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH, SB>);
-    return real_h ? (WarpKern)eval_warp_mma_kernel<TL, true, CH, PA, SB> : (WarpKern)eval_warp_mma_kernel<TL, false, CH, PA, SB>;
+struct WarpVariant {
+    WarpKern eval = nullptr;
+    PrepKern prep = nullptr;     // Chebyshev variants only
+    size_t smem = 0, prep_smem = 0;
+    int rec = 0, kcap = 0, id = 0;
+};
+template <int TL, bool RH, bool CH, bool PA, bool SB>
+static WarpVariant make_variant() {
+    WarpVariant v;
+    v.eval = (WarpKern)eval_warp_mma_kernel<TL, RH, CH, PA, SB>;
+    v.smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH, SB>);
+    v.kcap = WarpScratch<TL, CH, SB>::KCAP;
+    v.id = (SB ? 16 : 0) + (PA ? 8 : 0) + (TL == 2 ? 4 : 0) + (CH ? 2 : 0) + (RH ? 1 : 0);
+    if constexpr (CH) {
+        v.prep = (PrepKern)prepare_models_kernel<TL, RH, PA>;
+        v.prep_smem = PREP_WARPS * sizeof(PrepScratch<TL, RH>);
+        v.rec = prep_record_doubles<TL, RH, PA>();
+    }
+    return v;
+}
+template <int TL, bool CH, bool PA, bool SB>
+static WarpVariant make_variant_rh(bool real_h) {
+    return real_h ? make_variant<TL, true, CH, PA, SB>() : make_variant<TL, false, CH, PA, SB>();
+}
+static WarpVariant pick_variant(bool tl2, bool real_h, bool chebyshev, bool parity, bool sector) {
+    if (!tl2) return chebyshev ? make_variant_rh<1, true, false, false>(real_h) : make_variant_rh<1, false, false, false>(real_h);
+    if (!chebyshev) return make_variant_rh<2, false, false, false>(real_h);
+    if (sector) return make_variant_rh<2, true, true, true>(real_h);
+    if (parity) return make_variant_rh<2, true, true, false>(real_h);
+    return make_variant_rh<2, true, false, false>(real_h);
 }
 
+// bytes of prepare-kernel workspace per model of the Chebyshev variant a plan runs (0: Taylor variant, no prepare kernel)
+size_t warp_prep_bytes_per_model(const DevProblem& P, bool real_h, bool chebyshev, bool parity_h, bool sector_b) {
+    const bool tl2 = (P.n_tls == 4), parity = parity_h && chebyshev && tl2, sector = parity && sector_b;
+    return (size_t)pick_variant(tl2, real_h, chebyshev, parity, sector).rec * sizeof(double);
+}
+
+// prep_ws: workspace of the prepare kernel for prep_cap models (larger batches run in chunks of prep_cap)
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
-                            bool real_h, bool chebyshev, bool parity_h, bool sector_b, const int* cost_hint, cudaStream_t stream) {
+                            bool real_h, bool chebyshev, bool parity_h, bool sector_b, const int* cost_hint,
+                            double* prep_ws, long long prep_cap, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = init_inv_table()) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     const bool tl2 = (P.n_tls == 4);
-    size_t smem = 0;
     const bool parity = parity_h && chebyshev && tl2;     // H block diagonal by parity: half the DMMAs (d = 16)
     const bool sector = parity && sector_b;               // parity-even part of rho0 is a steady state: evolve the odd tiles only
-    const WarpKern kern = tl2 ? (chebyshev ? (sector ? pick_kernel<2, true, true, true>(real_h, smem)
-                                              : parity ? pick_kernel<2, true, true>(real_h, smem) : pick_kernel<2, true, false>(real_h, smem))
-                                           : pick_kernel<2, false, false>(real_h, smem))
-                              : (chebyshev ? pick_kernel<1, true, false>(real_h, smem) : pick_kernel<1, false, false>(real_h, smem));
+    const WarpVariant v = pick_variant(tl2, real_h, chebyshev, parity, sector);
     // per device and kernel variant: dynamic shared memory opt-in and the resident CTAs per SM
     static int per_sm_cache[64][32] = {{0}};
-    const int variant = (sector ? 16 : 0) + (parity ? 8 : 0) + (tl2 ? 4 : 0) + (chebyshev ? 2 : 0) + (real_h ? 1 : 0);
-    int per_sm = (dev < 64) ? per_sm_cache[dev][variant] : 0;
+    int per_sm = (dev < 64) ? per_sm_cache[dev][v.id] : 0;
     if (per_sm == 0) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(v.eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem)) != cudaSuccess) return e;
+        if (v.prep != nullptr &&
+            (e = cudaFuncSetAttribute(v.prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.prep_smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.eval, WARPS_PER_CTA * 32, v.smem)) != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        if (dev < 64) per_sm_cache[dev][variant] = per_sm;
+        if (dev < 64) per_sm_cache[dev][v.id] = per_sm;
         if (std::getenv("EML_B200_DEBUG") != nullptr)
-            fprintf(stderr, "eml: warp kernel variant %d: %d CTAs of %d warps per SM, %zu B shared memory per CTA\n", variant, per_sm,
-                    WARPS_PER_CTA, smem);
+            fprintf(stderr, "eml: warp kernel variant %d: %d CTAs of %d warps per SM, %zu B shared memory per CTA\n", v.id, per_sm,
+                    WARPS_PER_CTA, v.smem);
     }
-    long long ctas = (n_models + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
-    if (ctas > max_ctas) ctas = max_ctas;
-    const int kcap = tl2 ? (sector ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1;
-    const double zcap = chebyshev ? cheb_zcap_for(kcap) : 0.0;
-    // Model order.  d = 16 Chebyshev kernel with a real H and a few models per warp slot: exact costs (or the caller's
-    // measured ones) packed onto the warp slots (eml_order.cu); otherwise a longest-first list when the batch is worth sorting.
-    const int* use_order = nullptr;
-    const int slots = (int)ctas * WARPS_PER_CTA;
-    const int pack_mode = order_pack_mode();
-    if (order != nullptr && tl2 && chebyshev && real_h && pack_mode >= (cost_hint != nullptr ? 2 : 1) &&
-        packed_order_applicable(P, n_models, slots)) {
-        // cost model in units of one generator application (ncu samples: set-up + epilogue, output phase per term)
-        const float fixed = sector ? 45.f : 25.f, per_application = sector ? 1.28f : 1.15f;
-        use_order = launch_packed_order(P, n_models, params, order, cost_hint, slots, zcap, kcap, fixed, per_application, stream);
-    } else if (order != nullptr && n_models > 4LL * sms * CTAS_PER_SM && n_models <= ORDER_MAX_MODELS) {      // more than one model per resident warp
-        launch_model_order(P, n_models, params, order, cost_hint, stream);
-        use_order = order;
+    if (chebyshev && (prep_ws == nullptr || prep_cap < 1)) return cudaErrorInvalidValue;
+    const long long chunk_cap = chebyshev ? prep_cap : n_models;
+    const double zcap = chebyshev ? cheb_zcap_for(v.kcap) : 0.0;
+    for (long long off = 0; off < n_models; off += chunk_cap) {
+        const long long n = (n_models - off < chunk_cap) ? n_models - off : chunk_cap;
+        const double* p_ = params + off * P.n_params;
+        const int* ts_ = target_set ? target_set + off : nullptr;
+        double* ex_ = expect ? expect + (size_t)off * P.n_obs * P.n_times * 2 : nullptr;
+        double* lo_ = loss ? loss + off : nullptr;
+        int* st_ = status ? status + off : nullptr;
+        if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+        // Model order: longest first.  Chebyshev variants: by the generator applications the prepare kernel computes (exact);
+        // Taylor variants: by the caller's measured cost or a proxy computed from the parameters.
+        const bool sort = order != nullptr && n > (long long)WARPS_PER_CTA * max_ctas && n <= ORDER_MAX_MODELS;
+        float* cost = (order != nullptr && n <= ORDER_MAX_MODELS) ? reinterpret_cast<float*>(order + ORDER_MAX_MODELS) : nullptr;
+        if (chebyshev) {
+            v.prep<<<(unsigned)((n + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, v.prep_smem, stream>>>(
+                P, n, p_, prep_ws, sort ? cost : nullptr, zcap, v.kcap);
+            if (sort) order_models_kernel<<<1, 1024, 0, stream>>>((int)n, cost, order);
+        } else if (sort) {
+            launch_model_order(P, n, p_, order, cost_hint ? cost_hint + off : nullptr, stream);
+        }
+        long long ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if (ctas > max_ctas) ctas = max_ctas;
+        v.eval<<<(unsigned)ctas, WARPS_PER_CTA * 32, v.smem, stream>>>(P, n, p_, ts_, ex_, lo_, st_, counter, sort ? order : nullptr,
+                                                                      prep_ws);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    kern<<<(unsigned)ctas, WARPS_PER_CTA * 32, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter,
-                                                              use_order, zcap);
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 }  // namespace eml

@@ -50,10 +50,30 @@ def partition_sizes(n_chains: int, world: int) -> list[int]:
     return [partition(n_chains, world, r)[1] - partition(n_chains, world, r)[0] for r in range(world)]
 
 
-def gather_chain_stats(local_stats, n_chains: int | None = None) -> np.ndarray:
+def balanced_owners(group_sizes, world: int) -> list[np.ndarray]:
+    """
+    Cost-balanced ownership of a sweep whose chains come in groups of equal cost (one group per (dataset, configuration,
+    number of defects), chains of a group contiguous in the global order): EVERY group is split contiguously over the
+    ranks, so each rank gets 1/world of every model size instead of a contiguous slice of the launcher order (which
+    gives one rank mostly d = 16 chains and another mostly d = 4 chains: d = 16 costs ~3.5x d = 4).
+    Returns, for each rank, the sorted global indices of the chains it owns.
+    """
+    owners = [[] for _ in range(world)]
+    start = 0
+    for n in group_sizes:
+        for r in range(world):
+            lo, hi = partition(int(n), world, r)
+            owners[r].append(np.arange(start + lo, start + hi, dtype=np.int64))
+        start += int(n)
+    return [np.concatenate(o) if o else np.zeros(0, dtype=np.int64) for o in owners]
+
+
+def gather_chain_stats(local_stats, n_chains: int | None = None, owners=None) -> np.ndarray:
     """
     local_stats: [n_local][len(CHAIN_STATS_FIELDS)] float64 (numpy array or torch tensor on the rank's device).
     Returns the [n_chains][8] table of ALL chains, in global chain order, on every rank -- ONE all_gather.
+    owners (optional): for every rank the global indices of its rows (e.g. `balanced_owners`); default = the
+    contiguous `partition` of n_chains.
     """
     t = local_stats if isinstance(local_stats, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local_stats))
     t = t.to(torch.float64)
@@ -64,7 +84,12 @@ def gather_chain_stats(local_stats, n_chains: int | None = None) -> np.ndarray:
     world, rank = dist.get_world_size(), dist.get_rank()
     if n_chains is None:
         raise RuntimeError('n_chains (global) is required when world_size > 1')
-    sizes = partition_sizes(n_chains, world)
+    if owners is not None:
+        if len(owners) != world or sum(len(o) for o in owners) != n_chains:
+            raise RuntimeError('owners must list every chain exactly once, one index array per rank')
+        sizes = [len(o) for o in owners]
+    else:
+        sizes = partition_sizes(n_chains, world)
     if t.shape[0] != sizes[rank]:
         raise RuntimeError(f'rank {rank} holds {t.shape[0]} chains, partition says {sizes[rank]}')
     width = max(sizes)
@@ -75,4 +100,9 @@ def gather_chain_stats(local_stats, n_chains: int | None = None) -> np.ndarray:
     out = torch.empty((world * width, t.shape[1]), dtype=torch.float64, device=t.device)
     dist.all_gather_into_tensor(out, padded)          # concatenation along dim 0 (works for NCCL and gloo)
     out = out.view(world, width, t.shape[1]).cpu().numpy()
-    return np.concatenate([out[r, :sizes[r]] for r in range(world)], axis=0)
+    if owners is None:
+        return np.concatenate([out[r, :sizes[r]] for r in range(world)], axis=0)
+    table = np.empty((n_chains, t.shape[1]))
+    for r in range(world):
+        table[np.asarray(owners[r], dtype=np.int64)] = out[r, :sizes[r]]
+    return table

@@ -1,11 +1,13 @@
 """
 Multiset sweep on one node: the nested loop of the reference's bash launchers
 (launch_execute_learning_multiset.sh:35-66 -- target datasets x configurations x defect numbers x repetitions,
-one OS process per chain) as ONE job: every (dataset, configuration, D, repetition) is a chain; the global chain
-list is split contiguously over the ranks (one process per GPU, `dist.partition`), each rank groups its chains by
-(dataset, configuration, D) into `BatchedChains` engines -- models of different sizes run in different launches of
-the same kernels -- and advances them on separate CUDA streams.  There is no collective on the hot path; at
-checkpoints the per-chain statistics of all ranks are gathered with one all_gather (`dist.gather_chain_stats`).
+one OS process per chain) as ONE job: every (dataset, configuration, D, repetition) is a chain.  Chains of one
+(dataset, configuration, D) cost the same, chains of different D do not (d = 16 costs ~3.5x d = 4), so EVERY such group
+is split over the ranks (`dist.balanced_owners`; one process per GPU): each rank owns 1/world of every model size and
+runs one `BatchedChains` engine per group -- models of different sizes run in different launches of the same kernels,
+concurrently on separate CUDA streams.  A chain's random stream is keyed by its GLOBAL index, so the results do not
+depend on the partition.  There is no collective on the hot path; at checkpoints the per-chain statistics of all
+ranks are gathered with one all_gather (`dist.gather_chain_stats`).
 """
 from __future__ import annotations
 
@@ -53,16 +55,24 @@ class MultisetSweep:
             if torch.distributed.is_initialized() else (0, 1)
         self.chains = enumerate_chains(len(datasets), config_numbers, defects_numbers, repetitions_numbers)
         self.n_chains = len(self.chains)
-        self.lo, self.hi = dist.partition(self.n_chains, self.world, self.rank)
         if device is None:
             device = torch.cuda.current_device()
         names = list(configs.specific_experiment_chain_hyperparams)
-        # group this rank's chains (contiguous in the global order) by engine key, remembering global indices
-        groups: dict[tuple, list[int]] = {}
-        for gidx in range(self.lo, self.hi):
-            groups.setdefault(self.chains[gidx].key(), []).append(gidx)
+        # groups of equal-cost chains (contiguous in the launcher order); every group is split over the ranks
+        all_groups: dict[tuple, list[int]] = {}
+        for gidx, spec in enumerate(self.chains):
+            all_groups.setdefault(spec.key(), []).append(gidx)
+        for members in all_groups.values():
+            assert members == list(range(members[0], members[0] + len(members))), 'a group must be contiguous in the launcher order'
+        self.owners = dist.balanced_owners([len(m) for m in all_groups.values()], self.world)
+        self.owned = self.owners[self.rank]
+        self._row_of = {int(g): i for i, g in enumerate(self.owned)}
+        mine = set(int(g) for g in self.owned)
+        groups = {key: [g for g in members if g in mine] for key, members in all_groups.items()}
         self.engines = []
         for key, members in groups.items():
+            if not members:
+                continue
             ds, cfg_no, D = key
             cfg = configs.get_hyperparams(names[cfg_no])
             cfg.update(config_overrides or {})
@@ -82,16 +92,16 @@ class MultisetSweep:
             stream.synchronize()
 
     def local_stats(self) -> np.ndarray:
-        """[hi - lo][8] statistics of this rank's chains, in global chain order."""
-        out = np.zeros((self.hi - self.lo, len(dist.CHAIN_STATS_FIELDS)))
+        """[n_owned][8] statistics of this rank's chains, rows in the order of `self.owned` (ascending global index)."""
+        out = np.zeros((len(self.owned), len(dist.CHAIN_STATS_FIELDS)))
         for _, members, eng, stream in self.engines:
             stream.synchronize()
-            out[np.asarray(members) - self.lo] = eng.read()['stats']
+            out[[self._row_of[g] for g in members]] = eng.read()['stats']
         return out
 
     def checkpoint(self) -> np.ndarray:
         """Global [n_chains][8] table on every rank -- the one collective of the sweep."""
-        return dist.gather_chain_stats(self.local_stats(), self.n_chains)
+        return dist.gather_chain_stats(self.local_stats(), self.n_chains, owners=self.owners)
 
     def best_models(self, global_index: int):
         for _, members, eng, _ in self.engines:

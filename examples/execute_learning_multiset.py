@@ -64,13 +64,13 @@ class Toggles:
     text = True
 
 
-for gidx in range(sweep.lo, sweep.hi):
+for gidx in (int(g) for g in sweep.owned):
     spec = sweep.chains[gidx]
     best = sweep.best_models(gidx)
     filename = f'{experiment_name}_{dataset_names[spec.dataset]}_conf{spec.config}_D{spec.defects}_R{spec.repetition}'
     output.Output(toggles=Toggles, filename=filename, models_to_save=[best], model_names=['best'])
 if rank == 0:
-    print(f'{sweep.n_chains} chains on {world} rank(s); rank 0 wrote {sweep.hi - sweep.lo} best-model pickles')
+    print(f'{sweep.n_chains} chains on {world} rank(s); rank 0 wrote {len(sweep.owned)} best-model pickles')
 sweep.close()
 if world > 1:
     torch.distributed.destroy_process_group()

@@ -126,6 +126,10 @@ int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* tar
  *   status      [n_models] or NULL       >= 0: number of generator applications (series terms) the model
  *                                        needed; -1: not converged (series cap hit, or a non-finite / absurd generator)
  * `stream` is a cudaStream_t passed as void*.
+ * No host synchronisation.  The Chebyshev warp kernels (n_tls <= 4) run a prepare kernel first (assembly of the generators,
+ * spectral bounds, series plan, exact cost per model for the longest-first order) whose per-model records live in a
+ * workspace owned by the plan: the first call with a larger batch than any before grows it with one cudaMalloc (capped at
+ * 65536 models; larger batches run in chunks), every later call allocates nothing.
  */
 int eml_eval_batch(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
                    double* expect, double* loss, int32_t* status, void* stream);
@@ -140,14 +144,6 @@ int64_t eml_launch_count(void);
  * phase since the last reset, summed over warps -- [0] assembly + bounds, [1] plan + first output, [2] recurrence,
  * [3] output sums, [4] epilogue.  Current device. */
 int eml_debug_phase_clocks(uint64_t* out8, int reset);
-/* Order in which the persistent warps of the d = 16 Chebyshev kernel fetch the models of a launch (results do not depend
- * on it): 0 longest-first list, 1 exact-cost packing for cold batches, 2 also with caller-measured costs (chain engine);
- * any other value returns to the build default / the EML_ORDER_PACK environment variable.  Process-wide. */
-void eml_set_order_pack_mode(int mode);
-/* Diagnostic for the packed order: the generator applications the d = 16 Chebyshev kernel (real Hamiltonian) will
- * spend on every model, predicted by the FP32 pre-pass; compare with `status` of eml_eval_batch.  Device pointers:
- * params [n_models][n_params], applications [n_models].  EML_ERR_UNSUPPORTED for other plans. */
-int eml_predict_applications(EmlPlan* plan, int64_t n_models, const double* params, float* applications, void* stream);
 /* Name of the kernel the plan dispatches to ("generic", "warp_mma", ...). */
 const char* eml_plan_kernel_name(const EmlPlan* plan);
 /* FP64 microbenchmarks used to establish the roofline denominator (flops per second). */

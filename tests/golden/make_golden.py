@@ -153,57 +153,68 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'oracle_observables.npz'), **frozen)
 
     # ---------------------------------------------------------------- reference chain trajectories
-    for D, steps, seed in ((1, 400, 2024), (2, 250, 7)):
-        truth = lo.random_library_spec(np.random.default_rng(20260000 + 10 + D), 1, D)
-        ts_c = np.linspace(0.0, 2.5, 100)
-        noise = np.random.default_rng(99 + D)
-        targets = [np.asarray(e) + noise.normal(0, 0.01, len(ts_c)) for e in lo.expect_exact(truth, ts_c, OBS3)]
-        config = ref_configs.get_hyperparams(list(ref_configs.specific_experiment_chain_hyperparams)[11])
-        config['iterations_till_progress_update'] = False
-        np.random.seed(seed)
-        chain = ref_learning_chain.LearningChain(
-            target_times=ts_c, target_datasets=targets, target_observables=OBS3,
-            initial=(1, D), qubit_initial_state=ref_definitions.ops['plus'],
-            defect_initial_state=ref_definitions.ops['mm'], max_chain_steps=steps,
-            store_all_proposals=True, **config)
-        # Which partner "holds" a new coupling is decided in the reference by iterating a Python set
-        # of objects (process_handling.py:247-257), i.e. by memory addresses.  Record
-        # the outcome of every coupling addition so the port can be replayed with the same choices.
-        holder_is_first = []
-        ph = chain.process_handler
+    for D, steps, seed in CHAIN_FIXTURES:
+        chain_fixture(D, steps, seed)
 
-        def spying(orig):
-            def wrapped(model, **kw):
-                if not kw.get('update', True):
-                    return orig(model, **kw)
-                before = [{id(p): len(v) for p, v in t.couplings.items()} for t in model.TLSs]
-                out = orig(model, **kw)
-                for a, t in enumerate(model.TLSs):
-                    for p, v in t.couplings.items():
-                        if len(v) > before[a].get(id(p), 0):
-                            holder_is_first.append(bool(a < model.TLSs.index(p)))
-                return out
-            return wrapped
 
-        ph.add_random_qubit2defect_coupling = spying(ph.add_random_qubit2defect_coupling)
-        ph.add_random_defect2defect_coupling = spying(ph.add_random_defect2defect_coupling)
-        best = chain.run()
-        vals, labels, _ = best.vectorise_under_library(config)
-        with open(os.path.join(HERE, f'reference_chain_D{D}.json'), 'w') as f:
-            json.dump({'D': D, 'steps': steps, 'seed': seed, 'config_index': 11,
-                       'target_times': list(ts_c), 'targets': [list(map(float, t)) for t in targets],
-                       'step_types': chain.run_step_type_tracker,
-                       'loss': [float(x) for x in chain.explored_loss],
-                       'acceptance_probability': [float(x) for x in chain.explored_acceptance_probability],
-                       'acceptance': [bool(x) for x in chain.run_acceptance_tracker],
-                       'best_loss': float(chain.best_loss), 'best_values': [float(v) for v in vals],
-                       'best_labels': labels,
-                       'counters': [chain.tot_RJ_steps, chain.acc_RJ_steps, chain.tot_tweak_steps, chain.acc_tweak_steps],
-                       'coupling_holder_is_first': holder_is_first,
-                       'mesolve_calls': qutip.MESOLVE_CALLS}, f)
-        print(f'chain D={D}: {steps} steps, accepted {sum(chain.run_acceptance_tracker)}, best loss {chain.best_loss:.3e}, '
-              f'mesolve calls so far {qutip.MESOLVE_CALLS}')
+CHAIN_FIXTURES = ((1, 400, 2024), (2, 250, 7), (3, 160, 31))      # D = 3: the headline size (d = 16)
+
+
+def chain_fixture(D, steps, seed):
+    """One seeded LearningChain.run() of the REAL reference (learning_chain.py:314-614) -> reference_chain_D{D}.json."""
+    truth = lo.random_library_spec(np.random.default_rng(20260000 + 10 + D), 1, D)
+    ts_c = np.linspace(0.0, 2.5, 100)
+    noise = np.random.default_rng(99 + D)
+    targets = [np.asarray(e) + noise.normal(0, 0.01, len(ts_c)) for e in lo.expect_exact(truth, ts_c, OBS3)]
+    config = ref_configs.get_hyperparams(list(ref_configs.specific_experiment_chain_hyperparams)[11])
+    config['iterations_till_progress_update'] = False
+    np.random.seed(seed)
+    chain = ref_learning_chain.LearningChain(
+        target_times=ts_c, target_datasets=targets, target_observables=OBS3,
+        initial=(1, D), qubit_initial_state=ref_definitions.ops['plus'],
+        defect_initial_state=ref_definitions.ops['mm'], max_chain_steps=steps,
+        store_all_proposals=True, **config)
+    # Which partner "holds" a new coupling is decided in the reference by iterating a Python set
+    # of objects (process_handling.py:247-257), i.e. by memory addresses (SURVEY.md F8).  Record
+    # the outcome of every coupling addition so the port can be replayed with the same choices.
+    holder_is_first = []
+    ph = chain.process_handler
+    def spying(orig):
+        def wrapped(model, **kw):
+            if not kw.get('update', True):
+                return orig(model, **kw)
+            before = [{id(p): len(v) for p, v in t.couplings.items()} for t in model.TLSs]
+            out = orig(model, **kw)
+            for a, t in enumerate(model.TLSs):
+                for p, v in t.couplings.items():
+                    if len(v) > before[a].get(id(p), 0):
+                        holder_is_first.append(bool(a < model.TLSs.index(p)))
+            return out
+        return wrapped
+    ph.add_random_qubit2defect_coupling = spying(ph.add_random_qubit2defect_coupling)
+    ph.add_random_defect2defect_coupling = spying(ph.add_random_defect2defect_coupling)
+    best = chain.run()
+    vals, labels, _ = best.vectorise_under_library(config)
+    with open(os.path.join(HERE, f'reference_chain_D{D}.json'), 'w') as f:
+        json.dump({'D': D, 'steps': steps, 'seed': seed, 'config_index': 11,
+                   'target_times': list(ts_c), 'targets': [list(map(float, t)) for t in targets],
+                   'step_types': chain.run_step_type_tracker,
+                   'loss': [float(x) for x in chain.explored_loss],
+                   'acceptance_probability': [float(x) for x in chain.explored_acceptance_probability],
+                   'acceptance': [bool(x) for x in chain.run_acceptance_tracker],
+                   'best_loss': float(chain.best_loss), 'best_values': [float(v) for v in vals],
+                   'best_labels': labels,
+                   'counters': [chain.tot_RJ_steps, chain.acc_RJ_steps, chain.tot_tweak_steps, chain.acc_tweak_steps],
+                   'coupling_holder_is_first': holder_is_first,
+                   'mesolve_calls': qutip.MESOLVE_CALLS}, f)
+    print(f'chain D={D}: {steps} steps, accepted {sum(chain.run_acceptance_tracker)}, best loss {chain.best_loss:.3e}, '
+          f'mesolve calls so far {qutip.MESOLVE_CALLS}')
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == 'chains':      # only the listed chain fixtures: make_golden.py chains 3
+        for D, steps, seed in CHAIN_FIXTURES:
+            if str(D) in sys.argv[2:]:
+                chain_fixture(D, steps, seed)
+        sys.exit(0)
     main()

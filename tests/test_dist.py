@@ -74,3 +74,47 @@ def test_enumerate_chains_follows_launcher_loop_order():
     ch = enumerate_chains(1, [11], [1, 2], [3, 1])
     assert [(c.defects, c.repetition) for c in ch] == [(1, 1), (1, 2), (1, 3), (2, 1)]
     assert len(enumerate_chains(1, [11], [1, 2], [5, 5, 5])) == 6      # malformed repetitions -> default 3 each
+
+
+def test_balanced_owners_split_every_group_over_the_ranks():
+    sizes = [5, 3, 7, 1]
+    for world in (1, 2, 3, 8):
+        owners = edist.balanced_owners(sizes, world)
+        assert len(owners) == world
+        allidx = np.sort(np.concatenate(owners))
+        assert np.array_equal(allidx, np.arange(sum(sizes)))           # every chain exactly once
+        start = 0
+        for n in sizes:                                                # each group: sizes differ by at most one
+            per_rank = [int(((o >= start) & (o < start + n)).sum()) for o in owners]
+            assert max(per_rank) - min(per_rank) <= 1 and sum(per_rank) == n
+            start += n
+        assert all(np.all(np.diff(o) > 0) for o in owners if len(o) > 1)
+
+
+def _worker_owners(rank, world, port, sizes, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    edist.init('gloo')
+    owners = edist.balanced_owners(sizes, world)
+    mine = owners[rank].astype(np.float64)
+    local = np.stack([mine * 10 + f for f in range(len(edist.CHAIN_STATS_FIELDS))], axis=1)
+    q.put((rank, edist.gather_chain_stats(local, int(sum(sizes)), owners=owners)))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_gather_with_balanced_owners_two_ranks_gloo():
+    world, sizes = 2, [5, 3, 7, 1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_owners, args=(r, world, port, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = np.stack([np.arange(sum(sizes)) * 10.0 + f for f in range(len(edist.CHAIN_STATS_FIELDS))], axis=1)
+    for r in range(world):
+        assert np.array_equal(got[r], want)

@@ -99,7 +99,7 @@ def test_errors_match_reference_contract():
         m.calculate_dynamics(np.linspace(0, 1, 5), observable_ops=[1, 2])
 
 
-@pytest.mark.parametrize('D', [1, 2])
+@pytest.mark.parametrize('D', [1, 2, 3])      # D = 3: the headline size (d = 16, sector kernel)
 def test_chain_on_gpu_replays_reference_accept_reject_sequence(D):
     """north_star: for fixed seeds the accept/reject sequence matches the reference's (losses to 1e-8)."""
     import json

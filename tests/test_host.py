@@ -151,7 +151,7 @@ def test_deepcopy_is_independent():
     assert m.TLSs[1].Ls.get('sigmax') != 0.123 and m.TLSs[1].energy != 9.0
 
 
-@pytest.mark.parametrize('D', [1, 2])
+@pytest.mark.parametrize('D', [1, 2, 3])
 def test_chain_replays_reference_trajectory(oracle_backend, D):
     """
     Same seed, same hyperparameters as the REAL reference chain recorded in make_golden.py: the port must
