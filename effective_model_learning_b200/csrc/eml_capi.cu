@@ -1,4 +1,5 @@
 // extern "C" boundary of libeml_b200.so (see include/eml_b200.h).
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -50,6 +51,103 @@ static bool op_is_hermitian(const double* op) {
     const double tol = 1e-15;
     return std::fabs(op[1]) <= tol && std::fabs(op[7]) <= tol && std::fabs(op[2] - op[4]) <= tol &&
            std::fabs(op[3] + op[5]) <= tol;
+}
+
+// The generator assembly of the warp kernels as a linear program (see eml_common.cuh): column p of the map
+// c -> (G_re, G_im, jw, kd) is what the term-by-term assembly (eml_warp_mma.cu: assemble_generator, reference
+// basic_model.py:152-255) produces for the unit vector e_p; rows are listed longest first so that the lanes of a warp,
+// which take 32 consecutive rows at a time, run gathers of similar length.
+static int compile_linear_program(EmlPlan* plan, const EmlProblemDesc* d) {
+    const int N = plan->Pw.n_tls, D = 1 << N, obs_site = plan->Pw.obs_site, P = d->n_params;
+    if (P > eml::WARP_MAXP) return EML_OK;
+    std::vector<int> sq(P, -1);
+    for (int t = 0; t < d->n_terms; ++t) {
+        const int want = d->terms[t].kind == EML_TERM_COUPLING ? 1 : 0;
+        if (sq[d->terms[t].param] >= 0 && sq[d->terms[t].param] != want) return EML_OK;   // a column shared by a coupling and a linear term
+        sq[d->terms[t].param] = want;
+    }
+    for (int& v : sq) if (v < 0) v = 0;
+    auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
+    struct C2 { double re, im; };
+    auto op = [&](int o, int r, int c) { const double* p = d->op_table + o * 8 + (r * 2 + c) * 2; return C2{p[0], p[1]}; };
+    auto mul = [](C2 a, C2 b) { return C2{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; };
+    const int n_out = 2 * D * (D + 1) + eml::WARP_MAXP + 40;
+    std::vector<std::vector<eml::LinEntry>> rows(n_out);
+    std::vector<double> y(n_out);
+    for (int p = 0; p < P; ++p) {
+        std::fill(y.begin(), y.end(), 0.0);
+        for (int t = 0; t < d->n_terms; ++t) {
+            const EmlTerm& tm = d->terms[t];
+            if (tm.param != p) continue;
+            const int sa = pos(tm.site_a);
+            for (int r = 0; r < D; ++r) {
+                const int ra = (r >> sa) & 1;
+                if (tm.kind == EML_TERM_ENERGY) {
+                    for (int a = 0; a < 2; ++a) {
+                        const C2 A = op(tm.op_a, ra, a);
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        y[eml::prep_off_gre(D, r, c)] += A.im;      // -i h
+                        y[eml::prep_off_gim(D, r, c)] -= A.re;
+                    }
+                } else if (tm.kind == EML_TERM_COUPLING) {
+                    const int sb = pos(tm.site_b), rb = (r >> sb) & 1;
+                    for (int a = 0; a < 2; ++a)
+                        for (int bb = 0; bb < 2; ++bb) {
+                            const C2 AB = mul(op(tm.op_a, ra, a), op(tm.op_b, rb, bb));
+                            const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
+                            y[eml::prep_off_gre(D, r, c)] += AB.im;
+                            y[eml::prep_off_gim(D, r, c)] -= AB.re;
+                        }
+                } else {
+                    for (int a = 0; a < 2; ++a) {
+                        C2 M{0.0, 0.0};
+                        for (int z = 0; z < 2; ++z) {
+                            const C2 az = op(tm.op_a, z, ra);
+                            const C2 m = mul(C2{az.re, -az.im}, op(tm.op_a, z, a));
+                            M.re += m.re; M.im += m.im;
+                        }
+                        const int c = (r & ~(1 << sa)) | (a << sa);
+                        y[eml::prep_off_gre(D, r, c)] -= 0.5 * M.re;
+                        y[eml::prep_off_gim(D, r, c)] -= 0.5 * M.im;
+                    }
+                }
+            }
+            if (tm.kind == EML_TERM_LINDBLAD) {
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int bp = lane >> 3, type = (lane >> 2) & 1, ra = (lane >> 1) & 1, ca = lane & 1;
+                    if (bp >= N || sa != bp) continue;
+                    const int a = type ? 1 - ra : ra, bb = type ? 1 - ca : ca;
+                    const C2 cb = op(tm.op_a, ca, bb);
+                    y[eml::prep_off_jw(D, lane)] += mul(op(tm.op_a, ra, a), C2{cb.re, -cb.im}).re;
+                    if (type == 0 && ca == 0) {
+                        const C2 m0 = op(tm.op_a, 0, ra), m1 = op(tm.op_a, 1, ra);
+                        y[eml::prep_off_kd(D, bp * 2 + ra)] += (m0.re * m0.re + m0.im * m0.im) + (m1.re * m1.re + m1.im * m1.im);
+                    }
+                }
+            }
+        }
+        for (int o = 0; o < n_out; ++o)
+            if (y[o] != 0.0) rows[o].push_back(eml::LinEntry{y[o], p, 0});
+    }
+    std::vector<int> idx;
+    for (int o = 0; o < n_out; ++o) if (!rows[o].empty()) idx.push_back(o);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    std::vector<eml::LinRow> lrow;
+    std::vector<eml::LinEntry> lent;
+    for (int o : idx) {
+        lrow.push_back(eml::LinRow{o, (int)lent.size(), (int)(lent.size() + rows[o].size()), 0});
+        lent.insert(lent.end(), rows[o].begin(), rows[o].end());
+    }
+    if (lrow.empty()) { lrow.push_back(eml::LinRow{0, 0, 0, 0}); lent.push_back(eml::LinEntry{0.0, 0, 0}); }
+    int rc;
+    const eml::LinRow* d_row = nullptr; const eml::LinEntry* d_ent = nullptr; const int* d_sq = nullptr;
+    if ((rc = upload(plan, lrow.data(), lrow.size(), &d_row)) != EML_OK) return rc;
+    if ((rc = upload(plan, lent.data(), lent.size(), &d_ent)) != EML_OK) return rc;
+    if ((rc = upload(plan, sq.data(), sq.size() ? sq.size() : 1, &d_sq)) != EML_OK) return rc;
+    for (eml::DevProblem* Q : {&plan->P, &plan->Pw}) {
+        Q->lin_rows = (int)idx.size(); Q->lin_nnz = (int)lent.size(); Q->lin_row = d_row; Q->lin_ent = d_ent; Q->lin_sq = d_sq;
+    }
+    return EML_OK;
 }
 
 extern "C" {
@@ -142,6 +240,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     P.theta_target = (opts && opts->theta_target > 0) ? opts->theta_target : 16.0;
     P.tol = (opts && opts->tol > 0) ? opts->tol : 1e-11;
     if (P.theta_target > 16.0) P.theta_target = 16.0;  // MCAP = 80 terms converge below 1e-15 for theta <= 16
+    P.h_span = d->times[d->n_times - 1] - d->times[0];
     const int dd = 1 << (2 * d->n_tls);
     int rc;
 #define EML_TRY(x) if ((rc = (x)) != EML_OK) { eml_plan_destroy(plan); return rc; }
@@ -227,6 +326,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
             }
     }
     plan->sector_b = sector;
+    P.lin_rows = 0; P.lin_nnz = 0; P.lin_row = nullptr; P.lin_ent = nullptr; P.lin_sq = nullptr;
     // Models with fewer than 3 sites are embedded for the warp kernel: spectator sites (identity dynamics,
     // state |0><0|) are appended as the least significant factors, which changes neither the reduced dynamics of
     // the real sites nor the observables.
@@ -242,6 +342,7 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         plan->Pw.n_tls = 3;
         EML_TRY(upload(plan, big.data(), big.size(), &plan->Pw.rho0));
     }
+    if (eml::warp_mma_supported(plan->Pw, herm)) EML_TRY(compile_linear_program(plan, d));
     {
         void* c = nullptr;
         cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int));

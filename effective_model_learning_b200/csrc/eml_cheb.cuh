@@ -85,6 +85,76 @@ __device__ __forceinline__ ChebPlan cheb_make_plan(const double spread, const do
     return pl;
 }
 
+// ---- warp-cooperative versions for the prepare kernel (one warp per model): the scalar versions above cost a warp the same
+//      number of instructions whether 1 or 32 lanes run them, so the independent pieces go to different lanes.
+//      Same results as the scalar versions (same operations on the same values; ties keep the earlier candidate).
+__device__ __forceinline__ void cheb_site_ranges_warp(const double* jw, const double* kd, const int n_sites, const int lane,
+                                                      double& dlo, double& dhi, double& dasym) {
+    // lane = 4 bp + rc for lane < 16: one row of one site's 4 x 4 generator
+    const int bp = (lane >> 2) & 3, rc = lane & 3, ra = rc >> 1, ca = rc & 1;
+    const bool on = lane < 16 && bp < n_sites;
+    double lo = 1e300, hi = -1e300, as = 0.0;
+    if (on) {
+        const double dg = jw[bp * 8 + rc] - 0.5 * (kd[bp * 2 + ra] + kd[bp * 2 + ca]);
+        const double fa = jw[bp * 8 + 4 + rc], fb = jw[bp * 8 + 4 + (3 - rc)];
+        const double rad = 0.5 * fabs(fa + fb);
+        lo = dg - rad; hi = dg + rad; as = 0.5 * fabs(fa - fb);
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {      // over the four rows of a site
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        as = fmax(as, __shfl_xor_sync(0xffffffffu, as, o));
+    }
+    if (!on) { lo = 0.0; hi = 0.0; as = 0.0; }
+#pragma unroll
+    for (int o = 4; o <= 8; o <<= 1) {      // the ranges of a Kronecker sum add
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        as += __shfl_xor_sync(0xffffffffu, as, o);
+    }
+    dlo = __shfl_sync(0xffffffffu, lo, 0); dhi = __shfl_sync(0xffffffffu, hi, 0); dasym = __shfl_sync(0xffffffffu, as, 0);
+}
+
+__device__ __forceinline__ ChebPlan cheb_make_plan_warp(const double spread, const double dlo, const double dhi, const double dasym,
+                                                        const double span, const double zcap, const int kcap, const int lane) {
+    ChebPlan pl;
+    pl.ac = -0.5 * (dlo + dhi);
+    const double ah = 0.5 * (dhi - dlo), yext = spread + dasym;
+    // lane i < 6 evaluates enclosure candidate i
+    const int i = lane & 7;
+    const double delta = (i == 0) ? 0.03 : (i == 1) ? 0.06 : (i == 2) ? 0.12 : (i == 3) ? 0.25 : (i == 4) ? 0.5 : 1.0;
+    const double Rc = fmax(fmax(yext * (1.0 + delta), ah), 1e-3 / fmax(span, 1e-300));
+    const double cc = Rc * Rc - ah * ah - yext * yext, xr2 = ah * ah * Rc * Rc;
+    const double disc = sqrt(cc * cc + 4.0 * xr2);
+    const double u = (cc > 0.0) ? 2.0 * xr2 / (cc + disc) : 0.5 * (disc - cc);
+    double Bb = sqrt(u), Rb = Rc;
+    double Sb = sqrt(u + Rc * Rc) + Bb;
+    int ok = (i < 6 && span * Bb <= CHEB_HUMP) ? 1 : 0, who = i;
+    if (i >= 6) Sb = 1e300;      // not a candidate: loses against every real one that is not ok, and ok is 0
+    // first candidate that is ok with the smallest A + B, else the smallest A + B (ties: the earlier one) -- the scalar rule
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+        const int ok2 = __shfl_xor_sync(0xffffffffu, ok, o), who2 = __shfl_xor_sync(0xffffffffu, who, o);
+        const double S2 = __shfl_xor_sync(0xffffffffu, Sb, o), R2 = __shfl_xor_sync(0xffffffffu, Rb, o);
+        const double B2 = __shfl_xor_sync(0xffffffffu, Bb, o);
+        const bool take = (ok2 > ok) || (ok2 == ok && (S2 < Sb || (S2 == Sb && who2 < who)));
+        if (take) { ok = ok2; who = who2; Sb = S2; Rb = R2; Bb = B2; }
+    }
+    // NaN inputs: every comparison is false, lane 0 keeps candidate 0 (NaN) -- as the scalar version does
+    Rb = __shfl_sync(0xffffffffu, Rb, 0); Sb = __shfl_sync(0xffffffffu, Sb, 0); Bb = __shfl_sync(0xffffffffu, Bb, 0);
+    pl.R = Rb; pl.S = Sb;
+    double tau_max = zcap / Sb;
+    if (Bb > 0.0) tau_max = fmin(tau_max, CHEB_HUMP / Bb);
+    const double lnr = log(Sb / Rb);
+    if (lnr * (double)kcap > 560.0) {
+        const double kall = 560.0 / lnr;
+        tau_max = fmin(tau_max, fmax(kall - CHEB_C1 * cbrt(kall) - CHEB_C0, 1.0) / Sb);
+    }
+    pl.tau_max = tau_max;
+    return pl;
+}
+
 // v * 2^-1 (hsub = 0x00100000) or v (hsub = 0) on the integer pipe; zeros and the very smallest numbers pass unchanged
 __device__ __forceinline__ double scale_pow2(const double v, const int hsub) {
     const int hi = __double2hiint(v);

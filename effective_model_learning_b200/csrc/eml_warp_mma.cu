@@ -34,6 +34,7 @@
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
 #include <atomic>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -52,7 +53,7 @@ constexpr int WARPS_PER_CTA = EML_WARPS_PER_CTA;
 #define EML_CTAS_PER_SM 2
 #endif
 constexpr int CTAS_PER_SM = EML_CTAS_PER_SM;   // 2 -> 8 warps per SM (<= 255 regs); 3 -> 12 warps (<= 168 regs)
-constexpr int MAXP = 128;       // parameter-vector cap for this kernel
+constexpr int MAXP = WARP_MAXP; // parameter-vector cap for this kernel
 
 // Chebyshev series: terms per macro step that fit the per-warp trace buffer (8 warps x 26.4 KB at d = 16,
 // 16 warps x 13 KB at d <= 8), and the largest  tau * (A + B)  whose series fits (cheb_terms(z) <= cap)
@@ -90,10 +91,10 @@ static_assert(WARPS_PER_SM_SB % EML_WARPS_PER_CTA == 0, "resident warps per SM m
 // Per-warp shared memory.  The Taylor variants assemble the generator themselves (G, parameters, norm-bound scratch);
 // the Chebyshev variants receive it from the prepare kernel and keep the trace table, the coefficient table of a
 // non-final macro step and the transposition tile instead.
-template <int TL, bool CHEB, bool SB = false>
+template <int TL, bool CHEB, bool SB = false, bool PA = false>
 struct alignas(16) WarpScratch;
 template <int TL>
-struct alignas(16) WarpScratch<TL, false, false> {
+struct alignas(16) WarpScratch<TL, false, false, false> {
     static constexpr int D = 8 * TL, KCAP = 0, NTR = 4;
     double G_re[D][D + 1];
     double G_im[D][D + 1];
@@ -107,8 +108,8 @@ struct alignas(16) WarpScratch<TL, false, false> {
     alignas(16) double xt_im[XT];   // X' staged column-major (swizzled) for the conjugate transpose
     alignas(16) double tr[4];
 };
-template <int TL, bool SB>
-struct alignas(16) WarpScratch<TL, true, SB> {
+template <int TL, bool SB, bool PA>
+struct alignas(16) WarpScratch<TL, true, SB, PA> {
     static constexpr int D = 8 * TL;
     static constexpr int KCAP = TL == 2 ? (SB ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1;
     static constexpr int NTR = SB ? 2 : 4;      // partial-trace values kept per term
@@ -118,8 +119,9 @@ struct alignas(16) WarpScratch<TL, true, SB> {
     double half_tr[2];  // sector variant: Tr(rho0) / 2 (rho00 = rho11 of the observed site never move)
     static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
     // SB: one 8 x 8 complex tile, planes re | im of 64 doubles, two buffers (256 doubles in xt_re; xt_im unused)
-    alignas(16) double xt_re[XT];
-    alignas(16) double xt_im[SB ? 2 : XT];   // X' staged column-major (swizzled) for the conjugate transpose
+    // (parity variants: 8 x 8 tiles, planes re | im of 64 doubles, two buffers -- one tile in the sector variant, three otherwise)
+    alignas(16) double xt_re[SB ? 256 : (PA ? 768 : XT)];
+    alignas(16) double xt_im[(SB || PA) ? 2 : XT];   // X' staged column-major (swizzled) for the conjugate transpose
     double cj[KCAP + 2];                     // Bessel coefficients of the step end (non-final macro steps only)
     alignas(16) double tr[(KCAP + 4) * NTR]; // partial traces of the Chebyshev terms (+3 zero entries: groups of four)
 };
@@ -351,18 +353,21 @@ __device__ __forceinline__ double assemble_generator(SC& S, const DevProblem& P,
 //      Chebyshev plan and writes ONE RECORD per model for the evaluator:
 //        [NA][32]  A fragments of G per lane (im plane, then re plane for a complex H), k index permuted as the evaluator
 //                  multiplies them;  [32] jw;  [16] diagonal of G.re;  [4] R, S, ac, tau_max  (R = NaN: not evaluable)
-//      and the number of generator applications the evaluation will need (exact for a single macro step) -- the cost the
-//      persistent warps of the evaluator are ordered by.
+//      and the number of generator applications the evaluation will need (exact for a single macro step): the cost the
+//      persistent warps of the evaluator are ordered by.  Persistent CTAs: the plan's linear program (eml_common.cuh) is
+//      staged in shared memory once per CTA, then every warp takes models gw, gw + (warps of the grid), ...; the scalar
+//      tail (site ranges, the six enclosure candidates) is spread over lanes (eml_cheb.cuh: *_warp).
 template <int TL, bool REAL_H, bool PARITY>
 __host__ __device__ constexpr int prep_fragments() { return (REAL_H ? 1 : 2) * TL * (PARITY ? 2 : 2 * TL); }
 template <int TL, bool REAL_H, bool PARITY>
 __host__ __device__ constexpr int prep_record_doubles() { return prep_fragments<TL, REAL_H, PARITY>() * 32 + 32 + 16 + 4; }
 constexpr int PREP_WARPS = 4;
+constexpr int PREP_LIN_STAGE_MAX = 40 * 1024;      // largest linear program staged in shared memory (else it is read through L1/L2)
 
 template <int TL, bool REAL_H, bool PARITY>
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prepare_models_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params, double* __restrict__ rec,
-                      float* __restrict__ cost, const double cheb_zcap, const int kcap) {
+                      float* __restrict__ cost, const double cheb_zcap, const int kcap, const int stage_lin) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL, KSE = PARITY ? 2 : KS;
     constexpr int NA = prep_fragments<TL, REAL_H, PARITY>(), REC = prep_record_doubles<TL, REAL_H, PARITY>();
     auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
@@ -370,17 +375,68 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
     using Scratch = PrepScratch<TL, REAL_H>;
     Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const long long b = (long long)blockIdx.x * PREP_WARPS + (threadIdx.x >> 5);
-    if (b >= n_models) return;
+    // the linear program, staged behind the per-warp scratch (rows, then entries) when the launch reserved room for it
+    const LinRow* lin_row = P.lin_row;
+    const LinEntry* lin_ent = P.lin_ent;
+    if (stage_lin) {
+        int4* dst = reinterpret_cast<int4*>(smem_raw + PREP_WARPS * sizeof(Scratch));
+        const int4* src_r = reinterpret_cast<const int4*>(P.lin_row);
+        const int4* src_e = reinterpret_cast<const int4*>(P.lin_ent);
+        for (int i = threadIdx.x; i < P.lin_rows; i += blockDim.x) dst[i] = src_r[i];
+        for (int i = threadIdx.x; i < P.lin_nnz; i += blockDim.x) dst[P.lin_rows + i] = src_e[i];
+        lin_row = reinterpret_cast<const LinRow*>(dst);
+        lin_ent = reinterpret_cast<const LinEntry*>(dst + P.lin_rows);
+        __syncthreads();
+    }
+    const double span = P.times[P.n_times - 1] - P.times[0];
+    const long long warps_in_grid = (long long)gridDim.x * PREP_WARPS;
+    for (long long b = (long long)blockIdx.x * PREP_WARPS + (threadIdx.x >> 5); b < n_models; b += warps_in_grid) {
     double* const R = rec + (size_t)b * REC;
-    const int T = P.n_times;
-    const double span = P.times[T - 1] - P.times[0];
-    const double nu = assemble_generator<TL, true>(S, P, params + b * P.n_params, lane);
-    // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
-    if (!(nu * span < 1e5)) {
-        if (lane < 4) R[NA * 32 + 48 + lane] = nan("");
-        if (lane == 0 && cost != nullptr) cost[b] = 0.f;
-        return;
+    double nu;
+    if (P.lin_rows > 0) {
+        // ---- K1 as a linear program (compiled once per plan, eml_capi.cu): every entry of G, jw, kd is a gather over the
+        //      transformed parameters c_p (coupling strengths squared, reference basic_model.py:245,247) -- independent
+        //      accumulations, rows of similar length in one pass of the warp
+        const double* const prow = params + b * P.n_params;
+        for (int i = lane; i < P.n_params; i += 32) { const double v = prow[i]; S.par[i] = P.lin_sq[i] ? v * v : v; }
+        double* const Y = &S.G_re[0][0];
+        static_assert(offsetof(Scratch, G_im) == sizeof(double) * D * (D + 1) && offsetof(Scratch, par) == sizeof(double) * 2 * D * (D + 1) &&
+                      offsetof(Scratch, jw) == sizeof(double) * prep_off_jw(D, 0) && offsetof(Scratch, kd) == sizeof(double) * prep_off_kd(D, 0),
+                      "the linear program addresses the scratch by these offsets");
+        for (int i = lane; i < 2 * D * (D + 1); i += 32) Y[i] = 0.0;
+        S.jw[lane] = 0.0;
+        if (lane < 8) S.kd[lane] = 0.0;
+        __syncwarp();
+        for (int i = lane; i < P.lin_rows; i += 32) {
+            const LinRow rw = lin_row[i];
+            double acc = 0.0;
+            for (int k = rw.begin; k < rw.end; ++k) {
+                const LinEntry e = lin_ent[k];
+                acc = fma(e.val, S.par[e.col], acc);
+            }
+            Y[rw.offset] = acc;
+        }
+        __syncwarp();
+        // norm bound for the guard below: 2 max row sum (|re| + |im|) of G + the jump part, NaNs carried along
+        double rs = 0.0;
+        if (lane < D)
+            for (int c = 0; c < D; ++c) rs += fabs(S.G_re[lane][c]) + fabs(S.G_im[lane][c]);
+        double jp = 0.0;
+        if (lane < N) {
+            for (int a = 0; a < 2; ++a)
+                for (int bb = 0; bb < 2; ++bb)
+                    jp = fmax(jp, fabs(S.jw[lane * 8 + a * 2 + bb]) + fabs(S.jw[lane * 8 + 4 + (1 - a) * 2 + (1 - bb)]));
+        }
+        double mx = rs, sum = rs + jp;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            jp += __shfl_xor_sync(0xffffffffu, jp, o);
+        }
+        nu = 2.0 * mx + jp + 0.0 * sum;
+    } else {
+        nu = assemble_generator<TL, true>(S, P, params + b * P.n_params, lane);
     }
     // ---- record: A fragments with the permuted k index (PARITY: only the diagonal tiles, kept in ks = 0, 1), weights
 #pragma unroll
@@ -394,7 +450,7 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
     R[NA * 32 + lane] = S.jw[lane];
     if (lane < 16) R[NA * 32 + 32 + lane] = (lane < D) ? S.G_re[lane][lane] : 0.0;
     // ---- spectral enclosure
-    double spread, dlo, dhi, dasym;
+    double spread;
     {
         double hi = -1e300, lo = 1e300;
         if (lane < D) {
@@ -462,17 +518,26 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
         spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
-        cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
     }
-    const ChebPlan plan = cheb_make_plan(spread, dlo, dhi, dasym, span, cheb_zcap, kcap);
-    if (lane == 0) {
-        R[NA * 32 + 48] = plan.R; R[NA * 32 + 49] = plan.S; R[NA * 32 + 50] = plan.ac; R[NA * 32 + 51] = plan.tau_max;
-        if (cost != nullptr) {
-            // generator applications: one macro step when the span fits (exact), else about span / tau_max full steps
-            const double steps = ceil(span / plan.tau_max);
-            const int k1 = min(cheb_terms(fmin(span, plan.tau_max) * plan.S), kcap);
-            cost[b] = (float)(fmax(steps, 1.0) * (double)k1);
+    // a non-finite generator (NaN / inf parameters) or an absurd step count must not hang the device
+    if (!(nu * span < 1e5)) {
+        if (lane < 4) R[NA * 32 + 48 + lane] = nan("");
+        if (lane == 0 && cost != nullptr) cost[b] = 0.f;
+    } else {
+        double dlo, dhi, dasym;
+        cheb_site_ranges_warp(S.jw, S.kd, N, lane, dlo, dhi, dasym);
+        const ChebPlan plan = cheb_make_plan_warp(spread, dlo, dhi, dasym, span, cheb_zcap, kcap, lane);
+        if (lane == 0) {
+            R[NA * 32 + 48] = plan.R; R[NA * 32 + 49] = plan.S; R[NA * 32 + 50] = plan.ac; R[NA * 32 + 51] = plan.tau_max;
+            if (cost != nullptr) {
+                // generator applications: one macro step when the span fits (exact), else about span / tau_max full steps
+                const double steps = ceil(span / plan.tau_max);
+                const int k1 = min(cheb_terms(fmin(span, plan.tau_max) * plan.S), kcap);
+                cost[b] = (float)(fmax(steps, 1.0) * (double)k1);
+            }
         }
+    }
+    __syncwarp();      // the scratch is reused by this warp's next model
     }
 }
 
@@ -503,7 +568,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     // flip already was), the lane shuffles are unchanged.
     auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Scratch = WarpScratch<TL, CHEB, SB>;
+    using Scratch = WarpScratch<TL, CHEB, SB, PARITY>;
     constexpr int NTR = Scratch::NTR;
     Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -987,9 +1052,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 if constexpr (PARITY) {
                     // the observed site's bits are (I ^ p, J ^ p), p = parity of the (equal) low bits of row and column
                     const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
-                    const double w2 = gp ? xr[1][0][1] : xr[1][0][0], w3 = gp ? xi[1][0][1] : xi[1][0][0];
+                    // (tile (1,0) is the conjugate transpose of tile (0,1); a partial-trace element sits on its tile's diagonal)
                     const double a0 = v0, a1 = v1;
-                    v0 = pl ? a1 : a0; v1 = pl ? a0 : a1; v2 = pl ? w2 : v2; v3 = pl ? w3 : v3;
+                    v0 = pl ? a1 : a0; v1 = pl ? a0 : a1; v3 = pl ? neg(v3) : v3;
                 }
                 const bool hb = g & 4, mb = g & 2;
                 const double r0 = shfl(hb ? v0 : v2, dl4), r1 = shfl(hb ? v1 : v3, dl4);
@@ -1069,20 +1134,36 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     cscale = exp(-ac * tau_end) / (2.0 * ssum + jn);
                     __syncwarp();
                 }
-                if constexpr (SB) {
-                // ---- sector variant: the STATE is tile (0,1) alone (m); tile (1,0) = m^dag (n) is kept only as an operand:
-                //      w01 = J(v)01 + G00 m + m G11^dag + (previous term).  Every site flip maps tile (0,1) <-> (1,0) in the
-                //      parity coordinates, so the flip stencils read n; G00 m takes B = conj(n) from the lane's own registers,
-                //      m G11^dag takes A = m from the lane's own registers (k index permuted as for G's A fragments, whose
-                //      registers are also the B fragments of G11^dag).  No X' + X'^dag pass, half the stencil work, weights
-                //      unhalved; the new n = w01^dag goes through a double-buffered 1 KB tile in shared memory.
+                if constexpr (PARITY) {
+                // ---- parity coordinates: rho is Hermitian, so the odd tile (1,0) is the conjugate transpose of tile (0,1) and
+                //      the even tiles (0,0), (1,1) are Hermitian themselves.  The STATE is  m = tile (0,1)  and, unless the
+                //      even sector is steady (SB),  d[I] = tile (I,I);  n = m^dag is kept only as an operand.
+                //      Odd tile:  w01 = J(v)01 + G00 m + m G11^dag + (previous term).  Every site flip maps tile (0,1) <-> (1,0),
+                //      so the flip stencils read n; G00 m takes B = conj(n) from the lane's own registers, m G11^dag takes
+                //      A = m from the lane's own registers (k index permuted as for G's A fragments, whose registers are also
+                //      the B fragments of G11^dag): no X' + X'^dag pass, the new n = w01^dag goes through shared memory.
+                //      Even tiles:  w[I] = X' + X'^dag,  X' = J(v)[I][I]/2 + G[I][I] d[I]  (B = conj(d[I]) = own registers; the flips
+                //      read d[I ^ 1]); X'^dag comes back through the same shared-memory transposition.
                 double m_re[2] = {acc_re[0][1][0], acc_re[0][1][1]}, m_im[2] = {acc_im[0][1][0], acc_im[0][1][1]};
                 double n_re[2], nn_im[2], p_re[2] = {0.0, 0.0}, p_im[2] = {0.0, 0.0};      // n = n_re - i nn_im
                 acc_re[0][1][0] = acc_re[0][1][1] = acc_im[0][1][0] = acc_im[0][1][1] = 0.0;
+                [[maybe_unused]] double d_re[2][2], d_im[2][2], q_re[2][2], q_im[2][2];     // [I][e]; q = previous term, halved
+                if constexpr (!SB) {
+#pragma unroll
+                    for (int I = 0; I < 2; ++I)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            d_re[I][e] = acc_re[I][I][e]; d_im[I][e] = acc_im[I][I][e];
+                            q_re[I][e] = q_im[I][e] = 0.0;
+                            acc_re[I][I][e] = acc_im[I][I][e] = 0.0;
+                        }
+                }
                 // transposition tile: element (R, C) of a plane at 2 pi + (R & 1), pi = 8 h + (a & 1) + 2 ((C >> 1) ^ h),
                 // a = R >> 1, h = 2 (C & 1) + (a >> 1): the STS.64 of the accumulator fragments (R = g, C = 2t + e) and the
                 // LDS.128 of the transposed pairs (R = 2t, 2t + 1; C = g) are both bank-conflict free.  Planes re | im of 64
-                // doubles, two buffers (term k uses buffer k & 1, so one __syncwarp per application suffices).
+                // doubles per tile (odd tile, then the two even tiles), two buffers (term k uses buffer k & 1, so one
+                // __syncwarp per application suffices).
+                constexpr int XBUF = SB ? 128 : 384;
                 auto xt_addr = [](const int R, const int C) {
                     const int a = R >> 1, h = 2 * (C & 1) + (a >> 1);
                     return 2 * (8 * h + (a & 1) + 2 * ((C >> 1) ^ h)) + (R & 1);
@@ -1090,31 +1171,86 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 double* const xs0 = S.xt_re + xt_addr(g, 2 * t), * const xs1 = S.xt_re + xt_addr(g, 2 * t + 1);
                 const double* const xl = S.xt_re + xt_addr(2 * t, g);
                 auto transpose_conj = [&](const int buf) {      // n = m^dag
-                    xs0[buf * 128] = m_re[0]; xs1[buf * 128] = m_re[1];
-                    xs0[buf * 128 + 64] = m_im[0]; xs1[buf * 128 + 64] = m_im[1];
+                    xs0[buf * XBUF] = m_re[0]; xs1[buf * XBUF] = m_re[1];
+                    xs0[buf * XBUF + 64] = m_im[0]; xs1[buf * XBUF + 64] = m_im[1];
                     __syncwarp();
-                    const double2 cr = *reinterpret_cast<const double2*>(xl + buf * 128);
-                    const double2 ci = *reinterpret_cast<const double2*>(xl + buf * 128 + 64);
+                    const double2 cr = *reinterpret_cast<const double2*>(xl + buf * XBUF);
+                    const double2 ci = *reinterpret_cast<const double2*>(xl + buf * XBUF + 64);
                     n_re[0] = cr.x; n_re[1] = cr.y; nn_im[0] = ci.x; nn_im[1] = ci.y;
                 };
                 __syncwarp();
                 transpose_conj(1);
-                auto application = [&](const int k, auto na_tag, auto first_tag) {
-                    constexpr bool NA = decltype(na_tag)::value, FIRST = decltype(first_tag)::value;
-                    trace_store_sb(m_re, m_im, k);
-                    if constexpr (NA) {
-                        const double c = cJ[k] * cscale;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            acc_re[0][1][e] = fma(c, m_re[e], acc_re[0][1][e]);
-                            acc_im[0][1][e] = fma(c, m_im[e], acc_im[0][1][e]);
-                        }
-                    }
-                    double x_re[2], x_im[2];
+                // flip stencils of the lane-bit sites and of the observed site onto (ar, ai): sources (sr, -si), weights F, f2, f1, f0
+                auto flips = [&](double (&ar)[2], double (&ai)[2], const double (&sr)[2], const double (&si)[2], const double (&F)[FE],
+                                 const bool neg_im) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        x_re[e] = fma(W0[0][1][e], m_re[e], p_re[e]);
-                        x_im[e] = fma(W0[0][1][e], m_im[e], p_im[e]);
+                        ar[e] = fma(F[e], sr[e], ar[e]);
+                        ai[e] = fma(F[e], neg_im ? -si[e] : si[e], ai[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double hr = __shfl_xor_sync(0xffffffffu, sr[e], 18), hi = __shfl_xor_sync(0xffffffffu, si[e], 18);
+                        ar[e] = fma(f2, hr, ar[e]); ai[e] = fma(f2, neg_im ? -hi : hi, ai[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double hr = __shfl_xor_sync(0xffffffffu, sr[e], 9), hi = __shfl_xor_sync(0xffffffffu, si[e], 9);
+                        ar[e] = fma(f1, hr, ar[e]); ai[e] = fma(f1, neg_im ? -hi : hi, ai[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double hr = __shfl_xor_sync(0xffffffffu, sr[e ^ 1], 4), hi = __shfl_xor_sync(0xffffffffu, si[e ^ 1], 4);
+                        ar[e] = fma(f0[e], hr, ar[e]); ai[e] = fma(f0[e], neg_im ? -hi : hi, ai[e]);
+                    }
+                };
+                auto trace_put = [&](const int k) {
+                    if constexpr (SB) {
+                        trace_store_sb(m_re, m_im, k);
+                    } else {
+                        // rho00, rho11 from the even tiles, rho01 from tile (0,1) (conjugated where the parity of the low bits is odd)
+                        const bool pl = (g ^ (g >> 1) ^ (g >> 2)) & 1;
+                        const double a0 = gp ? d_re[0][1] : d_re[0][0], a1 = gp ? d_re[1][1] : d_re[1][0];
+                        const double v0 = pl ? a1 : a0, v1 = pl ? a0 : a1;
+                        const double v2 = gp ? m_re[1] : m_re[0], a3 = gp ? m_im[1] : m_im[0];
+                        const double v3 = pl ? neg(a3) : a3;
+                        const bool hb = g & 4, mb = g & 2;
+                        const double r0 = shfl(hb ? v0 : v2, dl4), r1 = shfl(hb ? v1 : v3, dl4);
+                        const double k0 = (hb ? v2 : v0) + r0, k1 = (hb ? v3 : v1) + r1;
+                        const double kk = (mb ? k1 : k0) + shfl(mb ? k0 : k1, dl2);
+                        tr_put(k, kk + shfl(kk, dl1));
+                    }
+                };
+                auto accumulate = [&](const int k) {
+                    const double c = cJ[k] * cscale;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        acc_re[0][1][e] = fma(c, m_re[e], acc_re[0][1][e]);
+                        acc_im[0][1][e] = fma(c, m_im[e], acc_im[0][1][e]);
+                        if constexpr (!SB) {
+#pragma unroll
+                            for (int I = 0; I < 2; ++I) {
+                                acc_re[I][I][e] = fma(c, d_re[I][e], acc_re[I][I][e]);
+                                acc_im[I][I][e] = fma(c, d_im[I][e], acc_im[I][I][e]);
+                            }
+                        }
+                    }
+                };
+                auto application = [&](const int k, auto na_tag, auto first_tag) {
+                    constexpr bool NA = decltype(na_tag)::value, FIRST = decltype(first_tag)::value;
+                    trace_put(k);
+                    if constexpr (NA) accumulate(k);
+                    // ---- odd tile
+                    double x_re[2], x_im[2];
+                    if constexpr (SB) {      // weights unhalved: the stencils accumulate straight into x
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[e] = fma(W0[0][1][e], m_re[e], p_re[e]);
+                            x_im[e] = fma(W0[0][1][e], m_im[e], p_im[e]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) { x_re[e] = p_re[e]; x_im[e] = p_im[e]; }
                     }
                     // m G11^dag: A = m (own registers), B = conj of G11's A fragment -- independent of n, issued first
 #pragma unroll
@@ -1126,25 +1262,15 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         dmma(x_re[0], x_re[1], m_im[ks], a_im[1][ks]);
                         dmma(x_im[0], x_im[1], m_re[ks], -a_im[1][ks]);
                     }
+                    if constexpr (SB) {
+                        flips(x_re, x_im, n_re, nn_im, F3[0][1], true);
+                    } else {                 // weights halved (the even tiles need them so): J(v)01 = 2 s
+                        double s_re[2], s_im[2];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        x_re[e] = fma(F3[0][1][e], n_re[e], x_re[e]);
-                        x_im[e] = fma(F3[0][1][e], -nn_im[e], x_im[e]);
-                    }
+                        for (int e = 0; e < 2; ++e) { s_re[e] = W0[0][1][e] * m_re[e]; s_im[e] = W0[0][1][e] * m_im[e]; }
+                        flips(s_re, s_im, n_re, nn_im, F3[0][1], true);
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        x_re[e] = fma(f2, __shfl_xor_sync(0xffffffffu, n_re[e], 18), x_re[e]);
-                        x_im[e] = fma(f2, -__shfl_xor_sync(0xffffffffu, nn_im[e], 18), x_im[e]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        x_re[e] = fma(f1, __shfl_xor_sync(0xffffffffu, n_re[e], 9), x_re[e]);
-                        x_im[e] = fma(f1, -__shfl_xor_sync(0xffffffffu, nn_im[e], 9), x_im[e]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        x_re[e] = fma(f0[e], __shfl_xor_sync(0xffffffffu, n_re[e ^ 1], 4), x_re[e]);
-                        x_im[e] = fma(f0[e], -__shfl_xor_sync(0xffffffffu, nn_im[e ^ 1], 4), x_im[e]);
+                        for (int e = 0; e < 2; ++e) { x_re[e] = fma(2.0, s_re[e], x_re[e]); x_im[e] = fma(2.0, s_im[e], x_im[e]); }
                     }
                     // G00 m: B = conj(n) from the lane's own registers
 #pragma unroll
@@ -1156,31 +1282,68 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         dmma(x_re[0], x_re[1], a_im[0][ks], -nn_im[ks]);
                         dmma(x_im[0], x_im[1], a_im[0][ks], n_re[ks]);
                     }
-                    // T_2 = (2 At) T_1 + 2 T_0, afterwards T_{k+1} = (2 At) T_k + T_{k-1}
+                    // ---- even tiles
+                    [[maybe_unused]] double y_re[2][2], y_im[2][2];
+                    if constexpr (!SB) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                y_re[I][e] = fma(W0[I][I][e], d_re[I][e], q_re[I][e]);
+                                y_im[I][e] = fma(W0[I][I][e], d_im[I][e], q_im[I][e]);
+                            }
+                            flips(y_re[I], y_im[I], d_re[I ^ 1], d_im[I ^ 1], F3[I][I], false);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                if (!REAL_H) {
+                                    dmma(y_re[I][0], y_re[I][1], a_re[I][ks], d_re[I][ks]);
+                                    dmma(y_im[I][0], y_im[I][1], a_re[I][ks], -d_im[I][ks]);
+                                }
+                                dmma(y_re[I][0], y_re[I][1], a_im[I][ks], d_im[I][ks]);
+                                dmma(y_im[I][0], y_im[I][1], a_im[I][ks], d_re[I][ks]);
+                            }
+                        }
+                    }
+                    // T_2 = (2 At) T_1 + 2 T_0, afterwards T_{k+1} = (2 At) T_k + T_{k-1}  (q is kept halved: X' + X'^dag doubles it)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         p_re[e] = FIRST ? 2.0 * m_re[e] : m_re[e]; p_im[e] = FIRST ? 2.0 * m_im[e] : m_im[e];
                         m_re[e] = x_re[e]; m_im[e] = x_im[e];
                     }
-                    transpose_conj(k & 1);
-                };
-                auto run_terms_sb = [&](auto na_tag) {
-                    application(0, na_tag, std::true_type{});
-#pragma unroll 2
-                    for (int k = 1; UNI(k < Kc); ++k) application(k, na_tag, std::false_type{});
-                    trace_store_sb(m_re, m_im, Kc);          // the last term
-                    if constexpr (decltype(na_tag)::value) {
-                        const double c = cJ[Kc] * cscale;
+                    const int buf = k & 1;
+                    if constexpr (!SB) {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            acc_re[0][1][e] = fma(c, m_re[e], acc_re[0][1][e]);
-                            acc_im[0][1][e] = fma(c, m_im[e], acc_im[0][1][e]);
+                        for (int I = 0; I < 2; ++I) {
+                            xs0[buf * XBUF + 128 * (1 + I)] = y_re[I][0]; xs1[buf * XBUF + 128 * (1 + I)] = y_re[I][1];
+                            xs0[buf * XBUF + 128 * (1 + I) + 64] = y_im[I][0]; xs1[buf * XBUF + 128 * (1 + I) + 64] = y_im[I][1];
+                        }
+                    }
+                    transpose_conj(buf);
+                    if constexpr (!SB) {
+#pragma unroll
+                        for (int I = 0; I < 2; ++I) {
+                            const double2 tr_ = *reinterpret_cast<const double2*>(xl + buf * XBUF + 128 * (1 + I));
+                            const double2 ti_ = *reinterpret_cast<const double2*>(xl + buf * XBUF + 128 * (1 + I) + 64);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                q_re[I][e] = FIRST ? d_re[I][e] : 0.5 * d_re[I][e]; q_im[I][e] = FIRST ? d_im[I][e] : 0.5 * d_im[I][e];
+                            }
+                            d_re[I][0] = y_re[I][0] + tr_.x; d_re[I][1] = y_re[I][1] + tr_.y;
+                            d_im[I][0] = y_im[I][0] - ti_.x; d_im[I][1] = y_im[I][1] - ti_.y;
                         }
                     }
                 };
-                if (need_acc) run_terms_sb(std::true_type{}); else run_terms_sb(std::false_type{});
+                auto run_terms_par = [&](auto na_tag) {
+                    application(0, na_tag, std::true_type{});
+#pragma unroll 2
+                    for (int k = 1; UNI(k < Kc); ++k) application(k, na_tag, std::false_type{});
+                    trace_put(Kc);          // the last term
+                    if constexpr (decltype(na_tag)::value) accumulate(Kc);
+                };
+                if (need_acc) run_terms_par(std::true_type{}); else run_terms_par(std::false_type{});
                 {   // a non-finite or absurd last term means the enclosure failed: report instead of returning garbage
-                    const double chk = fabs(m_re[0]) + fabs(m_im[0]) + fabs(m_re[1]);
+                    double chk = fabs(m_re[0]) + fabs(m_im[0]) + fabs(m_re[1]);
+                    if constexpr (!SB) chk += fabs(d_re[0][0]) + fabs(d_re[1][1]);
                     if (!UNI(chk < 1e300)) capped = true;
                 }
                 } else {
@@ -1556,7 +1719,7 @@ static cudaError_t init_inv_table() {
 
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
                           unsigned int*, const int*, const double*);
-using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, const double, const int);
+using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, const double, const int, const int);
 
 struct WarpVariant {
     WarpKern eval = nullptr;
@@ -1568,8 +1731,8 @@ template <int TL, bool RH, bool CH, bool PA, bool SB>
 static WarpVariant make_variant() {
     WarpVariant v;
     v.eval = (WarpKern)eval_warp_mma_kernel<TL, RH, CH, PA, SB>;
-    v.smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH, SB>);
-    v.kcap = WarpScratch<TL, CH, SB>::KCAP;
+    v.smem = WARPS_PER_CTA * sizeof(WarpScratch<TL, CH, SB, PA>);
+    v.kcap = WarpScratch<TL, CH, SB, PA>::KCAP;
     v.id = (SB ? 16 : 0) + (PA ? 8 : 0) + (TL == 2 ? 4 : 0) + (CH ? 2 : 0) + (RH ? 1 : 0);
     if constexpr (CH) {
         v.prep = (PrepKern)prepare_models_kernel<TL, RH, PA>;
@@ -1616,7 +1779,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     if (per_sm == 0) {
         if ((e = cudaFuncSetAttribute(v.eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem)) != cudaSuccess) return e;
         if (v.prep != nullptr &&
-            (e = cudaFuncSetAttribute(v.prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.prep_smem)) != cudaSuccess) return e;
+            (e = cudaFuncSetAttribute(v.prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(v.prep_smem + PREP_LIN_STAGE_MAX))) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.eval, WARPS_PER_CTA * 32, v.smem)) != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (dev < 64) per_sm_cache[dev][v.id] = per_sm;
@@ -1641,8 +1804,16 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         const bool sort = order != nullptr && n > (long long)WARPS_PER_CTA * max_ctas && n <= ORDER_MAX_MODELS;
         float* cost = (order != nullptr && n <= ORDER_MAX_MODELS) ? reinterpret_cast<float*>(order + ORDER_MAX_MODELS) : nullptr;
         if (chebyshev) {
-            v.prep<<<(unsigned)((n + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, v.prep_smem, stream>>>(
-                P, n, p_, prep_ws, sort ? cost : nullptr, zcap, v.kcap);
+            // persistent CTAs (the staged linear program is loaded once per CTA); as many as fit the device
+            const size_t lin_bytes = (size_t)(P.lin_rows + P.lin_nnz) * 16;
+            const int stage = (P.lin_rows > 0 && lin_bytes <= (size_t)PREP_LIN_STAGE_MAX) ? 1 : 0;
+            const size_t psmem = v.prep_smem + (stage ? lin_bytes : 0);
+            int prep_per_sm = (int)((size_t)(227 * 1024) / (psmem + 1024));
+            if (prep_per_sm > 16 / (PREP_WARPS / 4)) prep_per_sm = 16 / (PREP_WARPS / 4);      // 64 warps per SM at most
+            if (prep_per_sm < 1) prep_per_sm = 1;
+            long long pctas = (n + PREP_WARPS - 1) / PREP_WARPS;
+            if (pctas > (long long)sms * prep_per_sm) pctas = (long long)sms * prep_per_sm;
+            v.prep<<<(unsigned)pctas, PREP_WARPS * 32, psmem, stream>>>(P, n, p_, prep_ws, sort ? cost : nullptr, zcap, v.kcap, stage);
             if (sort) order_models_kernel<<<1, 1024, 0, stream>>>((int)n, cost, order);
         } else if (sort) {
             launch_model_order(P, n, p_, order, cost_hint ? cost_hint + off : nullptr, stream);

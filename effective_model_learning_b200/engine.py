@@ -256,7 +256,15 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
         mma = (2.0 if kernel_name.endswith('realH') else 4.0) * 2.0 * d ** 3
         if 'parity' in kernel_name:      # H block diagonal by parity: only the diagonal tiles of G are multiplied
             mma *= 0.5
-        if 'sector' in kernel_name:      # only the parity-odd tiles of rho are evolved: half of everything
-            return 0.5 * (mma + d * d * (2.0 + 4.0 * n_tls + 6.0))
+        if kernel_name.startswith('warp_cheb_parity'):
+            # d = 16 parity variants (round 2): the state is tile (0,1) (its conjugate transpose is only an operand) plus,
+            # without the sector reduction, the two Hermitian even tiles.  Odd tile, per complex element (64 of them):
+            # diagonal weight and 4 site flips; G00 m and m G11^dag together are the same DMMA count as before.
+            quarter = d * d / 4.0
+            if 'sector' in kernel_name:      # weights unhalved, everything fused: 2 FMA + 4 x 2 FMA = 20 flop per element
+                return 0.5 * mma + quarter * (4.0 + 4.0 * n_tls)
+            # full state: odd tile 2 MUL + 8 FMA + the doubling FMA pair = 22 flop; even tiles (2 x 64 elements) 10 FMA,
+            # X' + X'^dag 2 ADD, halving of the stored term 2 MUL = 24 flop
+            return mma + quarter * (2.0 + 4.0 * n_tls + 4.0) + 2.0 * quarter * (4.0 + 4.0 * n_tls + 4.0)
         return mma + d * d * (2.0 + 4.0 * n_tls + 6.0)
     raise RuntimeError('unknown kernel ' + kernel_name)

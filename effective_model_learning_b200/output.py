@@ -11,14 +11,20 @@ downstream analysis scripts (clustering, collation) find what they expect:
   ..._accepted_log_likelihood_prior.pickle, _AP.pickle, _accepted_AP.pickle
 
 Models hold numpy arrays instead of qutip.Qobj, so the pickles load without qutip (they need this package).
+With `reference_module_names=True` the model classes are pickled under the reference's flat module names
+(`learning_model.LearningModel`, ...), which is what the reference's analysis scripts look up (find_clusters.py:71-90);
+`compat.install_reference_aliases()` makes those names resolve to this package.
 The reference's svg figures are drawn only when matplotlib is importable; it is not part of this image and the
 figures are not part of the data contract.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import pickle
 import pprint
+
+from . import compat
 
 
 class Output:
@@ -28,7 +34,7 @@ class Output:
                  dynamics_datasets_labels=None, dynamics_formatting=False, observable_labels=None, loss=None,
                  acceptance_probability=None, best_loss=None, acceptance=None, overall_acceptance=False,
                  models_to_save=None, model_names=None, all_proposals=None, chain_hyperparams=False,
-                 chain_name=False, fontsize=False):
+                 chain_name=False, fontsize=False, reference_module_names: bool = False):
         loss = [] if loss is None else loss
         acceptance_probability = [] if acceptance_probability is None else acceptance_probability
         models_to_save = [] if models_to_save is None else models_to_save
@@ -37,9 +43,11 @@ class Output:
         on = lambda name: bool(getattr(toggles, name, False))   # noqa: E731
         self.written = []
 
+        naming = compat.reference_module_names if reference_module_names else contextlib.nullcontext
+
         def dump(path, obj, binary=True):
             if binary:
-                with open(path, 'wb') as f:
+                with open(path, 'wb') as f, naming():
                     pickle.dump(obj, f)
             else:
                 with open(path, 'w') as f:

@@ -1,0 +1,139 @@
+"""
+The batched RJMCMC engine (csrc/eml_chains.cu) tied to the single-chain drop-in `LearningChain`
+(reference learning_chain.py:346-596) -- beyond the step-by-step agreement with tests/chain_reference.py:
+
+ 1. the proposal kernel's Metropolis-Hastings correction  prior(prop)/prior(cur) * p_back/p_there  is recomputed for the
+    device's own (current, proposal) pairs with LearningChain's methods (_xi_product: truncated-Gaussian normalisers,
+    learning_chain.py:454-487, 979-994; _move_weights / priorities for jump moves, :493-498; prior, :847-853);
+ 2. populations of host chains (np.random streams, the reference's loop) and device chains (counter-based streams) on the
+    same targets and hyperparameters agree in distribution: move-type frequencies, acceptance per step class, model
+    complexity, window acceptance ratios and the loss quantiles after the same number of proposals.
+"""
+import numpy as np
+import pytest
+import torch
+
+import effective_model_learning_b200 as eml
+from effective_model_learning_b200 import BatchedChains, configs, definitions
+from effective_model_learning_b200.chains import MOVES
+from oracle import lindblad_oracle as lo
+from tests.helpers import OBS3
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(D, n_times=40):
+    cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    cfg['iterations_till_progress_update'] = False
+    cfg['shock_anneal_at'] = False
+    ts = np.linspace(0, 2.5, n_times)
+    truth = lo.random_library_spec(np.random.default_rng(20260000 + 10 + D), 1, D)
+    targets = np.array([np.asarray(e) for e in lo.expect_exact(truth, ts, OBS3)])
+    targets = targets + np.random.default_rng(5).normal(0, 0.01, targets.shape)
+    return cfg, ts, targets
+
+
+def _host_chain(cfg, ts, targets, D, steps):
+    return eml.LearningChain(target_times=ts, target_datasets=[t for t in targets], target_observables=OBS3,
+                             initial=(1, D), qubit_initial_state=definitions.ops['plus'],
+                             defect_initial_state=definitions.ops['mm'], max_chain_steps=steps, **cfg)
+
+
+def test_device_mh_correction_equals_learning_chain_formulas():
+    D, C, steps = 2, 48, 80
+    cfg, ts, targets = _problem(D)
+    cfg['jump_length_rescaling_factor'] = 1.0          # constant jump lengths: the normalisers use the initial ones
+    cfg['temperature_proposal'] = 0.02
+    cfg['chain_step_options'] = {m: (4 if m == MOVES[0] else 1) for m in MOVES}
+    eng = BatchedChains(ts, targets, OBS3, n_chains=C, n_defects=D, seed=77, defect_initial_state=definitions.ops['mm'], **cfg)
+    lc = _host_chain(cfg, ts, targets, D, 1)
+    state0 = eng.read()
+    P = eng.layout.n_params
+    hist = {'loss': torch.zeros((steps, C), dtype=torch.float64, device='cuda'),
+            'aprob': torch.zeros((steps, C), dtype=torch.float64, device='cuda'),
+            'code': torch.zeros((steps, C), dtype=torch.int32, device='cuda'),
+            'params': torch.zeros((steps, C, P), dtype=torch.float64, device='cuda')}
+    eng.run(steps, history=hist)
+    torch.cuda.synchronize()
+    loss, aprob, code, params = (hist[k].cpu().numpy() for k in ('loss', 'aprob', 'code', 'params'))
+    qs, dstate = eng.ctx.site_states[0], eng.ctx.site_states[-1]
+    T = cfg['temperature_proposal']
+    checked = {m: 0 for m in MOVES}
+    for c in range(C):
+        cur, cur_loss = state0['current_params'][c].copy(), float(state0['current_loss'][c])
+        for s in range(steps):
+            if code[s, c] & 1:
+                prop, move = params[s, c], MOVES[code[s, c] >> 1]
+                m_cur = eng.layout.model_from_params(cur, qs, dstate)
+                m_prop = eng.layout.model_from_params(prop, qs, dstate)
+                if move == 'tweak all parameters':
+                    p_there, p_back = lc._xi_product(m_prop), lc._xi_product(m_cur)
+                else:
+                    p_there = lc.next_step_priorities_dict[move] / sum(lc._move_weights(m_cur))
+                    p_back = lc.next_step_priorities_dict[lc.complementary_step(move)] / sum(lc._move_weights(m_prop))
+                want = np.exp(-(loss[s, c] - cur_loss) / T) * lc.prior(m_prop) / lc.prior(m_cur) * p_back / p_there
+                assert aprob[s, c] == pytest.approx(want, rel=1e-6), (c, s, move)
+                checked[move] += 1
+                cur, cur_loss = prop.copy(), float(loss[s, c])
+            else:
+                assert np.array_equal(params[s, c], cur)
+    assert checked['tweak all parameters'] > 200 and sum(v > 0 for v in checked.values()) >= 6, checked
+    eng.close()
+
+
+def test_device_chains_and_host_chains_agree_in_distribution():
+    D, steps, n_host, n_dev = 1, 200, 64, 2048
+    cfg, ts, targets = _problem(D)
+    cfg['jump_length_rescaling_factor'] = 1.2
+    cfg['acceptance_window'] = 10
+    cfg['temperature_proposal'] = 0.005
+    cfg['chain_step_options'] = {m: (6 if m == MOVES[0] else 1) for m in MOVES}
+    # ---- host population: the reference's loop on np.random, one seed per chain
+    h_moves = {m: 0 for m in MOVES}
+    h_counts = np.zeros(4)
+    h_loss, h_best, h_nproc, h_windows = [], [], [], []
+    for c in range(n_host):
+        np.random.seed(4000 + c)
+        chain = _host_chain(cfg, ts, targets, D, steps - 1)      # `while i <= steps` makes steps proposals
+        with np.errstate(over='ignore'):
+            chain.run()
+        for m in chain.run_step_type_tracker:
+            h_moves[m] += 1
+        h_counts += [chain.tot_RJ_steps, chain.acc_RJ_steps, chain.tot_tweak_steps, chain.acc_tweak_steps]
+        h_loss.append(chain.current_loss)
+        h_best.append(chain.best_loss)
+        ph = chain.process_handler
+        h_nproc.append(ph.count_Ls(chain.current) + ph.count_defect2defect_couplings(chain.current)
+                       + ph.count_qubit2defect_couplings(chain.current))
+        h_windows += list(chain.chain_windows_acceptance_log)
+    # ---- device population
+    eng = BatchedChains(ts, targets, OBS3, n_chains=n_dev, n_defects=D, seed=9, defect_initial_state=definitions.ops['mm'], **cfg)
+    code = torch.zeros((steps, n_dev), dtype=torch.int32, device='cuda')
+    eng.run(steps, history={'code': code})
+    st = eng.read()
+    code = code.cpu().numpy()
+    table = st['stats']
+    # move-type frequencies: binomial error of the (smaller) host sample, 5 sigma + a small absolute slack
+    n_h = sum(h_moves.values())
+    assert n_h == n_host * steps
+    for k, m in enumerate(MOVES):
+        p_h, p_d = h_moves[m] / n_h, float(np.mean((code >> 1) == k))
+        sigma = np.sqrt(max(p_d * (1 - p_d), 1e-6) / n_h)
+        assert abs(p_h - p_d) < 5 * sigma + 0.004, (m, p_h, p_d)
+    # acceptance per step class
+    acc_rj_h, acc_tw_h = h_counts[1] / h_counts[0], h_counts[3] / h_counts[2]
+    acc_rj_d = table[:, 4].sum() / table[:, 5].sum()
+    acc_tw_d = table[:, 2].sum() / table[:, 3].sum()
+    assert abs(acc_tw_h - acc_tw_d) < 0.04, (acc_tw_h, acc_tw_d)
+    assert abs(acc_rj_h - acc_rj_d) < 0.06, (acc_rj_h, acc_rj_d)
+    # model complexity and the acceptance-window ratios that drive the jump-length adaptation
+    assert abs(np.mean(h_nproc) - table[:, 7].mean()) < 0.6, (np.mean(h_nproc), table[:, 7].mean())
+    assert abs(np.mean(h_windows) - table[:, 6].mean()) < 0.06, (np.mean(h_windows), table[:, 6].mean())
+    # loss after the same number of proposals (it fell by ~2.5 orders of magnitude from the initial model): quantiles of
+    # log10(loss) within the sampling error of 64 host chains (bootstrap: ~0.1 per quantile, tools/chain_statistics.py)
+    for q in (0.25, 0.5, 0.75):
+        a, b = np.quantile(np.log10(h_best), q), np.quantile(np.log10(st['best_loss']), q)
+        assert abs(a - b) < 0.4, ('best loss quantile', q, a, b)
+        a, b = np.quantile(np.log10(h_loss), q), np.quantile(np.log10(st['current_loss']), q)
+        assert abs(a - b) < 0.45, ('current loss quantile', q, a, b)
+    eng.close()

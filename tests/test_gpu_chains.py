@@ -142,3 +142,51 @@ def test_checkpoint_resume_continues_exactly():
     with pytest.raises(RuntimeError):
         c = BatchedChains(ts, targets, OBS3, n_chains=41, n_defects=2, seed=1234, defect_initial_state=definitions.ops['mm'], **cfg)
         c.import_state(blob)
+
+
+def test_batched_chains_write_the_reference_output_files(tmp_path):
+    """
+    Scope row N3 from the batched engine: best models of device chains go through output.Output (the reference's file set,
+    output.py:79-128) under the reference's module names, and come back as models whose parameter vector under the
+    library (vectorise_under_library, basic_model.py:575-765) is the device's best row and whose dynamics reproduce its loss.
+    """
+    import json
+    import pickle
+    from effective_model_learning_b200 import compat, output
+    cfg, ts, targets, eng = _setup(2, 32)
+    eng.run(60)
+    state = eng.read()
+
+    class Toggles:
+        pickle = True
+        text = True
+        hyperparams = True
+
+    which = [0, 7, 31]
+    for c, best in zip(which, eng.best_models(which)):
+        st = state['stats'][c]
+        output.Output(toggles=Toggles, filename=str(tmp_path / f'sweep_D2_R{c + 1}'), models_to_save=[best], model_names=['best'],
+                      overall_acceptance={'RJ': st[4] / max(st[5], 1.0), 'tweak': st[2] / max(st[3], 1.0)},
+                      chain_hyperparams=cfg, chain_name='chain', reference_module_names=True)
+    compat.install_reference_aliases()
+    try:
+        for c in which:
+            base = str(tmp_path / f'sweep_D2_R{c + 1}')
+            with open(base + '_best.pickle', 'rb') as f:
+                m = pickle.load(f)
+            assert type(m).__module__.endswith('learning_model') and m.final_loss == state['best_loss'][c]
+            vals, labels, _ = m.vectorise_under_library(cfg)
+            want = [v for v, cls in zip(state['best_params'][c], eng.layout.classes) if cls != 'qubit_energy']
+            np.testing.assert_allclose(vals, want, rtol=0, atol=0)
+            loss = engine.evaluate_models([m], ts, OBS3, targets=targets)[1][0]
+            assert loss == pytest.approx(state['best_loss'][c], rel=1e-9)
+            acc = json.load(open(base + '_overall_acceptance.json'))
+            assert 0.0 <= acc['tweak'] <= 1.0
+            assert pickle.load(open(base + '_chain_hyperparameters.pickle', 'rb'))['complexity_factor'] == cfg['complexity_factor']
+            assert 'TLS' in open(base + '_best.txt').read() or len(open(base + '_best.txt').read()) > 20
+    finally:
+        import sys
+        for name in compat.FLAT_MODULES:
+            if getattr(sys.modules.get(name), '__name__', '').startswith('effective_model_learning_b200.'):
+                sys.modules.pop(name, None)
+    eng.close()

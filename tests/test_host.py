@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import scipy.linalg
 
 import effective_model_learning_b200 as eml
 from effective_model_learning_b200 import _native, configs, definitions, engine
@@ -257,3 +258,99 @@ def test_total_dev_paths_agree_and_wrap_single_dataset(oracle_backend):
         fused.step(truth, 'no such move')
     assert fused.complementary_step('add qubit L') == 'remove qubit L'
     assert fused.acceptance_probability((truth, 0.2), (truth, 0.1), 1.0, 1.0) > 1.0
+
+
+def test_build_Liouvillian_is_the_corrected_column_stacked_superoperator():
+    """
+    Scope row a10.  BasicModel.build_Liouvillian returns L = -i(I (x) H - H^T (x) I) + sum_c [conj(c) (x) c - 1/2 I (x) c^dag c
+    - 1/2 (c^dag c)^T (x) I] for vec with order='F' -- the superoperator qutip.liouvillian builds and mesolve integrates.
+    DELIBERATE DEVIATION from reference basic_model.py:285-310, which uses L.T @ L where the column-stacking convention
+    needs (L^dag L)^T and therefore is wrong for complex jump operators such as sigmay: for those the
+    reference's formula differs from the oracle, this one does not.
+    """
+    from oracle import lindblad_oracle as lo
+    from tests.helpers import model_from_spec, random_general_spec
+    for seed in range(6):
+        spec = random_general_spec(np.random.default_rng(700 + seed), 1 + seed % 3)
+        m = model_from_spec(spec)
+        L = m.build_Liouvillian()
+        want = lo.liouvillian(lo.build_H(spec), lo.build_c_ops(spec))
+        assert L.shape == want.shape and np.allclose(L, want, rtol=0, atol=1e-14)
+        assert m.Liouvillian is L
+        # it generates the dynamics the evaluation path reproduces: d vec(rho)/dt = L vec(rho)
+        rho0 = lo.build_rho0(spec)
+        v = scipy.linalg.expm(L * 0.3) @ rho0.ravel(order='F')
+        assert abs(np.trace(v.reshape(rho0.shape, order='F')) - np.trace(rho0)) < 1e-12
+    # the reference's own formula on a sigmay dissipator (what NOT to reproduce)
+    spec = {'tls': [{'is_qubit': True, 'energy': 1.0, 'Ls': {'sigmay': 0.3}, 'initial_state': None, 'couplings': []}]}
+    m = model_from_spec(spec)
+    H, c = m.H, m.Ls[0]
+    eye = np.eye(2)
+    ref_formula = (-1j * (np.kron(eye, H) - np.kron(H.T, eye)) + np.kron(c.conj(), c)
+                   - 0.5 * np.kron(eye, c.T @ c) - 0.5 * np.kron((c.T @ c).T, eye))       # L.T @ L as at basic_model.py:304-307
+    assert np.abs(ref_formula - m.build_Liouvillian()).max() > 0.1
+    empty = eml.BasicModel()
+    with pytest.raises(RuntimeError):
+        empty.build_Liouvillian()
+
+
+def test_reference_analysis_scripts_can_load_what_output_writes(oracle_backend, tmp_path):
+    """
+    Scope row N3, consumer side.  The reference's clustering scripts `import learning_model`, unpickle *_best.pickle /
+    *_proposals.pickle and call build_Liouvillian / vectorise_under_library / final_loss on the models
+    (find_clusters.py:71-90, cluster_accepted.py:42-58, models_params_corr_mat.py:38-56, collate.py:122-128).  Files written
+    with reference_module_names=True carry the reference's flat module names; a fresh interpreter that only installs the
+    aliases -- no import of the package's classes by their package path -- runs the consumers' statements on them.
+    """
+    import pickle
+    import subprocess
+    import sys
+    from effective_model_learning_b200 import output
+    config = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    config['iterations_till_progress_update'] = False
+    ts = np.linspace(0, 1.0, 12)
+    targets = [np.cos(2 * ts), np.sin(2 * ts), np.zeros_like(ts)]
+    np.random.seed(3)
+    chain = eml.LearningChain(target_times=ts, target_datasets=targets, target_observables=OBS3, initial=(1, 1),
+                              qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'],
+                              max_chain_steps=25, store_all_proposals=True, **config)
+    best = chain.run()
+
+    class Toggles:
+        pickle = True
+        all_proposals = True
+
+    base = str(tmp_path / 'run_D1_R1')
+    output.Output(toggles=Toggles, filename=base, models_to_save=[best], model_names=['best'],
+                  all_proposals=chain.all_proposals, reference_module_names=True)
+    raw = open(base + '_best.pickle', 'rb').read()
+    assert b'learning_model' in raw and b'effective_model_learning_b200' not in raw
+    assert type(best).__module__ == 'effective_model_learning_b200.learning_model'      # the renaming did not leak
+    consumer = '''
+import sys, pickle, json
+import numpy as np
+sys.path.insert(0, %r)
+from effective_model_learning_b200 import compat
+compat.install_reference_aliases()
+import learning_model, configs                      # what the reference's scripts import (find_clusters.py:13-20)
+with open(%r + '_best.pickle', 'rb') as filestream:
+    new_model = pickle.load(filestream)             # find_clusters.py:71-73
+assert type(new_model) is learning_model.LearningModel
+Liouvillian_mat = new_model.build_Liouvillian()     # find_clusters.py:84-87
+vect = np.concatenate((Liouvillian_mat.ravel().real, Liouvillian_mat.ravel().imag))
+hyperparams = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+with open(%r + '_proposals.pickle', 'rb') as filestream:
+    proposals = pickle.load(filestream)['proposals']    # models_params_corr_mat.py:38-39
+vectors = [p.vectorise_under_library(hyperparameters=hyperparams)[0] for p in proposals]
+print(json.dumps({'n': len(vect), 'loss': new_model.final_loss, 'proposals': len(vectors), 'width': len(vectors[0])}))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), base, base)
+    out = subprocess.run([sys.executable, '-c', consumer], capture_output=True, text=True, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout.strip().splitlines()[-1])
+    assert got['n'] == 2 * 16 * 16 and got['loss'] == pytest.approx(best.final_loss)
+    assert got['proposals'] == len(chain.all_proposals['proposals']) and got['width'] == 10
+    # and the default writer keeps the package path (loads wherever the package is importable, no aliases needed)
+    output.Output(toggles=Toggles, filename=base + '_pkg', models_to_save=[best], model_names=['best'])
+    with open(base + '_pkg_best.pickle', 'rb') as f:
+        again = pickle.load(f)
+    assert type(again) is type(best) and again.final_loss == best.final_loss
