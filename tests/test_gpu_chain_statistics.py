@@ -129,11 +129,13 @@ def test_device_chains_and_host_chains_agree_in_distribution():
     # model complexity and the acceptance-window ratios that drive the jump-length adaptation
     assert abs(np.mean(h_nproc) - table[:, 7].mean()) < 0.6, (np.mean(h_nproc), table[:, 7].mean())
     assert abs(np.mean(h_windows) - table[:, 6].mean()) < 0.06, (np.mean(h_windows), table[:, 6].mean())
-    # loss after the same number of proposals (it fell by ~2.5 orders of magnitude from the initial model): quantiles of
-    # log10(loss) within the sampling error of 64 host chains (bootstrap: ~0.1 per quantile, tools/chain_statistics.py)
-    for q in (0.25, 0.5, 0.75):
+    # loss after the same number of proposals (it fell by ~2.5 orders of magnitude from the initial model): quartiles of
+    # log10(loss).  Bootstrap standard deviations for 64 host chains (tools/chain_statistics.py, 192 host chains against 8192
+    # device chains: host / device quartiles -3.66 / -3.67, -2.02 / -2.01 (best), -2.48 / -2.46, -1.65 / -1.66 (current)):
+    # 0.10, 0.07, 0.16, 0.05; the MEDIAN of the best loss sits between two modes (sd 0.42) and gets a wide margin.
+    for q, tol_best, tol_cur in ((0.25, 0.4, 0.6), (0.5, 1.3, 0.4), (0.75, 0.3, 0.25)):
         a, b = np.quantile(np.log10(h_best), q), np.quantile(np.log10(st['best_loss']), q)
-        assert abs(a - b) < 0.4, ('best loss quantile', q, a, b)
+        assert abs(a - b) < tol_best, ('best loss quantile', q, a, b)
         a, b = np.quantile(np.log10(h_loss), q), np.quantile(np.log10(st['current_loss']), q)
-        assert abs(a - b) < 0.45, ('current loss quantile', q, a, b)
+        assert abs(a - b) < tol_cur, ('current loss quantile', q, a, b)
     eng.close()
