@@ -49,6 +49,7 @@ def parse_args():
                     help="eval: the headline evaluation batch (BASELINE.json configs[2]); multiset: configs[4], a fixed sweep of "
                          "8192 chains over mixed d = 4/8/16 models on N GPUs (strong scaling), all_gather at checkpoints")
     ap.add_argument('--sweep-chains', type=int, default=8192, help='multiset: chains of the whole sweep (fixed as N grows)')
+    ap.add_argument('--sweep-weak', action='store_true', help='multiset: --sweep-chains chains PER GPU (weak scaling) instead of in total')
     ap.add_argument('--checkpoint-every', type=int, default=50, help='multiset: steps between checkpoint all_gathers')
     ap.add_argument('--sustain-seconds', type=float, default=2.0, help='length of the sustained-throughput measurement (0 = skip)')
     ap.add_argument('--chain-steps', type=int, default=1000, help='RJMCMC steps measured after --chain-burn-in (independent of --steps)')
@@ -613,7 +614,8 @@ def run_multiset(args):
         datasets.append((ts, ex[0].real + np.random.default_rng(D).normal(0, 0.01, (3, N_TIMES)), OBS3))
     defects = [1, 2, 3]
     groups = len(datasets) * len(defects)
-    reps = [args.sweep_chains // groups + (1 if i < (args.sweep_chains % groups + 1) // 2 else 0) for i in range(len(defects))]
+    total = args.sweep_chains * (world if args.sweep_weak else 1)
+    reps = [total // groups + (1 if i < (total % groups + 1) // 2 else 0) for i in range(len(defects))]
     sweep = MultisetSweep(datasets, config_numbers=[CONFIG_INDEX], defects_numbers=defects, repetitions_numbers=reps, seed=1,
                           qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'], device=local)
 
@@ -658,7 +660,7 @@ def run_multiset(args):
     line = {
         'metric': 'RJMCMC steps/sec (multiset sweep, mixed 2-4 TLS)', 'value': value, 'unit': 'chain-steps/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * seconds / args.steps, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'scaling': 'weak' if args.sweep_weak else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'multiset sweep: {sweep.n_chains} chains = {len(datasets)} target datasets x library config {CONFIG_INDEX} x '
                                f'D in {defects} (d = 4, 8, 16) x {reps} repetitions, {N_TIMES} times on [0,2.5], observables sx,sy,sz; '
                                f'checkpoint all_gather every {args.checkpoint_every} steps',
