@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -178,6 +179,7 @@ int eml_plan_destroy(EmlPlan* plan) {
     cudaSetDevice(plan->device);
     for (void* p : plan->owned) cudaFree(p);
     if (plan->d_targets) cudaFree(plan->d_targets);
+    plan->drop_host_graphs();
     if (plan->d_prep) cudaFree(plan->d_prep);
     cudaFree(plan->d_params); cudaFree(plan->d_expect); cudaFree(plan->d_loss); cudaFree(plan->d_tset); cudaFree(plan->d_status);
     cudaFreeHost(plan->h_params); cudaFreeHost(plan->h_expect); cudaFreeHost(plan->h_loss); cudaFreeHost(plan->h_tset); cudaFreeHost(plan->h_status);
@@ -200,6 +202,8 @@ int eml_plan_set_targets(EmlPlan* plan, int32_t n_target_sets, const double* tar
         plan->targets_bytes = bytes;
     }
     if (bytes) EML_CUDA(cudaMemcpy(plan->d_targets, targets, bytes, cudaMemcpyHostToDevice));
+    const double* new_targets = n_target_sets > 0 ? plan->d_targets : nullptr;
+    if (new_targets != plan->P.targets || n_target_sets != plan->P.n_target_sets) plan->drop_host_graphs();   // baked into the graphs' kernel arguments
     plan->P.targets = plan->Pw.targets = n_target_sets > 0 ? plan->d_targets : nullptr;
     plan->P.n_target_sets = plan->Pw.n_target_sets = n_target_sets;
     return EML_OK;
@@ -416,6 +420,7 @@ static int ensure_prep(EmlPlan* plan, long long n_models) {
     long long want = n_models < 1024 ? 1024 : n_models;
     if (want > kPrepMaxModels) want = kPrepMaxModels;
     if (want <= plan->prep_cap) return EML_OK;
+    plan->drop_host_graphs();
     if (plan->d_prep) { EML_CUDA(cudaFree(plan->d_prep)); plan->d_prep = nullptr; plan->prep_cap = 0; }   // cudaFree waits for work in flight
     void* p = nullptr;
     EML_CUDA(cudaMalloc(&p, per * (size_t)want));
@@ -477,6 +482,7 @@ static int ensure_staging(EmlPlan* plan, long long n) {
     long long cap = plan->cap_models ? plan->cap_models : 1;
     while (cap < n) cap *= 2;
     EML_CUDA(cudaStreamSynchronize(plan->stream));
+    plan->drop_host_graphs();
     cudaFree(plan->d_params); cudaFree(plan->d_expect); cudaFree(plan->d_loss); cudaFree(plan->d_tset); cudaFree(plan->d_status);
     cudaFreeHost(plan->h_params); cudaFreeHost(plan->h_expect); cudaFreeHost(plan->h_loss); cudaFreeHost(plan->h_tset); cudaFreeHost(plan->h_status);
     plan->d_params = plan->d_expect = plan->d_loss = nullptr; plan->d_tset = plan->d_status = nullptr;
@@ -514,6 +520,53 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     const size_t np = (size_t)n_models * plan->P.n_params;
     const size_t ne = (size_t)n_models * plan->P.n_obs * plan->P.n_times * 2;
     cudaStream_t s = plan->stream;
+    // ---- small batches: replay a CUDA graph of the whole call (through the plan's page-locked staging buffers)
+    static const bool graphs_on = [] { const char* e = std::getenv("EML_HOST_GRAPH"); return !(e && e[0] == '0'); }();
+    if (graphs_on && n_models <= 8 && ++plan->host_calls_small > 2) {
+        EmlPlan::HostGraph* hg = nullptr;
+        for (EmlPlan::HostGraph& g : plan->host_graphs)
+            if (g.n == n_models && g.has_tset == (target_set != nullptr) && g.has_expect == (expect != nullptr) && g.has_loss == (loss != nullptr)) hg = &g;
+        if (!hg && plan->host_graphs.size() < 16) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                if (np) ok = cudaMemcpyAsync(plan->d_params, plan->h_params, np * sizeof(double), cudaMemcpyHostToDevice, s) == cudaSuccess && ok;
+                if (target_set) ok = cudaMemcpyAsync(plan->d_tset, plan->h_tset, n_models * sizeof(int), cudaMemcpyHostToDevice, s) == cudaSuccess && ok;
+                const long long before = g_launches.load();
+                ok = eml_eval_batch(plan, n_models, plan->d_params, target_set ? plan->d_tset : nullptr, expect ? plan->d_expect : nullptr,
+                                    loss ? plan->d_loss : nullptr, plan->d_status, s) == EML_OK && ok;
+                g_launches.store(before);      // nothing ran yet; replays are counted when they are launched
+                if (expect) ok = cudaMemcpyAsync(plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
+                if (loss) ok = cudaMemcpyAsync(plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
+                ok = cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
+                ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && ok && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                plan->host_graphs.push_back(EmlPlan::HostGraph{(long long)n_models, target_set != nullptr, expect != nullptr, loss != nullptr, exec});
+                hg = &plan->host_graphs.back();
+            } else {
+                cudaGetLastError();
+                plan->host_calls_small = -(1 << 30);      // capture is not possible here: stay on the eager path
+            }
+        }
+        if (hg) {
+            if (np) std::memcpy(plan->h_params, params, np * sizeof(double));
+            if (target_set) std::memcpy(plan->h_tset, target_set, n_models * sizeof(int));
+            EML_CUDA(cudaGraphLaunch(hg->exec, s));
+            g_launches.fetch_add(1);
+            EML_CUDA(cudaStreamSynchronize(s));
+            if (expect) std::memcpy(expect, plan->h_expect, ne * sizeof(double));
+            if (loss) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
+            if (cur >= 0 && cur != plan->device) cudaSetDevice(cur);
+            for (long long i = 0; i < n_models; ++i)
+                if (plan->h_status[i] < 0)
+                    return fail(EML_ERR_NOT_CONVERGED, "model " + std::to_string(i) + " did not converge (series cap or non-finite generator)");
+            return EML_OK;
+        }
+    }
     // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for the DMA directly
     auto is_pinned = [](const void* ptr) {
         if (!ptr) return false;

@@ -40,6 +40,15 @@ struct EmlPlan {
     int* d_order = nullptr;             // LPT model order (capacity 2^18 models) followed by the float cost scratch
     double* d_prep = nullptr;           // records of the prepare kernel (Chebyshev warp kernels), prep_cap models
     long long prep_cap = 0;
+    // Small host batches (a single chain's total_dev: ONE model per call) are bound by the launch calls of the host:
+    // upload, memset, prepare, evaluator, downloads are captured once per call shape as a CUDA graph and replayed.
+    struct HostGraph { long long n; int has_tset, has_expect, has_loss; cudaGraphExec_t exec; };
+    std::vector<HostGraph> host_graphs;
+    int host_calls_small = 0;           // small-batch calls seen (the first ones run eagerly: lazy initialisations)
+    void drop_host_graphs() {
+        for (HostGraph& g : host_graphs) cudaGraphExecDestroy(g.exec);
+        host_graphs.clear();
+    }
 };
 
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,

@@ -164,6 +164,14 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // 1/(j+1) for the Taylor recurrences
 __constant__ double INV_TABLE[MCAP + 2];
 
+// Index checks of the shared-memory tables (trace table, coefficient table, transposition tiles, prepare records): compiled
+// in with -DEML_DEBUG_BOUNDS (tools/build_variant.sh dbg -DEML_DEBUG_BOUNDS), a violation traps the kernel.  The pool's
+// compute-sanitizer is closed, so the GPU suite is run once per round against this build instead.
+#ifdef EML_DEBUG_BOUNDS
+#define EML_CHECK(cond) do { if (!(cond)) { printf("eml bounds check failed: %s (line %d)\n", #cond, __LINE__); __trap(); } } while (0)
+#else
+#define EML_CHECK(cond) do { } while (0)
+#endif
 // warp-uniform predicate the compiler can SEE is uniform (vote result): keeps shuffles free of divergence guards
 #define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
@@ -409,6 +417,8 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
         __syncwarp();
         for (int i = lane; i < P.lin_rows; i += 32) {
             const LinRow rw = lin_row[i];
+            EML_CHECK(rw.offset >= 0 && rw.offset < (int)(sizeof(Scratch) / sizeof(double)) - (int)((REAL_H ? 2 : 4) * D * D) &&
+                      rw.begin >= 0 && rw.end <= P.lin_nnz && rw.begin <= rw.end);
             double acc = 0.0;
             for (int k = rw.begin; k < rw.end; ++k) {
                 const LinEntry e = lin_ent[k];
@@ -611,6 +621,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
             // ---- the prepare kernel's record of this model: A fragments (coalesced), weights and plan through shared memory
             constexpr int KSE = PARITY ? 2 : KS;
             constexpr int NA = prep_fragments<TL, REAL_H, PARITY>(), REC = prep_record_doubles<TL, REAL_H, PARITY>();
+            EML_CHECK(b >= 0 && b < n_models);
             const double* const R = prep + (size_t)b * REC;
 #pragma unroll
             for (int I = 0; I < TL; ++I)
@@ -1027,6 +1038,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         const unsigned tr_base = (unsigned)__cvta_generic_to_shared(&S.tr[tr_off]);
         // predicated shared store of one table entry (kept out of a branch so that the recurrence loop stays one basic block)
         auto tr_put = [&](const int kterm, const double val) {
+            EML_CHECK(kterm >= 0 && kterm <= Scratch::KCAP);
             asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }"
                          :: "r"(tr_base + (unsigned)(kterm * NTR * 8)), "d"(val), "r"((int)tr_lane) : "memory");
         };
@@ -1125,6 +1137,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     const double tz = 2.0 / (tau_end * Rb);
                     double jn = 1.0, jn1 = 0.0, ssum = 0.0;
                     for (int k = Kc; k >= 1; --k) {
+                        EML_CHECK(k <= Scratch::KCAP + 1);
                         if ((k & 31) == lane) cJ[k] = jn;
                         if (!(k & 1)) ssum += jn;
                         const double jm = fma((double)k * tz, jn, -jn1);
@@ -1170,7 +1183,9 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 };
                 double* const xs0 = S.xt_re + xt_addr(g, 2 * t), * const xs1 = S.xt_re + xt_addr(g, 2 * t + 1);
                 const double* const xl = S.xt_re + xt_addr(2 * t, g);
+                EML_CHECK(xt_addr(g, 2 * t + 1) < 64 && xt_addr(2 * t, g) + 1 < 64 && (2 * XBUF) * sizeof(double) <= sizeof(S.xt_re));
                 auto transpose_conj = [&](const int buf) {      // n = m^dag
+                    EML_CHECK(buf == 0 || buf == 1);
                     xs0[buf * XBUF] = m_re[0]; xs1[buf * XBUF] = m_re[1];
                     xs0[buf * XBUF + 64] = m_im[0]; xs1[buf * XBUF + 64] = m_im[1];
                     __syncwarp();
@@ -1433,6 +1448,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     }
                 }
                 n_apply += Kc;
+                EML_CHECK(Kc >= 1 && Kc <= Scratch::KCAP);
                 if (lane < 3 * NTR) S.tr[(Kc + 1) * NTR + lane] = 0.0;      // the output sums read the table in groups of four terms
                 __syncwarp();
                 PHASE_MARK(2);      // recurrence (and the coefficient table of a non-final step)
@@ -1480,6 +1496,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int kk = k - j;
+                                EML_CHECK(kk >= 1 && kk <= Kc + 3 && kk <= Scratch::KCAP + 3);
                                 double2 ta = make_double2(0.0, 0.0);
                                 if constexpr (!SB) ta = *reinterpret_cast<const double2*>(&S.tr[kk * NTR]);
                                 const double2 tb = *reinterpret_cast<const double2*>(&S.tr[kk * NTR + NTR - 2]);

@@ -445,3 +445,36 @@ def test_randomised_general_models_dmma_vs_generic_vs_oracle(use_kernel, n):
             assert np.abs(np.asarray(x) - np.asarray(y)).max() < 1e-10
     for i in (0, 7, 19):
         assert_close(results['auto'][i], lo.expect_exact(specs[i], ts, obs), TOL, f'n={n} model {i}')
+
+
+def test_small_host_batches_replayed_from_a_graph_equal_the_eager_path():
+    """
+    eml_eval_batch_host replays a CUDA graph of the whole call for batches of <= 8 models from the third such call on
+    (a single chain's total_dev is one model per call).  Same results as the eager path, also after the targets change
+    (they are kernel arguments of the captured graph) and when the call shape alternates.
+    """
+    from effective_model_learning_b200 import configs, synthetic
+    hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    ts = np.linspace(0.0, 2.5, 40)
+    for D in (1, 3):
+        lay = synthetic.LibraryLayout(1, D, hyper)
+        ctx = lay.context(ts, OBS3)
+        rows = lay.batch_params(1000 + np.arange(12))
+        tg1 = np.random.default_rng(1).normal(0, 0.3, (3, len(ts)))
+        tg2 = np.random.default_rng(2).normal(0, 0.3, (3, len(ts)))
+        ctx.set_targets(tg1)
+        ex_all, loss1 = ctx.evaluate(rows, want_expect=True, want_loss=True)            # 12 models: eager
+        for i in range(12):                                                             # one model per call: graph from call 3
+            ex, loss = ctx.evaluate(rows[i:i + 1], want_expect=True, want_loss=True)
+            assert np.array_equal(ex[0], ex_all[i]) and loss[0] == loss1[i], (D, i)
+            _, only_loss = ctx.evaluate(rows[i:i + 1], want_expect=False, want_loss=True)   # another call shape
+            assert only_loss[0] == loss1[i]
+        for i in range(0, 12, 3):
+            ex, loss = ctx.evaluate(rows[i:i + 3], want_expect=True, want_loss=True)
+            assert np.array_equal(ex, ex_all[i:i + 3]) and np.array_equal(loss, loss1[i:i + 3])
+        ctx.set_targets(tg2)
+        _, loss2 = ctx.evaluate(rows, want_expect=False, want_loss=True)
+        assert not np.allclose(loss1, loss2)
+        for i in range(4):
+            _, loss = ctx.evaluate(rows[i:i + 1], want_expect=False, want_loss=True)
+            assert loss[0] == loss2[i]
