@@ -84,6 +84,16 @@ constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
 #ifndef EML_WARPS_PER_SM_SB
 #define EML_WARPS_PER_SM_SB 16
 #endif
+#ifndef EML_WARPS_PER_SM_PAR
+#define EML_WARPS_PER_SM_PAR 8      // full-state parity variant (d = 16): resident warps per SM (8: <= 255 regs, 12: <= 168 regs)
+#endif
+#ifndef EML_CHEB_KCAP_PAR
+#define EML_CHEB_KCAP_PAR 512
+#endif
+#ifndef EML_PAR_XT_BUFFERS
+#define EML_PAR_XT_BUFFERS 2        // transposition buffers of the full-state parity variant (1: a second __syncwarp per application)
+#endif
+constexpr int WARPS_PER_SM_PAR = EML_WARPS_PER_SM_PAR, CHEB_KCAP_PAR = EML_CHEB_KCAP_PAR, PAR_XT_BUFFERS = EML_PAR_XT_BUFFERS;
 constexpr int CHEB_KCAP_SB = EML_CHEB_KCAP_SB;      // sector variant: 16 warps per SM (<= 128 regs, 14 KB shared memory per warp), two trace values per term
 constexpr int WARPS_PER_SM_SB = EML_WARPS_PER_SM_SB;
 static_assert(WARPS_PER_SM_SB % EML_WARPS_PER_CTA == 0, "resident warps per SM must be a whole number of CTAs");
@@ -111,7 +121,7 @@ struct alignas(16) WarpScratch<TL, false, false, false> {
 template <int TL, bool SB, bool PA>
 struct alignas(16) WarpScratch<TL, true, SB, PA> {
     static constexpr int D = 8 * TL;
-    static constexpr int KCAP = TL == 2 ? (SB ? CHEB_KCAP_SB : CHEB_KCAP_TL2) : CHEB_KCAP_TL1;
+    static constexpr int KCAP = TL == 2 ? (SB ? CHEB_KCAP_SB : (PA ? CHEB_KCAP_PAR : CHEB_KCAP_TL2)) : CHEB_KCAP_TL1;
     static constexpr int NTR = SB ? 2 : 4;      // partial-trace values kept per term
     double jw[32];      // [bitpos][type(0 diag,1 flip)][ra][ca]          (from the prepare kernel's record)
     double gdiag[16];   // real H: diagonal of G.re = -1/2 sum c^dag c     (contiguous with plan: one record read)
@@ -120,7 +130,7 @@ struct alignas(16) WarpScratch<TL, true, SB, PA> {
     static constexpr int XT = TL == 1 ? 128 : (EML_TL2_SMEM_STENCIL ? 16 * 24 : (EML_TL2_SMEM_TRANSPOSE ? 256 : 2));
     // SB: one 8 x 8 complex tile, planes re | im of 64 doubles, two buffers (256 doubles in xt_re; xt_im unused)
     // (parity variants: 8 x 8 tiles, planes re | im of 64 doubles, two buffers -- one tile in the sector variant, three otherwise)
-    alignas(16) double xt_re[SB ? 256 : (PA ? 768 : XT)];
+    alignas(16) double xt_re[SB ? 256 : (PA ? 384 * PAR_XT_BUFFERS : XT)];
     alignas(16) double xt_im[(SB || PA) ? 2 : XT];   // X' staged column-major (swizzled) for the conjugate transpose
     double cj[KCAP + 2];                     // Bessel coefficients of the step end (non-final macro steps only)
     alignas(16) double tr[(KCAP + 4) * NTR]; // partial traces of the Chebyshev terms (+3 zero entries: groups of four)
@@ -553,7 +563,7 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
 
 template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
 // resident warps per SM: 16 (d = 8), 16 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM is quoted for four-warp CTAs
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (SB ? WARPS_PER_SM_SB : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (SB ? WARPS_PER_SM_SB : PARITY ? WARPS_PER_SM_PAR : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
@@ -1033,8 +1043,11 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         // (4 double shuffles) leaves value 2*bit2(g) + bit1(g) in the lanes with g even.
         const int dl4 = 4 * (g ^ 4) + ((g ^ 4) >> 1), dl2 = 4 * (g ^ 2) + ((g ^ 2) >> 1), dl1 = 4 * (g ^ 1) + ((g ^ 1) >> 1);
         // (the table entry is addressed by term index so that the store stays a predicated STS with a shared-window address)
-        const bool tr_lane = SB ? (diag_lane && (g & 3) == 0) : (TL == 2) ? (diag_lane && !(g & 1)) : ((lane & 7) == 0);
-        const int tr_off = SB ? (g >> 2) : (TL == 2) ? (g >> 1) : (lane >> 3);
+        // (d = 8: the four lanes of observed-bit pair (a, bb) are 16 a + 2 bb + 9 g1 + 4 g0; after the two-stage butterfly all of
+        //  them hold the totals: lane 0 stores rho00, lane 18 rho11, lane 2 Re rho01, lane 6 Im rho01)
+        const bool tr_lane = SB ? (diag_lane && (g & 3) == 0) : (TL == 2) ? (diag_lane && !(g & 1))
+                                : (lane == 0 || lane == 18 || lane == 2 || lane == 6);
+        const int tr_off = SB ? (g >> 2) : (TL == 2) ? (g >> 1) : (lane == 0 ? 0 : lane == 18 ? 1 : lane == 2 ? 2 : 3);
         const unsigned tr_base = (unsigned)__cvta_generic_to_shared(&S.tr[tr_off]);
         // predicated shared store of one table entry (kept out of a branch so that the recurrence loop stays one basic block)
         auto tr_put = [&](const int kterm, const double val) {
@@ -1075,8 +1088,13 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 const double tot = kk + shfl(kk, dl1);
                 tr_put(kterm, tot);
             } else {
-                const double trv = partial_trace(xr, xi);
-                tr_put(kterm, trv);
+                // d = 8: a partial-trace element (row and column agree on the two non-observed bits) sits at e = g & 1 of the
+                // lanes with t0 = g1; flipping g0 (lane ^ 4) or g1 together with t0 (lane ^ 9) stays among them
+                const double er = gp ? xr[0][0][1] : xr[0][0][0], ei = gp ? xi[0][0][1] : xi[0][0][0];
+                double sr = er + __shfl_xor_sync(0xffffffffu, er, 4), si = ei + __shfl_xor_sync(0xffffffffu, ei, 4);
+                sr += __shfl_xor_sync(0xffffffffu, sr, 9);
+                si += __shfl_xor_sync(0xffffffffu, si, 9);
+                tr_put(kterm, lane == 6 ? si : sr);
             }
         };
         double* const cJ = S.cj;     // coefficient table of the step end
@@ -1177,6 +1195,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                 // doubles per tile (odd tile, then the two even tiles), two buffers (term k uses buffer k & 1, so one
                 // __syncwarp per application suffices).
                 constexpr int XBUF = SB ? 128 : 384;
+                constexpr int NBUF = SB ? 2 : PAR_XT_BUFFERS;
                 auto xt_addr = [](const int R, const int C) {
                     const int a = R >> 1, h = 2 * (C & 1) + (a >> 1);
                     return 2 * (8 * h + (a & 1) + 2 * ((C >> 1) ^ h)) + (R & 1);
@@ -1194,7 +1213,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     n_re[0] = cr.x; n_re[1] = cr.y; nn_im[0] = ci.x; nn_im[1] = ci.y;
                 };
                 __syncwarp();
-                transpose_conj(1);
+                transpose_conj(NBUF - 1);
+                if constexpr (NBUF == 1) __syncwarp();
                 // flip stencils of the lane-bit sites and of the observed site onto (ar, ai): sources (sr, -si), weights F, f2, f1, f0
                 auto flips = [&](double (&ar)[2], double (&ai)[2], const double (&sr)[2], const double (&si)[2], const double (&F)[FE],
                                  const bool neg_im) {
@@ -1325,7 +1345,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         p_re[e] = FIRST ? 2.0 * m_re[e] : m_re[e]; p_im[e] = FIRST ? 2.0 * m_im[e] : m_im[e];
                         m_re[e] = x_re[e]; m_im[e] = x_im[e];
                     }
-                    const int buf = k & 1;
+                    const int buf = (NBUF == 2) ? (k & 1) : 0;
                     if constexpr (!SB) {
 #pragma unroll
                         for (int I = 0; I < 2; ++I) {
@@ -1347,6 +1367,7 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                             d_im[I][0] = y_im[I][0] - ti_.x; d_im[I][1] = y_im[I][1] - ti_.y;
                         }
                     }
+                    if constexpr (NBUF == 1) __syncwarp();      // the single buffer is rewritten by the next application
                 };
                 auto run_terms_par = [&](auto na_tag) {
                     application(0, na_tag, std::true_type{});
