@@ -12,6 +12,7 @@
 // Two __syncthreads per application.  REAL_H as in the warp kernel (half the DMMAs when H is a real matrix).
 //
 // Replaces qutip.mesolve + e_ops + loss for one model (reference basic_model.py:381-388, learning_chain.py:738-742).
+#include <cstdlib>
 #include <type_traits>
 #include "eml_common.cuh"
 #include "eml_cheb.cuh"
@@ -779,6 +780,10 @@ EML_CTA_INST(true, true, true) EML_CTA_INST(false, true, true)
 
 bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian && P.n_tls == 5 && P.n_params <= CMAXP; }
 
+// eml_cta_orbit.cu: the second-generation kernel for parity-conserving Hamiltonians (Chebyshev series)
+cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const double* params, const int* target_set, double* expect,
+                             double* loss, int* status, unsigned int* counter, const int* use_order, bool real_h, cudaStream_t stream);
+
 // declared in eml_warp_mma.cu
 void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, const int* cost_hint,
                         cudaStream_t stream);
@@ -808,6 +813,10 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
                           const int*, const double);
     const bool parity = parity_h && chebyshev;
+    // parity-conserving H: the orbit kernel (EML_D32_TILEROW=1 keeps the first-generation tile-row kernel, for A/B measurements)
+    static const bool tilerow = [] { const char* e = std::getenv("EML_D32_TILEROW"); return e && e[0] == '1'; }();
+    if (parity && !tilerow)
+        return launch_cta_orbit(P, n_models, params, target_set, expect, loss, status, counter, use_order, real_h, stream);
     const Kern kern = parity ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, true> : (Kern)eval_cta_mma_kernel<false, true, true>)
                     : chebyshev ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, false> : (Kern)eval_cta_mma_kernel<false, true, false>)
                                 : (real_h ? (Kern)eval_cta_mma_kernel<true, false, false> : (Kern)eval_cta_mma_kernel<false, false, false>);
