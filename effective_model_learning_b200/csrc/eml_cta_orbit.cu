@@ -38,11 +38,23 @@ namespace eml {
 
 constexpr int OMAXP = 192;
 constexpr int OLD = 40;                 // row stride (doubles) of the published term: conflict-free 16-byte accesses over (g, t)
-constexpr int ORB_KCAP = 1024;          // Chebyshev terms per macro step that fit the trace table
+#ifndef EML_ORBIT_CTAS_PER_SM
+#define EML_ORBIT_CTAS_PER_SM 2         // 3: <= 168 registers, single-buffered transposition tiles, 512-term trace table (73 KB of shared memory per CTA)
+#endif
+constexpr int ORB_CTAS = EML_ORBIT_CTAS_PER_SM;
+constexpr int ORB_KCAP = ORB_CTAS >= 3 ? 512 : 1024;      // Chebyshev terms per macro step that fit the trace table
+constexpr int ORB_XTBUF = ORB_CTAS >= 3 ? 1 : 2;          // buffers of the private transposition tiles (1: a second __syncwarp per application)
+// kernel-variant switches for experiments (tools/build_variant.sh); the defaults are the measured best
+#ifndef EML_ORBIT_PAIRBAR
+#define EML_ORBIT_PAIRBAR 1             // per-application barrier among the two warps that exchange tiles (D <-> warp 1, warp 2 <-> warp 3) instead of the CTA
+#endif
+#ifndef EML_ORBIT_ROTATE
+#define EML_ORBIT_ROTATE 1              // the second CTA of an SM runs its roles on the other schedulers (the D warp is the heaviest)
+#endif
 
 struct alignas(16) OrbitScratch {
     double Vs[2][2][32 * OLD];          // [buffer][re | im]: the whole current term, row-major (hosts G and the squarings during set-up)
-    double xt[2][10][128];              // private transposition tiles [buffer][slot][re 64 | im 64]; D: slots 0..3, warp r: 2 + 2 r, 3 + 2 r
+    double xt[ORB_XTBUF][10][128];              // private transposition tiles [buffer][slot][re 64 | im 64]; D: slots 0..3, warp r: 2 + 2 r, 3 + 2 r
     double par[OMAXP];
     double jw[40];                      // [bitpos 0..4][type (0 diag, 1 flip)][ra][ca]
     double kd[10];
@@ -56,6 +68,8 @@ struct alignas(16) OrbitScratch {
     double cJ[ORB_KCAP + 2];
 };
 
+// (not volatile, and the products written tile by tile: pinning a round-robin issue order over the accumulators by hand, or
+// fetching all cross operands before the first cross DMMA, was measured 7 % slower than the compiler's own schedule)
 __device__ __forceinline__ void dmma_o(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
         : "+d"(d0), "+d"(d1)
@@ -329,14 +343,15 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
             if constexpr (!DG) {
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 2; ++i) xt_put(1, i, v_re[i], v_im[i]);
+                for (int i = 0; i < 2; ++i) xt_put(ORB_XTBUF - 1, i, v_re[i], v_im[i]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     double2 cr, ci;
-                    xt_get(1, i, cr, ci);
+                    xt_get(ORB_XTBUF - 1, i, cr, ci);
                     n_re[i][0] = cr.x; n_re[i][1] = cr.y; n_im[i][0] = -ci.x; n_im[i][1] = -ci.y;
                 }
+                if constexpr (ORB_XTBUF == 1) __syncwarp();
             }
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
@@ -383,8 +398,10 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
                         mma_v_Gdag<REAL_H>(x_re[i], x_im[i], v_re[i], v_im[i], aG_re[J][J & 1], aG_im[J][J & 1]);      // v[I,J] G[J,J]^dag
                     }
                 }
-                // ---- the published term k is complete
-                cta_bar();
+                // ---- the published term k is complete.  D and role 1 read only each other's tiles, roles 2 and 3 likewise: the two
+                //      pairs synchronise separately (named barriers of 64 threads) and may drift apart within a macro step
+                if constexpr (EML_ORBIT_PAIRBAR) asm volatile("bar.sync %0, 64;" :: "n"(1 + (ROLE >> 1)) : "memory");
+                else cta_bar();
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
                     const int I = TI[i], J = TJ[i];
@@ -398,7 +415,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
                     }
                 }
                 // ---- next term.  T_2 = (2 At) T_1 + 2 T_0, afterwards T_{k+1} = (2 At) T_k + T_{k-1}; D keeps the previous term halved
-                const int xb = k & 1;
+                const int xb = (ORB_XTBUF == 2) ? (k & 1) : 0;
 #pragma unroll
                 for (int i = 0; i < NT; ++i) xt_put(xb, i, x_re[i], x_im[i]);
                 __syncwarp();
@@ -419,6 +436,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
                         n_re[i][0] = cr.x; n_re[i][1] = cr.y; n_im[i][0] = -ci.x; n_im[i][1] = -ci.y;
                     }
                 }
+                if constexpr (ORB_XTBUF == 1) __syncwarp();      // the single buffer is rewritten by the next application
                 if (k + 1 < Kc) {
 #pragma unroll
                     for (int i = 0; i < NT; ++i) {
@@ -503,11 +521,11 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
 }
 
 template <bool REAL_H>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, ORB_CTAS)
 eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                       const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                       int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
-                      const double cheb_zcap) {
+                      const double cheb_zcap, const int sms) {
     constexpr int N = 5, D = 32;
     extern __shared__ __align__(16) unsigned char orbit_smem_raw[];
     OrbitScratch& S = *reinterpret_cast<OrbitScratch*>(orbit_smem_raw);
@@ -532,7 +550,7 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
         for (int i = tid; i < P.n_params; i += 128) S.par[i] = params[b * P.n_params + i];
         for (int i = tid; i < 32 * OLD; i += 128) { G_re[i] = 0.0; G_im[i] = 0.0; }
         __syncthreads();
-        if (tid < D) {
+        if (tid < D) {      // thread r owns row r of G (fixed summation order: results are reproducible bit for bit); zero entries skipped
             const int r = tid;
             for (int ti = 0; ti < P.n_terms; ++ti) {
                 const EmlTerm tm = P.terms[ti];
@@ -544,8 +562,8 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
                     for (int a = 0; a < 2; ++a) {
                         const cplx A = ld_op(P.op_table, tm.op_a, ra, a);
                         const int c = (r & ~(1 << sa)) | (a << sa);
-                        G_re[r * OLD + c] += v * A.im;        // -i h
-                        G_im[r * OLD + c] -= v * A.re;
+                        if (A.im != 0.0) G_re[r * OLD + c] += v * A.im;        // -i h
+                        if (A.re != 0.0) G_im[r * OLD + c] -= v * A.re;
                     }
                 } else if (tm.kind == EML_TERM_COUPLING) {
                     const int sb = pos(tm.site_b);
@@ -555,8 +573,8 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
                         for (int bb = 0; bb < 2; ++bb) {
                             const cplx AB = cmul(ld_op(P.op_table, tm.op_a, ra, a), ld_op(P.op_table, tm.op_b, rb, bb));
                             const int c = (r & ~((1 << sa) | (1 << sb))) | (a << sa) | (bb << sb);
-                            G_re[r * OLD + c] += v2 * AB.im;
-                            G_im[r * OLD + c] -= v2 * AB.re;
+                            if (AB.im != 0.0) G_re[r * OLD + c] += v2 * AB.im;
+                            if (AB.re != 0.0) G_im[r * OLD + c] -= v2 * AB.re;
                         }
                 } else {
                     for (int a = 0; a < 2; ++a) {
@@ -566,8 +584,8 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
                             M.re += m.re; M.im += m.im;
                         }
                         const int c = (r & ~(1 << sa)) | (a << sa);
-                        G_re[r * OLD + c] -= 0.5 * v * M.re;
-                        G_im[r * OLD + c] -= 0.5 * v * M.im;
+                        if (M.re != 0.0) G_re[r * OLD + c] -= 0.5 * v * M.re;
+                        if (M.im != 0.0) G_im[r * OLD + c] -= 0.5 * v * M.im;
                     }
                 }
             }
@@ -663,30 +681,40 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
             mu *= 1.0 / D;
             double spread = hi - lo;
             // 2 rho(H - mu) <= 2 ||(H - mu)^8||_1^(1/8): three squarings, planes [re | im] of 32 x 32
+            // (real H: on the DMMA pipe, warp w computes tile row w; row stride 36 makes the fragment loads conflict free)
+            constexpr int LDM = REAL_H ? 36 : D;
             double* Ma_re = S.Vs[1][0]; double* Ma_im = S.Vs[1][1];
             double* Mb_re = S.tr;       double* Mb_im = S.tr + D * D;
+            static_assert(32 * 36 <= 32 * OLD && 32 * 36 <= (ORB_KCAP + 4) * 4, "squaring scratch");
             for (int i = tid; i < D * D; i += 128) {
                 const int r = i / D, c = i % D;
-                Ma_re[i] = -G_im[r * OLD + c] - ((r == c) ? mu : 0.0);
+                Ma_re[r * LDM + c] = -G_im[r * OLD + c] - ((r == c) ? mu : 0.0);
                 if (!REAL_H) Ma_im[i] = (r == c) ? 0.0 : G_re[r * OLD + c];
             }
             __syncthreads();
             for (int sq = 0; sq < 3; ++sq) {
+                if constexpr (REAL_H) {
+#pragma unroll
+                    for (int J = 0; J < 4; ++J) {
+                        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            dmma_o(d0, d1, Ma_re[(8 * w + g) * LDM + 4 * ks + t], Ma_re[(4 * ks + t) * LDM + 8 * J + g]);
+                        *reinterpret_cast<double2*>(&Mb_re[(8 * w + g) * LDM + 8 * J + 2 * t]) = make_double2(d0, d1);
+                    }
+                } else
                 for (int i = tid; i < D * D; i += 128) {
                     const int r = i / D, c = i % D;
                     double sre = 0.0, sim = 0.0;
 #pragma unroll 4
                     for (int k = 0; k < D; ++k) {
                         const double are = Ma_re[r * D + k], bre = Ma_re[k * D + c];
-                        sre = fma(are, bre, sre);
-                        if (!REAL_H) {
-                            const double aim = Ma_im[r * D + k], bim = Ma_im[k * D + c];
-                            sre = fma(-aim, bim, sre);
-                            sim = fma(are, bim, fma(aim, bre, sim));
-                        }
+                        const double aim = Ma_im[r * D + k], bim = Ma_im[k * D + c];
+                        sre = fma(are, bre, fma(-aim, bim, sre));
+                        sim = fma(are, bim, fma(aim, bre, sim));
                     }
                     Mb_re[i] = sre;
-                    if (!REAL_H) Mb_im[i] = sim;
+                    Mb_im[i] = sim;
                 }
                 __syncthreads();
                 double* tmp = Ma_re; Ma_re = Mb_re; Mb_re = tmp;
@@ -694,7 +722,7 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
             }
             if (tid < D) {
                 double cs = 0.0;
-                for (int r = 0; r < D; ++r) cs += REAL_H ? fabs(Ma_re[r * D + tid]) : hypot(Ma_re[r * D + tid], Ma_im[r * D + tid]);
+                for (int r = 0; r < D; ++r) cs += REAL_H ? fabs(Ma_re[r * LDM + tid]) : hypot(Ma_re[r * D + tid], Ma_im[r * D + tid]);
                 S.colsum[tid] = cs;
             }
             __syncthreads();
@@ -723,9 +751,11 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
         double my_loss = 0.0;
         int n_apply = 0;
         bool capped = false;
-        if (w == 0) orbit_series<REAL_H, 0>(C, aG_re, aG_im, my_loss, n_apply, capped);
-        else if (w == 1) orbit_series<REAL_H, 1>(C, aG_re, aG_im, my_loss, n_apply, capped);
-        else if (w == 2) orbit_series<REAL_H, 2>(C, aG_re, aG_im, my_loss, n_apply, capped);
+        // CTAs b and b + (number of SMs) share an SM: rotating the roles by two puts their D warps on different schedulers
+        const int role = EML_ORBIT_ROTATE ? ((w + 2 * ((int)(blockIdx.x / sms) & 1)) & 3) : w;
+        if (role == 0) orbit_series<REAL_H, 0>(C, aG_re, aG_im, my_loss, n_apply, capped);
+        else if (role == 1) orbit_series<REAL_H, 1>(C, aG_re, aG_im, my_loss, n_apply, capped);
+        else if (role == 2) orbit_series<REAL_H, 2>(C, aG_re, aG_im, my_loss, n_apply, capped);
         else orbit_series<REAL_H, 3>(C, aG_re, aG_im, my_loss, n_apply, capped);
 
         // every warp produced outputs: combine the per-warp losses in a fixed order
@@ -742,8 +772,8 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
     }
 }
 
-template __global__ void eval_cta_orbit_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
-template __global__ void eval_cta_orbit_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double);
+template __global__ void eval_cta_orbit_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double, const int);
+template __global__ void eval_cta_orbit_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double, const int);
 
 cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const double* params, const int* target_set, double* expect,
                              double* loss, int* status, unsigned int* counter, const int* use_order, bool real_h, cudaStream_t stream) {
@@ -752,7 +782,7 @@ cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const doub
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
-                          const int*, const double);
+                          const int*, const double, const int);
     const Kern kern = real_h ? (Kern)eval_cta_orbit_kernel<true> : (Kern)eval_cta_orbit_kernel<false>;
     const size_t smem = sizeof(OrbitScratch);
     static int per_sm_cache[64][2] = {{0}};
@@ -766,7 +796,7 @@ cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const doub
     long long ctas = n_models;
     if (ctas > (long long)per_sm * sms) ctas = (long long)per_sm * sms;
     const double zcap = cheb_zcap_for(ORB_KCAP);
-    kern<<<(unsigned)ctas, 128, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order, zcap);
+    kern<<<(unsigned)ctas, 128, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order, zcap, sms);
     return cudaGetLastError();
 }
 

@@ -266,5 +266,10 @@ def flops_per_application(kernel_name: str, n_tls: int) -> float:
             # full state: odd tile 2 MUL + 8 FMA + the doubling FMA pair = 22 flop; even tiles (2 x 64 elements) 10 FMA,
             # X' + X'^dag 2 ADD, halving of the stored term 2 MUL = 24 flop
             return mma + quarter * (2.0 + 4.0 * n_tls + 4.0) + 2.0 * quarter * (4.0 + 4.0 * n_tls + 4.0)
+        if kernel_name.startswith('cta_cheb_parity'):
+            # d = 32 orbit kernel (round 2, eml_cta_orbit.cu): only the 10 upper-triangle tiles (640 complex elements) are
+            # state: diagonal weight + 5 site flips = 2 + 10 FMA per element; the 4 Hermitian tiles (256 elements) also pay
+            # X' + X'^dag (2 ADD) and the halving of the stored term (2 MUL).  Same DMMA count as the tile-row kernel.
+            return mma + 640.0 * (4.0 + 4.0 * n_tls) + 256.0 * 4.0
         return mma + d * d * (2.0 + 4.0 * n_tls + 6.0)
     raise RuntimeError('unknown kernel ' + kernel_name)
