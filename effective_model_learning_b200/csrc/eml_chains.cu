@@ -291,6 +291,286 @@ __global__ void chains_accept_kernel(const ChainHyperDev H, const ChainState S, 
     st[6] = S.last_ratio[c]; st[7] = n_proc;
 }
 
+// ---- warp-per-chain versions of the two kernels (the default; EML_CHAIN_THREAD_KERNELS=1 selects the thread-per-chain ones
+//      above, which they reproduce bit for bit: same random-stream positions, same order of every floating-point operation that
+//      feeds a result).  A thread-per-chain proposal is ~100 us of serial work (loops over the parameter row, Box-Muller draws,
+//      two error functions per tweaked parameter) on 2048 threads = 16 CTAs; here lane l owns the parameters l, l + 32, ...
+//      The Gaussian tweaks consume the chain's random stream sequentially (up to 10 redraws per parameter, the next parameter
+//      continues where the previous one stopped): the lanes start from the stream positions a scan of "one draw each" gives and
+//      repeat for the lanes behind a redraw until the positions are consistent (redraws are rare: usually one pass).
+constexpr int CH_MAXQ = 4;      // parameters per lane: n_params <= 128
+
+struct WaysW { double ways[N_MOVES]; int n_proc; };
+// number of ways of each move from the lanes' parameters: counts per class packed in bytes (n_params <= 128 < 256)
+__device__ inline WaysW count_ways_warp(const int (&cc)[CH_MAXQ], const double (&row)[CH_MAXQ], const bool (&have)[CH_MAXQ]) {
+    unsigned tot = 0, pres = 0;
+#pragma unroll
+    for (int i = 0; i < CH_MAXQ; ++i)
+        if (have[i] && cc[i] >= 1 && cc[i] <= 4) {
+            tot += 1u << (8 * (cc[i] - 1));
+            if (row[i] != 0.0) pres += 1u << (8 * (cc[i] - 1));
+        }
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    pres = __reduce_add_sync(0xffffffffu, pres);
+    auto T = [&](int c) { return (int)((tot >> (8 * (c - 1))) & 255u); };
+    auto Pn = [&](int c) { return (int)((pres >> (8 * (c - 1))) & 255u); };
+    WaysW w;
+    w.ways[MV_TWEAK] = 1;
+    w.ways[MV_ADD_QL] = T(EML_COL_QUBIT_L) - Pn(EML_COL_QUBIT_L);       w.ways[MV_REM_QL] = Pn(EML_COL_QUBIT_L);
+    w.ways[MV_ADD_DL] = T(EML_COL_DEFECT_L) - Pn(EML_COL_DEFECT_L);     w.ways[MV_REM_DL] = Pn(EML_COL_DEFECT_L);
+    w.ways[MV_ADD_Q2D] = T(EML_COL_Q2D_COUPLING) - Pn(EML_COL_Q2D_COUPLING); w.ways[MV_REM_Q2D] = Pn(EML_COL_Q2D_COUPLING);
+    w.ways[MV_ADD_D2D] = T(EML_COL_D2D_COUPLING) - Pn(EML_COL_D2D_COUPLING); w.ways[MV_REM_D2D] = Pn(EML_COL_D2D_COUPLING);
+    w.n_proc = Pn(1) + Pn(2) + Pn(3) + Pn(4);
+    return w;
+}
+// product over the tweakable parameters in parameter order (the order of the sequential loop in xi_product)
+__device__ inline double xi_product_warp(const ChainHyperDev& H, const int (&cc)[CH_MAXQ], const double (&row)[CH_MAXQ],
+                                         const bool (&have)[CH_MAXQ], const double (&jump)[3], const int nq) {
+    double out = 1.0;
+    for (int i = 0; i < nq; ++i) {
+        const bool tw = have[i] && tweakable(cc[i], row[i]);
+        const int pc = pclass(cc[i]);
+        const double x = tw ? xi(row[i], jump[pc], H.lo[pc], H.hi[pc]) : 1.0;
+        const unsigned tm = __ballot_sync(0xffffffffu, tw);
+#pragma unroll 1
+        for (int l = 0; l < 32; ++l) {
+            const double v = __shfl_sync(0xffffffffu, x, l);
+            if ((tm >> l) & 1u) out *= v;
+        }
+    }
+    return out;
+}
+
+__global__ void chains_propose_warp_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo,
+                                                                  const long long c_hi, const unsigned long long seed,
+                                                                  const long long first_chain) {
+    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= c_hi) return;      // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int P = H.n_params, nq = (P + 31) >> 5;
+    double* cur = S.cur + c * P;
+    double* prop = S.prop + c * P;
+    Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};      // every lane follows the same stream
+    int cc[CH_MAXQ];
+    bool have[CH_MAXQ];
+    double curv[CH_MAXQ], propv[CH_MAXQ];
+#pragma unroll
+    for (int i = 0; i < CH_MAXQ; ++i) {
+        const int p = lane + 32 * i;
+        have[i] = i < nq && p < P;
+        cc[i] = have[i] ? H.col_class[p] : EML_COL_FIXED;
+        curv[i] = have[i] ? cur[p] : 0.0;
+    }
+    double jump[3] = {S.jump[c * 3 + 0], S.jump[c * 3 + 1], S.jump[c * 3 + 2]};
+    long long step = S.step[c];
+    int kwin = S.kwin[c];
+    unsigned long long wbits = S.window_bits[c];
+    bool anneal_now = false;
+    double cur_loss_new = 0.0;
+    // shock annealing: switch to the annealed jump lengths and restart from the best model (learning_chain.py:349-367)
+    if (H.shock_anneal_at > 0 && step == H.shock_anneal_at) {
+        for (int k = 0; k < 3; ++k) jump[k] = H.jump_annealed[k];
+        anneal_now = true;
+        step += 1;
+#pragma unroll
+        for (int i = 0; i < CH_MAXQ; ++i)
+            if (have[i]) curv[i] = S.best[c * P + lane + 32 * i];
+        cur_loss_new = S.best_loss[c];
+        wbits = (wbits << 1) | 1ull;
+    }
+    // MH temperature (learning_chain.py:371, 945-958)
+    const double T = (H.temperature_scale > 0.0) ? rng.gamma(H.temperature, H.temperature_scale) : H.temperature;
+    // acceptance window -> jump length adaptation (learning_chain.py:374-388)
+    double last_ratio = 0.0;
+    bool new_ratio = false;
+    if (kwin >= H.window) {
+        kwin = 0;
+        const unsigned long long mask = (H.window >= 64) ? ~0ull : ((1ull << H.window) - 1ull);
+        const double ratio = (double)__popcll(wbits & mask) / (double)H.window;
+        last_ratio = ratio; new_ratio = true;
+        if (ratio - H.acc_target > H.acc_band) { for (int k = 0; k < 3; ++k) jump[k] *= 1.0 / H.jump_rescale; }
+        else if (ratio - H.acc_target < -H.acc_band) { for (int k = 0; k < 3; ++k) jump[k] *= H.jump_rescale; }
+    }
+    kwin += 1;
+    __syncwarp();      // every lane has read the chain's scalars: lane 0 may overwrite them
+    if (lane == 0) {
+        if (anneal_now) { S.annealed[c] = 1; S.cur_loss[c] = cur_loss_new; }
+        S.step[c] = step; S.window_bits[c] = wbits; S.kwin[c] = kwin; S.temp[c] = T;
+        if (new_ratio) S.last_ratio[c] = last_ratio;
+        for (int k = 0; k < 3; ++k) S.jump[c * 3 + k] = jump[k];
+    }
+    if (anneal_now) {
+#pragma unroll
+        for (int i = 0; i < CH_MAXQ; ++i)
+            if (have[i]) cur[lane + 32 * i] = curv[i];
+    }
+
+    // move choice: probability ~ priority x number of ways (learning_chain.py:409-414)
+    const WaysW wc = count_ways_warp(cc, curv, have);
+    double wsum = 0.0;
+    for (int m = 0; m < N_MOVES; ++m) wsum += H.priority[m] * wc.ways[m];
+    const double u = rng.uniform();
+#pragma unroll
+    for (int i = 0; i < CH_MAXQ; ++i) propv[i] = curv[i];
+    if (!(wsum > 0.0)) {
+        // no move with a non-zero priority is available: re-propose the current model with acceptance probability 0
+#pragma unroll
+        for (int i = 0; i < CH_MAXQ; ++i)
+            if (have[i]) prop[lane + 32 * i] = curv[i];
+        if (lane == 0) {
+            S.log_ratio[c] = 0.0; S.move[c] = MV_TWEAK; S.counters[c * 4 + 2] += 1; S.rng_ctr[c] = rng.ctr;
+        }
+        return;
+    }
+    int mv = N_MOVES - 1;
+    {
+        double cdf = 0.0;
+        for (int m = 0; m < N_MOVES; ++m) {
+            cdf += H.priority[m] * wc.ways[m] / wsum;
+            if (cdf > u) { mv = m; break; }
+        }
+        while (mv > 0 && wc.ways[mv] == 0.0) --mv;    // guard against round-off at the end of the cdf
+    }
+    double p_there, p_back;
+    if (mv == MV_TWEAK) {
+        // Gaussian jitter, up to 10 redraws into the class bounds (learning_model.py:144-191)
+        for (int i = 0; i < nq; ++i) {
+            const bool tw = have[i] && tweakable(cc[i], curv[i]);
+            const int pc = pclass(cc[i]);
+            int att = tw ? 1 : 0, my_off = -1;
+            double val = curv[i];
+            unsigned long long total = 0;
+            for (;;) {
+                int incl = att;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                const int excl = incl - att;
+                total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+                int natt = att;
+                if (tw && excl != my_off) {
+                    my_off = excl;
+                    Rng r{rng.key, rng.ctr + 2ull * (unsigned long long)excl};
+                    val = curv[i]; natt = 10;
+                    for (int a = 0; a < 10; ++a) {
+                        const double cand = curv[i] + jump[pc] * r.normal();
+                        if (cand >= H.lo[pc] && cand <= H.hi[pc]) { val = cand; natt = a + 1; break; }
+                    }
+                }
+                const bool changed = natt != att;
+                att = natt;
+                if (!__any_sync(0xffffffffu, changed)) break;
+            }
+            if (tw) propv[i] = val;
+            rng.ctr += 2ull * total;
+        }
+        p_there = xi_product_warp(H, cc, propv, have, jump, nq);    // learning_chain.py:454-487
+        p_back = xi_product_warp(H, cc, curv, have, jump, nq);
+    } else {
+        const int mcc = move_class(mv);
+        const bool add = is_add(mv);
+        const int n = (int)wc.ways[mv];
+        int pick = (int)(rng.uniform() * n);
+        if (pick >= n) pick = n - 1;
+        bool done = false;
+        for (int i = 0; i < nq && !done; ++i) {
+            const bool cand = have[i] && cc[i] == mcc && ((curv[i] == 0.0) == add);
+            const unsigned cm = __ballot_sync(0xffffffffu, cand);
+            const int cnt = __popc(cm);
+            if (pick < cnt) {
+                int sel = 0;       // lane of the (pick + 1)-th candidate
+                {
+                    unsigned rest = cm;
+                    for (int j = 0; j < pick; ++j) rest &= rest - 1u;
+                    sel = __ffs(rest) - 1;
+                }
+                const int pc = pclass(mcc);
+                const double v = add ? H.lo[pc] + (H.hi[pc] - H.lo[pc]) * rng.uniform() : 0.0;   // process_handling.py:98-103
+                if (lane == sel) propv[i] = v;
+                done = true;
+            } else {
+                pick -= cnt;
+            }
+        }
+        const WaysW wp = count_ways_warp(cc, propv, have);
+        double wsum_p = 0.0;
+        for (int m = 0; m < N_MOVES; ++m) wsum_p += H.priority[m] * wp.ways[m];
+        p_there = H.priority[mv] / wsum;                           // learning_chain.py:493-498
+        p_back = H.priority[complement(mv)] / wsum_p;
+    }
+    const int n_prop = count_ways_warp(cc, propv, have).n_proc, n_cur = wc.n_proc;
+#pragma unroll
+    for (int i = 0; i < CH_MAXQ; ++i)
+        if (have[i]) prop[lane + 32 * i] = propv[i];
+    if (lane == 0) {
+        // prior ratio exp(-n/cf) with the reference's sub-precision guards (learning_chain.py:792-800)
+        const double PP = exp(-(double)n_prop / H.complexity_factor), PC = exp(-(double)n_cur / H.complexity_factor);
+        double prior_ratio;
+        if (fabs(PP) < 1e-40 && fabs(PC) < 1e-40) prior_ratio = 1.0;
+        else if (fabs(PC) < 1e-40) prior_ratio = INFINITY;
+        else prior_ratio = PP / PC;
+        S.log_ratio[c] = prior_ratio * p_back / p_there;     // stored as a plain ratio
+        S.move[c] = mv;
+        S.counters[c * 4 + (mv == MV_TWEAK ? 2 : 0)] += 1;
+        S.rng_ctr[c] = rng.ctr;
+    }
+}
+
+__global__ void chains_accept_warp_kernel(const ChainHyperDev H, const ChainState S, const int* __restrict__ eval_status,
+                                                                 const long long c_lo, const long long c_hi, const unsigned long long seed,
+                                                                 const long long first_chain, double* hist_loss, double* hist_aprob,
+                                                                 int* hist_code, double* hist_params) {
+    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= c_hi) return;      // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int P = H.n_params;
+    Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
+    const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
+    const double best_before = S.best_loss[c];
+    const double a = exp(-1.0 / S.temp[c] * (Lp - Lc)) * S.log_ratio[c];     // learning_chain.py:802-805
+    // a proposal whose evaluation did not converge must never be accepted or become the best model; the uniform draw is
+    // consumed either way so that the random stream does not depend on it
+    const bool usable = eval_status[c] >= 0 && isfinite(Lp);
+    const bool accept = (rng.uniform() < a) && usable;
+    const int mv = S.move[c];
+    const bool new_best = accept && Lp < best_before;
+    int n_proc = 0;
+    for (int p = lane; p < P; p += 32) {
+        const double pv = S.prop[c * P + p], cv = accept ? pv : S.cur[c * P + p];
+        if (accept) {
+            S.cur[c * P + p] = pv;
+            if (new_best) S.best[c * P + p] = pv;
+        }
+        if (hist_params) hist_params[c * P + p] = cv;
+        const int cls = H.col_class[p];
+        if (cls >= 1 && cls <= 4 && cv != 0.0) ++n_proc;
+    }
+    n_proc = __reduce_add_sync(0xffffffffu, n_proc);
+    __syncwarp();      // every lane has read the chain's scalars
+    if (lane == 0) {
+        if (!usable) S.bad_evals[c] += 1;
+        if (accept) {
+            S.cur_loss[c] = Lp;
+            if (new_best) S.best_loss[c] = Lp;
+            S.counters[c * 4 + (mv == MV_TWEAK ? 3 : 1)] += 1;
+        }
+        S.window_bits[c] = (S.window_bits[c] << 1) | (accept ? 1ull : 0ull);
+        S.step[c] += 1;
+        S.rng_ctr[c] = rng.ctr;
+        if (hist_loss) hist_loss[c] = Lp;
+        if (hist_aprob) hist_aprob[c] = a;
+        if (hist_code) hist_code[c] = (mv << 1) | (accept ? 1 : 0);
+        // statistics record for the checkpoint all_gather
+        double* st = S.stats + c * EML_CHAIN_STATS;
+        st[0] = accept ? Lp : Lc; st[1] = new_best ? Lp : best_before;
+        st[2] = S.counters[c * 4 + 3]; st[3] = S.counters[c * 4 + 2];
+        st[4] = S.counters[c * 4 + 1]; st[5] = S.counters[c * 4 + 0];
+        st[6] = S.last_ratio[c]; st[7] = n_proc;
+    }
+}
+
 __global__ void chains_init_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chains) return;
@@ -473,17 +753,28 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
             cudaStream_t gs = ch->gstream[g];
             const unsigned blocks = (unsigned)((cnt + 127) / 128);
             const int P = ch->H.n_params;
-            eml::chains_propose_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            static const bool thread_kernels = [] { const char* e = std::getenv("EML_CHAIN_THREAD_KERNELS"); return e && e[0] == '1'; }();
+            const bool warp_kernels = !thread_kernels && P <= 32 * eml::CH_MAXQ;
+            const unsigned wblocks = (unsigned)((cnt + 3) / 4);       // a warp per chain, four chains per CTA
+            if (warp_kernels) eml::chains_propose_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            else eml::chains_propose_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
             // the generator applications each chain's previous proposal needed order this step's models (longest first)
             int rc = eml_eval_batch_hinted(ch->plan, cnt, ch->S.prop + lo * P, ch->d_target_set ? ch->d_target_set + lo : nullptr,
                                            nullptr, ch->S.prop_loss + lo, ch->d_status + lo, gs, ch->d_status + lo,
                                            ch->g_counter[g], ch->g_order[g], ch->g_prep[g], cnt);
             if (rc != EML_OK) return rc;
-            eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
-                                                             hist_loss ? hist_loss + i * ch->n : nullptr,
-                                                             hist_aprob ? hist_aprob + i * ch->n : nullptr,
-                                                             hist_code ? hist_code + i * ch->n : nullptr,
-                                                             hist_params ? hist_params + i * ch->n * P : nullptr);
+            if (warp_kernels)
+                eml::chains_accept_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
+                                                                       hist_loss ? hist_loss + i * ch->n : nullptr,
+                                                                       hist_aprob ? hist_aprob + i * ch->n : nullptr,
+                                                                       hist_code ? hist_code + i * ch->n : nullptr,
+                                                                       hist_params ? hist_params + i * ch->n * P : nullptr);
+            else
+                eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
+                                                                 hist_loss ? hist_loss + i * ch->n : nullptr,
+                                                                 hist_aprob ? hist_aprob + i * ch->n : nullptr,
+                                                                 hist_code ? hist_code + i * ch->n : nullptr,
+                                                                 hist_params ? hist_params + i * ch->n * P : nullptr);
         }
     }
     // join: the caller's stream continues after both groups are done

@@ -81,6 +81,12 @@ constexpr int CHEB_UNROLL = EML_CHEB_UNROLL;
 #ifndef EML_OUTPUT_CHAINS
 #define EML_OUTPUT_CHAINS 1        // output times per lane and pass of the Bessel-weighted sums (measured: 2 chains +-0, 4 chains -6 %, 8 chains -22 %: the phase is bound by the FP64 pipe it shares with the recurrences of the other warps, not by the latency of its dependent FMA chain)
 #endif
+#ifndef EML_LAT_OUTPUT_CHAINS
+#define EML_LAT_OUTPUT_CHAINS 4    // output times per lane and pass in the latency variant (launches with fewer models than warp slots)
+#endif
+#ifndef EML_LAT_WARPS_PER_SM
+#define EML_LAT_WARPS_PER_SM 8     // resident warps per SM of the latency variant (<= 255 registers)
+#endif
 #ifndef EML_WARPS_PER_SM_SB
 #define EML_WARPS_PER_SM_SB 16
 #endif
@@ -561,9 +567,13 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
     }
 }
 
-template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB>
+// LAT ("latency variant", Chebyshev kernels): chosen when a launch has no more models than this variant has warp slots, i.e.
+// when the FP64 pipe is mostly idle and a model's time is the latency of its own dependent chains: the Bessel-weighted
+// output sums run EML_LAT_OUTPUT_CHAINS independent output times per lane (the same phase is bound by the pipe, and slower
+// with several chains, when all 16 warps of an SM are busy), with the registers of 8 warps per SM.
+template <int TL, bool REAL_H, bool CHEB, bool PARITY, bool SB, bool LAT = false>
 // resident warps per SM: 16 (d = 8), 16 (d = 16 sector variant), 8 (d = 16); CTAS_PER_SM is quoted for four-warp CTAs
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (SB ? WARPS_PER_SM_SB : PARITY ? WARPS_PER_SM_PAR : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, LAT ? EML_LAT_WARPS_PER_SM / WARPS_PER_CTA : (SB ? WARPS_PER_SM_SB : PARITY ? WARPS_PER_SM_PAR : 4 * ((TL == 1) ? 4 : CTAS_PER_SM)) / WARPS_PER_CTA)
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
@@ -1483,24 +1493,35 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                     //      and three subtractions, the even terms of the normalisation sum J_0 + 2 sum J_2k = 1 are known
                     //      statically, and the test "this chain starts here" is only needed down to the smallest start index
                     //      of the pass (a chain that has not started carries exact zeros).
-                    constexpr int NCH = EML_OUTPUT_CHAINS;
+                    //      The per-output scalar work (term count, 2 / z, e^{-ac tau}, observables) is written without branches
+                    //      so that the chains of a pass interleave: reciprocals by __drcp_rn instead of divisions, the term count
+                    //      from a single-precision cube root with an upward margin (a start index one too high costs one term),
+                    //      the exponential issued before the term loop, the observables' coefficients loaded once per pass.
+                    constexpr int NCH = LAT ? EML_LAT_OUTPUT_CHAINS : EML_OUTPUT_CHAINS;
                     const double t0o = P.times[kidx], tau_e = (P.times[kidx + q] - t0o) / nsub;
+                    const double tzs = 2.0 / Rb;
                     for (int pbase = 0; UNI(pbase < q); pbase += 32 * NCH) {
                         int Kp[NCH], pidx[NCH];
-                        double tz[NCH], tau[NCH];
+                        double tz[NCH], tau[NCH], ex[NCH];
                         bool direct[NCH];
                         int kmax = 0, kmin = 0x7fffffff;
 #pragma unroll
                         for (int c = 0; c < NCH; ++c) {
                             pidx[c] = q - 1 - pbase - 32 * c - lane;
                             const bool act = pidx[c] >= 0;
-                            tau[c] = act ? ((nsub == 1) ? P.times[kidx + 1 + pidx[c]] - t0o : tau_e) : 0.0;
-                            const double z = tau[c] * Rb;
+                            tau[c] = act ? ((nsub == 1) ? P.times[kidx + 1 + max(pidx[c], 0)] - t0o : tau_e) : 0.0;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            const double z = tau[c] * Rb, zs = tau[c] * Sb;
                             direct[c] = !(z >= 1e-40);
-                            Kp[c] = 0;
-                            if (act && !direct[c]) { Kp[c] = cheb_terms(tau[c] * Sb); if (Kp[c] > Kc) Kp[c] = Kc; kmin = min(kmin, Kp[c]); }
+                            const int kraw = (int)ceil(fma(CHEB_C1 * (1.0 + 1e-6), (double)cbrtf((float)zs), zs) + (CHEB_C0 + 1e-3));
+                            const bool on = pidx[c] >= 0 && !direct[c];
+                            Kp[c] = on ? min(kraw, Kc) : 0;
+                            kmin = min(kmin, on ? Kp[c] : 0x7fffffff);
                             kmax = max(kmax, Kp[c]);
-                            tz[c] = direct[c] ? 0.0 : 2.0 / z;
+                            tz[c] = direct[c] ? 0.0 : tzs * __drcp_rn(tau[c]);
+                            ex[c] = exp(-ac * tau[c]);
                         }
                         kmax = __reduce_max_sync(0xffffffffu, kmax);
                         kmin = __reduce_min_sync(0xffffffffu, kmin);
@@ -1539,19 +1560,42 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
                         while (UNI(k >= 4)) four_terms(std::false_type{});
                         const double2 ta = SB ? make_double2(half_tr, half_tr) : *reinterpret_cast<const double2*>(&S.tr[0]);
                         const double2 tb = *reinterpret_cast<const double2*>(&S.tr[NTR - 2]);
+                        double r[NCH][4];
 #pragma unroll
                         for (int c = 0; c < NCH; ++c) {
-                            double r[4];
-                            if (direct[c]) {
-                                r[0] = ta.x; r[1] = ta.y; r[2] = tb.x; r[3] = tb.y;
-                            } else {
-                                const double nrm = exp(-ac * tau[c]) / (2.0 * ssum[c] + jn[c]);
-                                // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
-                                r[0] = SB ? half_tr : fma(jn[c], ta.x, a0[c]) * nrm; r[1] = (ta.x + ta.y) - r[0];
-                                r[2] = fma(jn[c], tb.x, a2[c]) * nrm; r[3] = fma(jn[c], tb.y, a3[c]) * nrm;
-                            }
-                            if (pidx[c] >= 0) finish_output(kidx + 1 + pidx[c], r);
+                            const double nrm = ex[c] * __drcp_rn(2.0 * ssum[c] + jn[c]);
+                            // the generator is trace preserving: rho11 = Tr rho(step start) - rho00 saves a quarter of the sums
+                            const double r0 = SB ? half_tr : fma(jn[c], ta.x, a0[c]) * nrm;
+                            r[c][0] = direct[c] ? ta.x : r0; r[c][1] = direct[c] ? ta.y : (ta.x + ta.y) - r0;
+                            r[c][2] = direct[c] ? tb.x : fma(jn[c], tb.x, a2[c]) * nrm; r[c][3] = direct[c] ? tb.y : fma(jn[c], tb.y, a3[c]) * nrm;
                         }
+                        double lsum[NCH];       // loss terms of one output time are summed first (the same order whatever NCH is)
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) lsum[c] = 0.0;
+                        for (int m = 0; m < K; ++m) {      // as finish_output, the coefficients of an observable shared by the chains
+                            const double* O = P.obs + m * 8;
+                            const double c0 = O[0], c1 = O[6], c2 = O[2] + O[4], c3 = O[3] - O[5];
+                            const double d0 = O[1], d1 = O[7], d2 = O[3] + O[5], d3 = O[4] - O[2];
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) {
+                                const int kk = kidx + 1 + max(pidx[c], 0);
+                                const double ere = c0 * r[c][0] + c1 * r[c][1] + c2 * r[c][2] + c3 * r[c][3];
+                                const double eim = d0 * r[c][0] + d1 * r[c][1] + d2 * r[c][2] + d3 * r[c][3];
+                                if (pidx[c] >= 0) {
+                                    if (expect != nullptr) {      // (caller-owned: only 8-byte alignment is assumed)
+                                        double* eo = expect + (((size_t)b * K + m) * T + kk) * 2;
+                                        eo[0] = ere; eo[1] = eim;
+                                    }
+                                    if (tgt != nullptr) {
+                                        const double2 tg = *reinterpret_cast<const double2*>(tgt + ((size_t)m * T + kk) * 2);
+                                        const double dre = ere - tg.x, dim = eim - tg.y;
+                                        lsum[c] += dre * dre + dim * dim;
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) my_loss += lsum[c];
                     }
                     __syncwarp();
                     PHASE_MARK(3);      // Bessel-weighted output sums, observables, loss terms
@@ -1719,6 +1763,9 @@ EML_WARP_INST(1, true, false, false, false) EML_WARP_INST(1, false, false, false
 EML_WARP_INST(1, true, true, false, false) EML_WARP_INST(1, false, true, false, false) EML_WARP_INST(2, true, true, false, false) EML_WARP_INST(2, false, true, false, false)
 EML_WARP_INST(2, true, true, true, false) EML_WARP_INST(2, false, true, true, false)
 EML_WARP_INST(2, true, true, true, true) EML_WARP_INST(2, false, true, true, true)
+#define EML_WARP_INST_LAT(TL, RH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, true, PA, SB, true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+EML_WARP_INST_LAT(1, true, false, false) EML_WARP_INST_LAT(1, false, false, false) EML_WARP_INST_LAT(2, true, false, false) EML_WARP_INST_LAT(2, false, false, false)
+EML_WARP_INST_LAT(2, true, true, false) EML_WARP_INST_LAT(2, false, true, false) EML_WARP_INST_LAT(2, true, true, true) EML_WARP_INST_LAT(2, false, true, true)
 
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1761,6 +1808,7 @@ using PrepKern = void (*)(const DevProblem, const long long, const double*, doub
 
 struct WarpVariant {
     WarpKern eval = nullptr;
+    WarpKern eval_lat = nullptr; // latency variant (Chebyshev kernels): launches with no more models than it has warp slots
     PrepKern prep = nullptr;     // Chebyshev variants only
     size_t smem = 0, prep_smem = 0;
     int rec = 0, kcap = 0, id = 0;
@@ -1773,6 +1821,7 @@ static WarpVariant make_variant() {
     v.kcap = WarpScratch<TL, CH, SB, PA>::KCAP;
     v.id = (SB ? 16 : 0) + (PA ? 8 : 0) + (TL == 2 ? 4 : 0) + (CH ? 2 : 0) + (RH ? 1 : 0);
     if constexpr (CH) {
+        v.eval_lat = (WarpKern)eval_warp_mma_kernel<TL, RH, CH, PA, SB, true>;
         v.prep = (PrepKern)prepare_models_kernel<TL, RH, PA>;
         v.prep_smem = PREP_WARPS * sizeof(PrepScratch<TL, RH>);
         v.rec = prep_record_doubles<TL, RH, PA>();
@@ -1813,8 +1862,16 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     const WarpVariant v = pick_variant(tl2, real_h, chebyshev, parity, sector);
     // per device and kernel variant: dynamic shared memory opt-in and the resident CTAs per SM
     static int per_sm_cache[64][32] = {{0}};
+    static int per_sm_lat_cache[64][32] = {{0}};
     int per_sm = (dev < 64) ? per_sm_cache[dev][v.id] : 0;
+    int per_sm_lat = (dev < 64) ? per_sm_lat_cache[dev][v.id] : 0;
     if (per_sm == 0) {
+        if (v.eval_lat != nullptr) {
+            if ((e = cudaFuncSetAttribute(v.eval_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lat, v.eval_lat, WARPS_PER_CTA * 32, v.smem)) != cudaSuccess) return e;
+            if (per_sm_lat < 1) per_sm_lat = 1;
+            if (dev < 64) per_sm_lat_cache[dev][v.id] = per_sm_lat;
+        }
         if ((e = cudaFuncSetAttribute(v.eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem)) != cudaSuccess) return e;
         if (v.prep != nullptr &&
             (e = cudaFuncSetAttribute(v.prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(v.prep_smem + PREP_LIN_STAGE_MAX))) != cudaSuccess) return e;
@@ -1857,8 +1914,11 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
             launch_model_order(P, n, p_, order, cost_hint ? cost_hint + off : nullptr, stream);
         }
         long long ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        // every model gets a warp at once and the SMs are at most half full: the latency variant
+        static const bool lat_on = [] { const char* e = std::getenv("EML_LATENCY_VARIANT"); return !(e && e[0] == '0'); }();
+        const bool lat = lat_on && v.eval_lat != nullptr && ctas <= (long long)sms * per_sm_lat;
         if (ctas > max_ctas) ctas = max_ctas;
-        v.eval<<<(unsigned)ctas, WARPS_PER_CTA * 32, v.smem, stream>>>(P, n, p_, ts_, ex_, lo_, st_, counter, sort ? order : nullptr,
+        (lat ? v.eval_lat : v.eval)<<<(unsigned)ctas, WARPS_PER_CTA * 32, v.smem, stream>>>(P, n, p_, ts_, ex_, lo_, st_, counter, sort ? order : nullptr,
                                                                       prep_ws);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
