@@ -8,6 +8,8 @@ cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams
 ts = np.linspace(0, 2.5, 200)
 import os
 SHAPES = ((3, 4096, 100),) if os.environ.get("EML_CHAIN_GROUPS") else ((1, 1024, 200), (1, 8192, 100), (2, 1024, 200), (2, 8192, 100), (3, 512, 100), (3, 4096, 100))
+if len(sys.argv) > 1:       # shapes on the command line: D:chains:steps ...
+    SHAPES = tuple(tuple(int(x) for x in a.split(':')) for a in sys.argv[1:])
 for D, C, steps in SHAPES:
     lay = synthetic.LibraryLayout(1, D, cfg)
     ctx = lay.context(ts, OBS3)
