@@ -1767,6 +1767,367 @@ EML_WARP_INST(2, true, true, true, true) EML_WARP_INST(2, false, true, true, tru
 EML_WARP_INST_LAT(1, true, false, false) EML_WARP_INST_LAT(1, false, false, false) EML_WARP_INST_LAT(2, true, false, false) EML_WARP_INST_LAT(2, false, false, false)
 EML_WARP_INST_LAT(2, true, true, false) EML_WARP_INST_LAT(2, false, true, false) EML_WARP_INST_LAT(2, true, true, true) EML_WARP_INST_LAT(2, false, true, true)
 
+// =====================================================================================================================
+// d = 4 (and d = 2): TWO MODELS PER WARP.  Models with one or two sites are embedded into three sites by spectator sites in
+// |0><0| (identity dynamics), so only the block of the 8 x 8 tile with spectator bit 0 in row and column is alive.  The
+// lowest bit of the kernel's index is such a spectator bit: here it is the MODEL index instead -- rho = rho_A (+) rho_B,
+// G = G_A (+) G_B (the records of the prepare kernel already hold G_4 (x) 1, so lane (g, t) simply reads the fragments of
+// model g & 1), weights, shift and scale of the Chebyshev recurrence per row model.  No flip connects the two blocks, so
+// one recurrence (the same DMMAs, half the stencils: the spectator's flip is dropped) advances both models; the macro steps
+// follow the shorter tau_max, the number of terms the longer series.  Partial traces are kept per model (8 values per
+// term), the Bessel-weighted output sums, observables and losses are per model as in eval_warp_mma_kernel.
+// Used for launches with more models than warp slots (below that the FP64 pipe is idle and two warps are faster than one).
+struct alignas(16) Pack2Scratch {
+    static constexpr int KCAP = 124;     // terms per macro step: the trace table holds 8 values per term
+    double jw[2][32];
+    double gdiag[2][16];
+    double plan[2][4];                   // R, S, ac, tau_max per model
+    alignas(16) double xt_re[128];
+    alignas(16) double xt_im[128];
+    double cj[2][KCAP + 2];
+    alignas(16) double tr[(KCAP + 4) * 8];
+};
+
+template <bool REAL_H>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 16 / WARPS_PER_CTA)
+eval_pack2_kernel(const DevProblem P, const long long n_models, const int* __restrict__ target_set, double* __restrict__ expect,
+                  double* __restrict__ loss, int* __restrict__ status, unsigned int* __restrict__ counter,
+                  const int* __restrict__ order, const double* __restrict__ prep) {
+    constexpr int N = 3, D = 8, KCAP = Pack2Scratch::KCAP;
+    constexpr int NA = prep_fragments<1, REAL_H, false>(), REC = prep_record_doubles<1, REAL_H, false>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pack2Scratch& S = reinterpret_cast<Pack2Scratch*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, gp = g & 1;
+    const int mr = g & 1;                 // the model this lane's row belongs to
+    const int T = P.n_times, K = P.n_obs;
+    const int obs_site = P.obs_site;
+    auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
+    auto orig_index = [&](int x) {
+        int o = 0;
+#pragma unroll
+        for (int s = 0; s < N; ++s) o |= ((x >> pos(s)) & 1) << (N - 1 - s);
+        return o;
+    };
+    // partial-trace lanes (see trace_put below)
+    const int tl = lane & ~4;
+    const bool tr_lane = (tl == 0 || tl == 18 || tl == 2 || tl == 11);
+    const int tr_off = 4 * mr + (tl == 0 ? 0 : tl == 18 ? 1 : tl == 2 ? 2 : 3);
+    const long long n_units = (n_models + 1) / 2;
+
+    for (;;) {
+        unsigned int bidx = 0;
+        if (lane == 0) bidx = atomicAdd(counter, 1u);
+        bidx = __shfl_sync(0xffffffffu, bidx, 0);
+        if (UNI((long long)bidx >= n_units)) break;
+        long long bm[2];
+        bool live[2] = {true, 2LL * bidx + 1 < n_models};
+        bm[0] = (order != nullptr) ? order[2LL * bidx] : 2LL * bidx;
+        bm[1] = live[1] ? ((order != nullptr) ? order[2LL * bidx + 1] : 2LL * bidx + 1) : bm[0];
+        // a model that cannot be evaluated (non-finite parameters or an absurd step count: R = NaN) is reported and its slot
+        // runs a copy of its partner, so that nothing non-finite enters the shared tile
+        long long src[2] = {bm[0], bm[1]};
+        {
+            const double r0 = prep[(size_t)bm[0] * REC + NA * 32 + 48], r1 = prep[(size_t)bm[1] * REC + NA * 32 + 48];
+            const bool bad0 = !(r0 == r0), bad1 = !(r1 == r1);
+            if (lane == 0) {
+                if (bad0) { if (loss != nullptr) loss[bm[0]] = nan(""); if (status != nullptr) status[bm[0]] = -1; }
+                if (bad1 && live[1]) { if (loss != nullptr) loss[bm[1]] = nan(""); if (status != nullptr) status[bm[1]] = -1; }
+            }
+            if (bad0) live[0] = false;
+            if (bad1) live[1] = false;
+            if (UNI(!live[0] && !live[1])) { __syncwarp(); continue; }
+            if (bad0) src[0] = bm[1];
+            if (bad1 || !live[1]) src[1] = live[0] ? bm[0] : bm[1];
+        }
+        __syncwarp();      // the previous unit's readers of the scratch are done
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const double* const R = prep + (size_t)src[m] * REC;
+            S.jw[m][lane] = R[NA * 32 + lane];
+            if (lane < 16) S.gdiag[m][lane] = R[NA * 32 + 32 + lane];
+            if (lane < 4) S.plan[m][lane] = R[NA * 32 + 48 + lane];
+        }
+        double a_re[2], a_im[2];
+        {
+            const double* const R = prep + (size_t)src[mr] * REC;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                a_im[ks] = R[ks * 32 + lane];
+                a_re[ks] = REAL_H ? 0.0 : R[(2 + ks) * 32 + lane];
+            }
+        }
+        __syncwarp();
+        // ---- weights of this lane's row model: generator -> 2 (L + ac) / R, stencil weights halved (X' + X'^dag doubles them)
+        const double* const jwp = S.jw[mr];
+        const double sc = 2.0 / S.plan[mr][0], acl = S.plan[mr][2];
+        double W0[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double w = jwp[2 * 8 + (g >> 2) * 2 + (t >> 1)] + jwp[1 * 8 + ((g >> 1) & 1) * 2 + (t & 1)] + jwp[0 * 8 + (g & 1) * 2 + e];
+            if (REAL_H) w += S.gdiag[mr][g] + S.gdiag[mr][2 * t + e];
+            W0[e] = (0.5 * w + 0.5 * acl) * sc;
+        }
+        const double f2 = 0.5 * jwp[2 * 8 + 4 + (g >> 2) * 2 + (t >> 1)] * sc;
+        const double f1 = 0.5 * jwp[1 * 8 + 4 + ((g >> 1) & 1) * 2 + (t & 1)] * sc;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) { a_re[ks] *= sc; a_im[ks] *= sc; }
+        // ---- state: block (model, model) of the tile carries rho0 of the embedded problem (spectator bits cleared)
+        double acc_re[2], acc_im[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = orig_index(g & ~1), c = orig_index(2 * t);
+            const bool alive = (e == mr);
+            acc_re[e] = alive ? P.rho0[2 * (r * D + c)] : 0.0;
+            acc_im[e] = alive ? P.rho0[2 * (r * D + c) + 1] : 0.0;
+        }
+        const double* tgt[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int tset = (target_set != nullptr) ? target_set[bm[m]] : 0;
+            tgt[m] = (P.targets != nullptr) ? P.targets + (size_t)tset * K * T * 2 : nullptr;
+        }
+        double my_loss[2] = {0.0, 0.0};
+        int n_apply = 0;
+        bool capped = false;
+
+        // 2x2 partial trace per model: a partial-trace element (row and column agree on the non-observed bits, the model bit
+        // included) sits at e = g & 1 of the lanes with t0 = g1; summing over g1 (lane ^ 9) leaves model g0's totals of the
+        // observed-bit pair (g2, t1) in lanes 16 g2 + 2 t1 + 4 g0 (and their partners ^ 9): rho00 <- lane 4m, rho11 <- 18 + 4m,
+        // Re rho01 <- 2 + 4m, Im rho01 <- 11 + 4m
+        const unsigned tr_base = (unsigned)__cvta_generic_to_shared(&S.tr[tr_off]);
+        auto trace_put = [&](const double (&xr)[2], const double (&xi)[2], const int kterm) {
+            const double er = gp ? xr[1] : xr[0], ei = gp ? xi[1] : xi[0];
+            const double sr = er + __shfl_xor_sync(0xffffffffu, er, 9), si = ei + __shfl_xor_sync(0xffffffffu, ei, 9);
+            EML_CHECK(kterm >= 0 && kterm <= KCAP);
+            asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }"
+                         :: "r"(tr_base + (unsigned)(kterm * 64)), "d"(tl == 11 ? si : sr), "r"((int)tr_lane) : "memory");
+        };
+        auto finish_output = [&](const int m, const int k, const double (&r)[4]) {
+            double ls = 0.0;
+            for (int o = 0; o < K; ++o) {
+                const double* O = P.obs + o * 8;
+                const double ere = O[0] * r[0] + O[6] * r[1] + (O[2] + O[4]) * r[2] + (O[3] - O[5]) * r[3];
+                const double eim = O[1] * r[0] + O[7] * r[1] + (O[3] + O[5]) * r[2] + (O[4] - O[2]) * r[3];
+                if (expect != nullptr) {
+                    double* e = expect + (((size_t)bm[m] * K + o) * T + k) * 2;
+                    e[0] = ere; e[1] = eim;
+                }
+                if (tgt[m] != nullptr) {
+                    const double dre = ere - tgt[m][((size_t)o * T + k) * 2], dim = eim - tgt[m][((size_t)o * T + k) * 2 + 1];
+                    ls += dre * dre + dim * dim;
+                }
+            }
+            my_loss[m] += ls;
+        };
+        auto first_like_output = [&](const int kfirst, const int count) {     // the state itself at `count` output times from kfirst
+            __syncwarp();
+            trace_put(acc_re, acc_im, 0);
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (!live[m]) continue;
+                const double r[4] = {S.tr[4 * m], S.tr[4 * m + 1], S.tr[4 * m + 2], S.tr[4 * m + 3]};
+                for (int pb = 0; UNI(pb < count); pb += 32)
+                    if (pb + lane < count) finish_output(m, kfirst + pb + lane, r);
+            }
+            __syncwarp();
+        };
+        first_like_output(0, 1);
+
+        const double tau_max = fmin(S.plan[0][3], S.plan[1][3]);
+        int kidx = 0;
+        while (UNI(kidx < T - 1)) {
+            const double t0 = P.times[kidx];
+            int q = 0;
+            for (;;) {
+                const int cand = kidx + q + 1 + lane;
+                const unsigned in = __ballot_sync(0xffffffffu, cand <= T - 1 && P.times[min(cand, T - 1)] - t0 <= tau_max);
+                const int run = __ffs(~in) - 1;
+                if (run >= 0) { q += run; break; }
+                q += 32;
+            }
+            int nsub = 1;
+            if (UNI(q == 0)) { nsub = (int)ceil((P.times[kidx + 1] - t0) / tau_max); q = 1; }
+            const double tau_end = (P.times[kidx + q] - t0) / nsub;
+            const bool final_step = (kidx + q == T - 1);
+            if (UNI(!(tau_end * fmin(S.plan[0][0], S.plan[1][0]) >= 1e-40))) {     // repeated time points: the state does not move
+                first_like_output(kidx + 1, q);
+                kidx += q;
+                continue;
+            }
+            int Kcm[2], Kc = 0;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) { Kcm[m] = min(cheb_terms(tau_end * S.plan[m][1]), KCAP); Kc = max(Kc, Kcm[m]); }
+            for (int sub = 0; UNI(sub < nsub); ++sub) {
+                const bool last = (sub == nsub - 1);
+                const bool need_acc = UNI(!(final_step && last));
+                double cscale = 0.0;       // of this lane's row model
+                if (need_acc) {
+                    __syncwarp();
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const double tz = 2.0 / (tau_end * S.plan[m][0]);
+                        double jn = 1.0, jn1 = 0.0, ssum = 0.0;
+                        for (int k = Kc; k >= 1; --k) {
+                            if ((k & 31) == lane) S.cj[m][k] = jn;
+                            if (!(k & 1)) ssum += jn;
+                            const double jm = fma((double)k * tz, jn, -jn1);
+                            jn1 = jn; jn = jm;
+                        }
+                        if (lane == 0) S.cj[m][0] = jn;
+                        const double cs = exp(-S.plan[m][2] * tau_end) / (2.0 * ssum + jn);
+                        if (m == mr) cscale = cs;
+                    }
+                    __syncwarp();
+                }
+                double v_re[2] = {acc_re[0], acc_re[1]}, v_im[2] = {acc_im[0], acc_im[1]}, ph_re[2] = {0.0, 0.0}, ph_im[2] = {0.0, 0.0};
+                acc_re[0] = acc_re[1] = acc_im[0] = acc_im[1] = 0.0;
+                auto run_terms = [&](auto na_tag) {
+                    constexpr bool NAC = decltype(na_tag)::value;
+                    double hmul = 1.0;
+                    for (int k = 0; UNI(k < Kc); ++k) {
+                        trace_put(v_re, v_im, k);
+                        if constexpr (NAC) {
+                            const double c = S.cj[mr][k] * cscale;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { acc_re[e] = fma(c, v_re[e], acc_re[e]); acc_im[e] = fma(c, v_im[e], acc_im[e]); }
+                        }
+                        double x_re[2], x_im[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) { x_re[e] = fma(W0[e], v_re[e], ph_re[e]); x_im[e] = fma(W0[e], v_im[e], ph_im[e]); }
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_re[e], 18), x_re[e]);
+                            x_im[e] = fma(f2, __shfl_xor_sync(0xffffffffu, v_im[e], 18), x_im[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            x_re[e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_re[e], 9), x_re[e]);
+                            x_im[e] = fma(f1, __shfl_xor_sync(0xffffffffu, v_im[e], 9), x_im[e]);
+                        }
+                        // X' = J(v)/2 + G v on the DMMA pipe, B = conj of the lane's own registers
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            if (!REAL_H) {
+                                dmma(x_re[0], x_re[1], a_re[ks], v_re[ks]);
+                                dmma(x_im[0], x_im[1], a_re[ks], neg(v_im[ks]));
+                            }
+                            dmma(x_re[0], x_re[1], a_im[ks], v_im[ks]);
+                            dmma(x_im[0], x_im[1], a_im[ks], v_re[ks]);
+                        }
+                        // w = X' + X'^dag through the swizzled tile (as the d = 8 kernel)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int Cc = 2 * t + e;
+                            const int m_ = 4 * (t & 1) + 8 * (((t >> 1) & 1) ^ e);
+                            S.xt_re[Cc * 16 + (g ^ m_)] = x_re[e];
+                            S.xt_im[Cc * 16 + (g ^ m_)] = x_im[e];
+                        }
+                        __syncwarp();
+                        {
+                            const int m_ = 4 * ((g >> 1) & 1) + 8 * (((g >> 2) & 1) ^ (g & 1));
+                            const int o = g * 16 + ((2 * t) ^ m_);
+                            const double2 tr_ = *reinterpret_cast<const double2*>(&S.xt_re[o]);
+                            const double2 ti_ = *reinterpret_cast<const double2*>(&S.xt_im[o]);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { ph_re[e] = hmul * v_re[e]; ph_im[e] = hmul * v_im[e]; }
+                            v_re[0] = x_re[0] + tr_.x; v_re[1] = x_re[1] + tr_.y;
+                            v_im[0] = x_im[0] - ti_.x; v_im[1] = x_im[1] - ti_.y;
+                        }
+                        __syncwarp();
+                        hmul = 0.5;
+                    }
+                    trace_put(v_re, v_im, Kc);
+                    if constexpr (NAC) {
+                        const double c = S.cj[mr][Kc] * cscale;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) { acc_re[e] = fma(c, v_re[e], acc_re[e]); acc_im[e] = fma(c, v_im[e], acc_im[e]); }
+                    }
+                };
+                if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
+                {
+                    const double chk = fabs(v_re[0]) + fabs(v_im[0]) + fabs(v_re[1]) + fabs(v_im[1]);
+                    if (!UNI(chk < 1e300)) capped = true;
+                }
+                n_apply += Kc;
+                if (lane < 24) S.tr[(Kc + 1) * 8 + lane] = 0.0;      // the output sums read the table in groups of four terms
+                __syncwarp();
+                if (UNI(last)) {
+                    // ---- outputs of the step, per model: as eval_warp_mma_kernel (one output time per lane and pass, passes cut
+                    //      from the end of the list, terms in groups of four)
+                    const double t0o = P.times[kidx], tau_e = (P.times[kidx + q] - t0o) / nsub;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        if (!live[m]) continue;
+                        const double Rb = S.plan[m][0], Sb = S.plan[m][1], acm = S.plan[m][2];
+                        const double tzs = 2.0 / Rb;
+                        for (int pbase = 0; UNI(pbase < q); pbase += 32) {
+                            const int pidx = q - 1 - pbase - lane;
+                            const bool act = pidx >= 0;
+                            const double tau = act ? ((nsub == 1) ? P.times[kidx + 1 + max(pidx, 0)] - t0o : tau_e) : 0.0;
+                            const double z = tau * Rb, zs = tau * Sb;
+                            const bool direct = !(z >= 1e-40);
+                            const int kraw = (int)ceil(fma(CHEB_C1 * (1.0 + 1e-6), (double)cbrtf((float)zs), zs) + (CHEB_C0 + 1e-3));
+                            const bool on = act && !direct;
+                            const int Kp = on ? min(kraw, Kcm[m]) : 0;
+                            const int kmax = __reduce_max_sync(0xffffffffu, Kp);
+                            const int kmin = __reduce_min_sync(0xffffffffu, on ? Kp : 0x7fffffff);
+                            const double tz = direct ? 0.0 : tzs * __drcp_rn(tau);
+                            const double ex = exp(-acm * tau);
+                            double a0 = 0.0, a2 = 0.0, a3 = 0.0, ssum = 0.0, jn = 0.0, jn1 = 0.0;
+                            int k = (kmax + 3) & ~3;
+                            double kd = (double)k;
+                            auto four_terms = [&](auto chk_tag) {
+                                constexpr bool CHK = decltype(chk_tag)::value;
+                                double cm = kd * tz;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int kk = k - j;
+                                    EML_CHECK(kk >= 1 && kk <= Kc + 3 && kk <= KCAP + 3);
+                                    const double2 ta = *reinterpret_cast<const double2*>(&S.tr[kk * 8 + 4 * m]);
+                                    const double2 tb = *reinterpret_cast<const double2*>(&S.tr[kk * 8 + 4 * m + 2]);
+                                    if constexpr (CHK)
+                                        jn = __hiloint2double(kk == Kp ? 0x3ff00000 : __double2hiint(jn), __double2loint(jn));
+                                    a0 = fma(jn, ta.x, a0); a2 = fma(jn, tb.x, a2); a3 = fma(jn, tb.y, a3);
+                                    if (!(j & 1)) ssum += jn;
+                                    const double jm = fma(cm, jn, -jn1);
+                                    jn1 = jn; jn = jm;
+                                    if (j < 3) cm -= tz;
+                                }
+                                k -= 4; kd -= 4.0;
+                            };
+                            while (UNI(k >= 4 && k >= kmin)) four_terms(std::true_type{});
+                            while (UNI(k >= 4)) four_terms(std::false_type{});
+                            const double2 ta = *reinterpret_cast<const double2*>(&S.tr[4 * m]);
+                            const double2 tb = *reinterpret_cast<const double2*>(&S.tr[4 * m + 2]);
+                            const double nrm = ex * __drcp_rn(2.0 * ssum + jn);
+                            const double r0 = fma(jn, ta.x, a0) * nrm;
+                            const double r[4] = {direct ? ta.x : r0, direct ? ta.y : (ta.x + ta.y) - r0,
+                                                 direct ? tb.x : fma(jn, tb.x, a2) * nrm, direct ? tb.y : fma(jn, tb.y, a3) * nrm};
+                            if (act) finish_output(m, kidx + 1 + pidx, r);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            kidx += q;
+        }
+        // ---- losses, fixed-order warp reductions
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_loss[m] += __shfl_xor_sync(0xffffffffu, my_loss[m], o);
+            if (lane == 0 && live[m]) {
+                if (loss != nullptr) loss[bm[m]] = (tgt[m] != nullptr) ? my_loss[m] / ((double)T * (double)K) : 0.0;
+                if (status != nullptr) status[bm[m]] = capped ? -1 : n_apply;
+            }
+        }
+        __syncwarp();
+    }
+}
+template __global__ void eval_pack2_kernel<true>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+template __global__ void eval_pack2_kernel<false>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n_models) cost[b] = (float)max(hint[b], 0);
@@ -1850,7 +2211,7 @@ size_t warp_prep_bytes_per_model(const DevProblem& P, bool real_h, bool chebyshe
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order,
                             bool real_h, bool chebyshev, bool parity_h, bool sector_b, const int* cost_hint,
-                            double* prep_ws, long long prep_cap, cudaStream_t stream) {
+                            double* prep_ws, long long prep_cap, bool pack2_ok, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1882,12 +2243,33 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
             fprintf(stderr, "eml: warp kernel variant %d: %d CTAs of %d warps per SM, %zu B shared memory per CTA\n", v.id, per_sm,
                     WARPS_PER_CTA, v.smem);
     }
+    // two d = 4 (d = 2) models per warp: launches with more models than warp slots (EML_PACK2=0 switches it off)
+    static const int pack2_mode = [] { const char* e = std::getenv("EML_PACK2"); return e ? std::atoi(e) : 1; }();      // 2: whenever n > slots
+    const bool pack2_on = pack2_mode != 0;
+    using PackKern = void (*)(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+    const PackKern pack_kern = real_h ? (PackKern)eval_pack2_kernel<true> : (PackKern)eval_pack2_kernel<false>;
+    const size_t pack_smem = WARPS_PER_CTA * sizeof(Pack2Scratch);
+    const bool pack2_possible = pack2_on && pack2_ok && chebyshev && !tl2;
+    static int per_sm_pack_cache[64][2] = {{0}};
+    int per_sm_pack = (dev < 64) ? per_sm_pack_cache[dev][real_h ? 1 : 0] : 0;
+    if (pack2_possible && per_sm_pack == 0) {
+        if ((e = cudaFuncSetAttribute(pack_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pack, pack_kern, WARPS_PER_CTA * 32, pack_smem)) != cudaSuccess) return e;
+        if (per_sm_pack < 1) per_sm_pack = 1;
+        if (dev < 64) per_sm_pack_cache[dev][real_h ? 1 : 0] = per_sm_pack;
+    }
     const long long max_ctas = (long long)sms * per_sm;      // persistent grid: every resident warp fetches models
     if (chebyshev && (prep_ws == nullptr || prep_cap < 1)) return cudaErrorInvalidValue;
     const long long chunk_cap = chebyshev ? prep_cap : n_models;
-    const double zcap = chebyshev ? cheb_zcap_for(v.kcap) : 0.0;
     for (long long off = 0; off < n_models; off += chunk_cap) {
         const long long n = (n_models - off < chunk_cap) ? n_models - off : chunk_cap;
+        // (a pair occupies one warp for one recurrence and TWO output phases: with fewer than ~3 models per warp slot the launch
+        //  is bound by that latency, not by the FP64 pipe, and one model per warp is faster: 5 001 models 26.0 M against 27.9 M
+        //  evaluations/s, 7 200 models 34.9 M against 30.0 M, 16 384 models 46.3 M against 33.3 M, 65 536 models 52.0 M against 35.5 M)
+        const long long pack2_min = (pack2_mode == 2 ? 2LL : 5LL) * WARPS_PER_CTA * max_ctas / 2;      // 2.5 models per warp slot
+        const bool pack2 = pack2_possible && n > pack2_min && n <= ORDER_MAX_MODELS && order != nullptr;
+        const int kcap = pack2 ? Pack2Scratch::KCAP : v.kcap;
+        const double zcap = chebyshev ? cheb_zcap_for(kcap) : 0.0;
         const double* p_ = params + off * P.n_params;
         const int* ts_ = target_set ? target_set + off : nullptr;
         double* ex_ = expect ? expect + (size_t)off * P.n_obs * P.n_times * 2 : nullptr;
@@ -1908,10 +2290,17 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
             if (prep_per_sm < 1) prep_per_sm = 1;
             long long pctas = (n + PREP_WARPS - 1) / PREP_WARPS;
             if (pctas > (long long)sms * prep_per_sm) pctas = (long long)sms * prep_per_sm;
-            v.prep<<<(unsigned)pctas, PREP_WARPS * 32, psmem, stream>>>(P, n, p_, prep_ws, sort ? cost : nullptr, zcap, v.kcap, stage);
+            v.prep<<<(unsigned)pctas, PREP_WARPS * 32, psmem, stream>>>(P, n, p_, prep_ws, sort ? cost : nullptr, zcap, kcap, stage);
             if (sort) order_models_kernel<<<1, 1024, 0, stream>>>((int)n, cost, order);
         } else if (sort) {
             launch_model_order(P, n, p_, order, cost_hint ? cost_hint + off : nullptr, stream);
+        }
+        if (pack2) {
+            long long pc = ((n + 1) / 2 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+            if (pc > (long long)sms * per_sm_pack) pc = (long long)sms * per_sm_pack;
+            pack_kern<<<(unsigned)pc, WARPS_PER_CTA * 32, pack_smem, stream>>>(P, n, ts_, ex_, lo_, st_, counter, sort ? order : nullptr, prep_ws);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            continue;
         }
         long long ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         // every model gets a warp at once and the SMs are at most half full: the latency variant
