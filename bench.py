@@ -536,7 +536,12 @@ def run_b200(args):
                    'partitioning': f'chains sharded contiguously over {world} GPU(s), no data-path collective; '
                                    'one all_gather of per-chain loss per timed region when n_gpus > 1'},
         'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(B * layout.n_params * 8),
-                'd2h_bytes_per_step': int(B * 8 + B * 4)},
+                'd2h_bytes_per_step': int(B * 8 + B * 4),
+                'transfer': 'EvalContext.evaluate -> eml_eval_batch_host with page-locked host arrays, every step: the prepare kernel '
+                            'reads the parameter matrix from the page-locked host memory itself and the evaluator stores loss and '
+                            'status there (unified addressing; the same bytes cross PCIe as with cudaMemcpyAsync, but inside the '
+                            'kernels instead of before and after them), then cudaStreamSynchronize; EML_HOST_ZEROCOPY=0 restores '
+                            'the explicit copies'},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'clocks': clocks,

@@ -507,6 +507,12 @@ static int ensure_staging(EmlPlan* plan, long long n) {
 
 extern "C" {
 
+// EML_HOST_ZEROCOPY=0: every host call copies through device buffers (A/B measurements)
+static bool zero_copy_on() {
+    static const bool on = [] { const char* e = std::getenv("EML_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
                         double* expect, double* loss) {
     if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");
@@ -532,15 +538,20 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
             cudaGraphExec_t exec = nullptr;
             bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                if (np) ok = cudaMemcpyAsync(plan->d_params, plan->h_params, np * sizeof(double), cudaMemcpyHostToDevice, s) == cudaSuccess && ok;
+                // the kernels read the parameters from, and write loss / status to, the plan's page-locked buffers directly
+                // (unified addressing: three copy nodes fewer on the critical path of a one-model call); observables, which a
+                // kernel writes in many small pieces, keep their device buffer and one bulk copy
+                const bool zc = zero_copy_on();
+                if (np && !zc) ok = cudaMemcpyAsync(plan->d_params, plan->h_params, np * sizeof(double), cudaMemcpyHostToDevice, s) == cudaSuccess && ok;
                 if (target_set) ok = cudaMemcpyAsync(plan->d_tset, plan->h_tset, n_models * sizeof(int), cudaMemcpyHostToDevice, s) == cudaSuccess && ok;
                 const long long before = g_launches.load();
-                ok = eml_eval_batch(plan, n_models, plan->d_params, target_set ? plan->d_tset : nullptr, expect ? plan->d_expect : nullptr,
-                                    loss ? plan->d_loss : nullptr, plan->d_status, s) == EML_OK && ok;
+                ok = eml_eval_batch(plan, n_models, zc ? plan->h_params : plan->d_params, target_set ? plan->d_tset : nullptr,
+                                    expect ? plan->d_expect : nullptr, loss ? (zc ? plan->h_loss : plan->d_loss) : nullptr,
+                                    zc ? plan->h_status : plan->d_status, s) == EML_OK && ok;
                 g_launches.store(before);      // nothing ran yet; replays are counted when they are launched
                 if (expect) ok = cudaMemcpyAsync(plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
-                if (loss) ok = cudaMemcpyAsync(plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
-                ok = cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
+                if (loss && !zc) ok = cudaMemcpyAsync(plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
+                if (!zc) ok = cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess && ok;
                 ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && ok && graph != nullptr;
             }
             if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -568,18 +579,30 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
             return EML_OK;
         }
     }
-    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used for the DMA directly
-    auto is_pinned = [](const void* ptr) {
-        if (!ptr) return false;
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) need no staging.  The parameter matrix
+    // is read exactly once, by the prepare kernel (or by the d = 32 / generic evaluator), and loss / status are written once
+    // per model: with unified addressing the kernels use the page-locked host memory itself, so the H2D copy (1.1 MB per
+    // 4096 d = 16 models) overlaps the prepare kernel instead of preceding it and the two small D2H copies disappear.
+    // Observables (many small stores per model) keep the device buffer and one bulk copy.
+    auto pinned_device_ptr = [](const void* ptr) -> void* {
+        if (!ptr) return nullptr;
         cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-        return at.type == cudaMemoryTypeHost;
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
     };
-    const bool params_pinned = np && is_pinned(params);
-    const bool loss_pinned = loss && is_pinned(loss);
-    const bool expect_pinned = expect && is_pinned(expect);
-    if (params_pinned) {
+    const bool zc = zero_copy_on();
+    const double* params_dev = np ? (const double*)pinned_device_ptr(params) : nullptr;
+    double* loss_dev = loss ? (double*)pinned_device_ptr(loss) : nullptr;
+    const bool expect_pinned = expect && pinned_device_ptr(expect) != nullptr;
+    const bool params_pinned = params_dev != nullptr, loss_pinned = loss_dev != nullptr;
+    const double* params_arg = plan->d_params;
+    if (params_pinned && zc) {
+        params_arg = params_dev;
+    } else if (params_pinned) {
         EML_CUDA(cudaMemcpyAsync(plan->d_params, params, np * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else if (np && zc) {
+        std::memcpy(plan->h_params, params, np * sizeof(double));      // pageable caller array: one host copy, then as above
+        params_arg = plan->h_params;
     } else if (np) {
         // staged in chunks so that the DMA of one chunk overlaps the host copy of the next
         const size_t chunk = (size_t)1 << 15;      // 256 KB of doubles
@@ -593,12 +616,13 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
         std::memcpy(plan->h_tset, target_set, n_models * sizeof(int));
         EML_CUDA(cudaMemcpyAsync(plan->d_tset, plan->h_tset, n_models * sizeof(int), cudaMemcpyHostToDevice, s));
     }
-    rc = eml_eval_batch(plan, n_models, plan->d_params, target_set ? plan->d_tset : nullptr,
-                        expect ? plan->d_expect : nullptr, loss ? plan->d_loss : nullptr, plan->d_status, s);
+    double* const loss_arg = !loss ? nullptr : (zc ? (loss_pinned ? loss_dev : plan->h_loss) : plan->d_loss);
+    rc = eml_eval_batch(plan, n_models, params_arg, target_set ? plan->d_tset : nullptr,
+                        expect ? plan->d_expect : nullptr, loss_arg, zc ? plan->h_status : plan->d_status, s);
     if (rc != EML_OK) return rc;
     if (expect) EML_CUDA(cudaMemcpyAsync(expect_pinned ? expect : plan->h_expect, plan->d_expect, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (loss) EML_CUDA(cudaMemcpyAsync(loss_pinned ? loss : plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
-    EML_CUDA(cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (loss && !zc) EML_CUDA(cudaMemcpyAsync(loss_pinned ? loss : plan->h_loss, plan->d_loss, n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (!zc) EML_CUDA(cudaMemcpyAsync(plan->h_status, plan->d_status, n_models * sizeof(int), cudaMemcpyDeviceToHost, s));
     EML_CUDA(cudaStreamSynchronize(s));
     if (expect && !expect_pinned) std::memcpy(expect, plan->h_expect, ne * sizeof(double));
     if (loss && !loss_pinned) std::memcpy(loss, plan->h_loss, n_models * sizeof(double));
