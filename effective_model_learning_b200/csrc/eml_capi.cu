@@ -23,8 +23,10 @@ size_t warp_prep_bytes_per_model(const DevProblem& P, bool real_h, bool chebyshe
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream);
+                           bool chebyshev, bool parity_h, const int* cost_hint, double* prep_ws, long long prep_cap, cudaStream_t stream);
 bool cta_mma_supported(const DevProblem& P, bool hermitian);
+size_t cta_orbit_prep_bytes_per_model(bool real_h);
+bool cta_orbit_selected();
 bool warp_mma_supported(const DevProblem& P, bool hermitian);
 cudaError_t measure_fp64(int use_mma, double seconds, double* flops_per_s);
 cudaError_t read_phase_clocks(unsigned long long* out, bool reset);
@@ -408,6 +410,8 @@ const char* eml_plan_kernel_name(const EmlPlan* plan) {
 
 // bytes of prepare-kernel workspace one model needs under this plan (0: the plan's kernel has no prepare pass)
 size_t eml_plan_prep_bytes_per_model(const EmlPlan* plan) {
+    if (plan && plan->kernel == EML_KERNEL_CTA_CHEB && plan->parity_h && eml::cta_orbit_selected())
+        return eml::cta_orbit_prep_bytes_per_model(plan->real_h);      // the d = 32 orbit kernel's records
     if (!plan || plan->kernel != EML_KERNEL_WARP_CHEB) return 0;
     return eml::warp_prep_bytes_per_model(plan->Pw, plan->real_h, true, plan->parity_h, plan->sector_b);
 }
@@ -418,8 +422,9 @@ static const long long kPrepMaxModels = 1 << 16;
 static int ensure_prep(EmlPlan* plan, long long n_models) {
     const size_t per = eml_plan_prep_bytes_per_model(plan);
     if (per == 0) return EML_OK;
-    long long want = n_models < 1024 ? 1024 : n_models;
-    if (want > kPrepMaxModels) want = kPrepMaxModels;
+    const long long cap = (per > 2048) ? (1 << 14) : kPrepMaxModels;       // d = 32 records are 4.7 KB: 77 MB at most
+    long long want = n_models < 1024 ? (per > 2048 ? (n_models < 256 ? 256 : n_models) : 1024) : n_models;
+    if (want > cap) want = cap;
     if (want <= plan->prep_cap) return EML_OK;
     plan->drop_host_graphs();
     if (plan->d_prep) { EML_CUDA(cudaFree(plan->d_prep)); plan->d_prep = nullptr; plan->prep_cap = 0; }   // cudaFree waits for work in flight
@@ -447,7 +452,7 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     int cur = -1;
     EML_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) EML_CUDA(cudaSetDevice(plan->device));
-    if (plan->kernel == EML_KERNEL_WARP_CHEB && !counter_ws) {
+    if (eml_plan_prep_bytes_per_model(plan) > 0 && !counter_ws) {
         const int rc = ensure_prep(plan, n_models);
         if (rc != EML_OK) { if (cur != plan->device && cur >= 0) cudaSetDevice(cur); return rc; }
         prep_ws = plan->d_prep; prep_cap = plan->prep_cap;
@@ -459,7 +464,8 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
                                  plan->P.n_tls <= 2, (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
-                                plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, (cudaStream_t)stream);
+                                plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, prep_ws, prep_cap,
+                                (cudaStream_t)stream);
     else
         e = eml::launch_generic(plan->P, n_models, params, target_set, expect, loss, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);   // the evaluator kernel (the optional ordering pre-pass is not counted)

@@ -782,7 +782,12 @@ bool cta_mma_supported(const DevProblem& P, bool hermitian) { return hermitian &
 
 // eml_cta_orbit.cu: the second-generation kernel for parity-conserving Hamiltonians (Chebyshev series)
 cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const double* params, const int* target_set, double* expect,
-                             double* loss, int* status, unsigned int* counter, const int* use_order, bool real_h, cudaStream_t stream);
+                             double* loss, int* status, unsigned int* counter, int* order, bool real_h, double* prep_ws,
+                             long long prep_cap, cudaStream_t stream);
+bool cta_orbit_selected() {
+    static const bool tilerow = [] { const char* e = std::getenv("EML_D32_TILEROW"); return e && e[0] == '1'; }();
+    return !tilerow;
+}
 
 // declared in eml_warp_mma.cu
 void launch_model_order(const DevProblem& P, long long n_models, const double* params, int* order, const int* cost_hint,
@@ -790,7 +795,7 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
 
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                            double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h,
-                           bool chebyshev, bool parity_h, const int* cost_hint, cudaStream_t stream) {
+                           bool chebyshev, bool parity_h, const int* cost_hint, double* prep_ws, long long prep_cap, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -804,6 +809,10 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
             if (dev < 64) done[dev] = true;
         }
     }
+    // parity-conserving H: the orbit kernel with its own prepare kernel (EML_D32_TILEROW=1 keeps the first-generation
+    // tile-row kernel, for A/B measurements)
+    if (parity_h && chebyshev && cta_orbit_selected())
+        return launch_cta_orbit(P, n_models, params, target_set, expect, loss, status, counter, order, real_h, prep_ws, prep_cap, stream);
     if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     const int* use_order = nullptr;
     if (order != nullptr && n_models > 2LL * sms && n_models <= (1 << 18)) {
@@ -813,10 +822,6 @@ cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
                           const int*, const double);
     const bool parity = parity_h && chebyshev;
-    // parity-conserving H: the orbit kernel (EML_D32_TILEROW=1 keeps the first-generation tile-row kernel, for A/B measurements)
-    static const bool tilerow = [] { const char* e = std::getenv("EML_D32_TILEROW"); return e && e[0] == '1'; }();
-    if (parity && !tilerow)
-        return launch_cta_orbit(P, n_models, params, target_set, expect, loss, status, counter, use_order, real_h, stream);
     const Kern kern = parity ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, true> : (Kern)eval_cta_mma_kernel<false, true, true>)
                     : chebyshev ? (real_h ? (Kern)eval_cta_mma_kernel<true, true, false> : (Kern)eval_cta_mma_kernel<false, true, false>)
                                 : (real_h ? (Kern)eval_cta_mma_kernel<true, false, false> : (Kern)eval_cta_mma_kernel<false, false, false>);

@@ -53,14 +53,10 @@ constexpr int ORB_XTBUF = ORB_CTAS >= 3 ? 1 : 2;          // buffers of the priv
 #endif
 
 struct alignas(16) OrbitScratch {
-    double Vs[2][2][32 * OLD];          // [buffer][re | im]: the whole current term, row-major (hosts G and the squarings during set-up)
+    double Vs[2][2][32 * OLD];          // [buffer][re | im]: the whole current term, row-major
     double xt[ORB_XTBUF][10][128];              // private transposition tiles [buffer][slot][re 64 | im 64]; D: slots 0..3, warp r: 2 + 2 r, 3 + 2 r
-    double par[OMAXP];
-    double jw[40];                      // [bitpos 0..4][type (0 diag, 1 flip)][ra][ca]
-    double kd[10];
+    double jw[40];                      // [bitpos 0..4][type (0 diag, 1 flip)][ra][ca]      (from the prepare kernel's record)
     double gdiag[32];                   // real H: diagonal of G.re = -1/2 sum c^dag c by PHYSICAL index
-    double colsum[32], rowlo[32], diagh[32];
-    double misc[4];
     double lossw[4];
     unsigned int fetch;
     int flag;
@@ -520,33 +516,44 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
     }
 }
 
+// ---- prepare kernel (one CTA of four warps per model, persistent): K1 (reference basic_model.py:152-255) -- G = -iH - 1/2 sum c^dag c,
+//      the real jump weights -- and the Chebyshev enclosure of eml_cheb.cuh (Gershgorin, 2 ||(H - mu)^8||_1^(1/8) on the DMMA pipe,
+//      per-site dissipator ranges, six candidate ellipses), at five CTAs per SM instead of inside the evaluator's two.
+//      ONE RECORD per model: [NF][32] A fragments of G per lane, [40] jw, [32] diagonal of G.re, [4] R, S, ac, tau_max (R = NaN: not
+//      evaluable), and the number of generator applications the evaluation will need (the cost the evaluator's CTAs are ordered by).
 template <bool REAL_H>
-__global__ void __launch_bounds__(128, ORB_CTAS)
-eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
-                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
-                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
-                      const double cheb_zcap, const int sms) {
-    constexpr int N = 5, D = 32;
-    extern __shared__ __align__(16) unsigned char orbit_smem_raw[];
-    OrbitScratch& S = *reinterpret_cast<OrbitScratch*>(orbit_smem_raw);
+__host__ __device__ constexpr int orbit_rec_doubles() { return (REAL_H ? 16 : 32) * 32 + 40 + 32 + 4; }
+constexpr int PREP32_MAXP = OMAXP;
+template <bool REAL_H>
+struct alignas(16) Prep32Scratch {
+    double G[2][32 * OLD];                  // G.re, G.im in PHYSICAL coordinates
+    double M[REAL_H ? 3 : 4][32 * 36];      // squaring scratch (real H: M[0] and M[2] only)
+    double par[PREP32_MAXP];
+    double jw[40];
+    double kd[10];
+    double gdiag[32];
+    double colsum[32], rowlo[32], diagh[32];
+    double misc[4];
+};
+
+template <bool REAL_H>
+__global__ void __launch_bounds__(128, 4)
+prepare32_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params, double* __restrict__ rec,
+                 float* __restrict__ cost, const double cheb_zcap) {
+    constexpr int N = 5, D = 32, NF = REAL_H ? 16 : 32, REC = orbit_rec_doubles<REAL_H>();
+    extern __shared__ __align__(16) unsigned char prep32_smem_raw[];
+    Prep32Scratch<REAL_H>& S = *reinterpret_cast<Prep32Scratch<REAL_H>*>(prep32_smem_raw);
     const int tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int T = P.n_times, K = P.n_obs;
+    const int T = P.n_times;
     const int obs_site = P.obs_site;
     auto pos = [&](int s) { return (s == obs_site) ? N - 1 : (s < obs_site ? N - 2 - s : N - 1 - s); };
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) S.fetch = atomicAdd(counter, 1u);
-        __syncthreads();
-        const unsigned int bidx = S.fetch;
-        if ((long long)bidx >= n_models) break;
-        const long long b = (order != nullptr) ? order[bidx] : bidx;
-
+    for (long long b = blockIdx.x; b < n_models; b += gridDim.x) {
+        __syncthreads();     // the previous model's readers of the scratch are done
         // ---- K1 (reference basic_model.py:152-255): parameters, G = -iH - 1/2 sum c^dag c in PHYSICAL coordinates (row stride OLD)
-        double* G_re = S.Vs[0][0];
-        double* G_im = S.Vs[0][1];
+        double* G_re = S.G[0];
+        double* G_im = S.G[1];
         for (int i = tid; i < P.n_params; i += 128) S.par[i] = params[b * P.n_params + i];
         for (int i = tid; i < 32 * OLD; i += 128) { G_re[i] = 0.0; G_im[i] = 0.0; }
         __syncthreads();
@@ -644,26 +651,25 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
         }
         __syncthreads();
         const double nu = S.misc[0];
-        if (!(nu * (P.times[T - 1] - P.times[0]) < 1e5)) {     // non-finite generator or absurd step count: do not hang
-            if (tid == 0) {
-                if (loss != nullptr) loss[b] = nan("");
-                if (status != nullptr) status[b] = -1;
-            }
+        double* const R = rec + (size_t)b * REC;
+        if (!(nu * (P.times[T - 1] - P.times[0]) < 1e5)) {     // non-finite generator or absurd step count: reported by the evaluator
+            if (tid < 4) R[NF * 32 + 72 + tid] = nan("");
+            if (tid == 0 && cost != nullptr) cost[b] = 0.f;
+            __syncthreads();
             continue;
         }
 
-        // ---- A fragments of G for all four tile rows X, column tiles kt = 2 (X >> 1) + kk, k index permuted pi(ks, t) = 2t + ks
-        double aG_re[4][2][2], aG_im[4][2][2];
+        // ---- record: A fragments of G for all four tile rows X, column tiles kt = 2 (X >> 1) + kk, k index permuted pi(ks, t) = 2t + ks
+        //      (fragment f = (2 X + kk) 2 + ks for every lane, coalesced; im plane, then re plane for a complex H), weights, diagonal
 #pragma unroll
-        for (int X = 0; X < 4; ++X)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const int row = phys32(8 * X + g), col = phys32(8 * (2 * (X >> 1) + kk) + 2 * t + ks);
-                    aG_re[X][kk][ks] = REAL_H ? 0.0 : G_re[row * OLD + col];
-                    aG_im[X][kk][ks] = G_im[row * OLD + col];
-                }
+        for (int q = 0; q < 4; ++q) {
+            const int f = 4 * w + q, X = f >> 2, kk = (f >> 1) & 1, ks = f & 1;
+            const int row = phys32(8 * X + g), col = phys32(8 * (2 * (X >> 1) + kk) + 2 * t + ks);
+            R[f * 32 + lane] = G_im[row * OLD + col];
+            if (!REAL_H) R[(16 + f) * 32 + lane] = G_re[row * OLD + col];
+        }
+        if (tid < 40) R[NF * 32 + tid] = S.jw[tid];
+        if (tid >= 64 && tid < 96) R[NF * 32 + 40 + (tid - 64)] = S.gdiag[tid - 64];
 
         // ---- Chebyshev enclosure (eml_cheb.cuh): G is still in the Vs[0] planes; Vs[1] and the trace table are scratch
         ChebPlan plan{};
@@ -683,9 +689,9 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
             // 2 rho(H - mu) <= 2 ||(H - mu)^8||_1^(1/8): three squarings, planes [re | im] of 32 x 32
             // (real H: on the DMMA pipe, warp w computes tile row w; row stride 36 makes the fragment loads conflict free)
             constexpr int LDM = REAL_H ? 36 : D;
-            double* Ma_re = S.Vs[1][0]; double* Ma_im = S.Vs[1][1];
-            double* Mb_re = S.tr;       double* Mb_im = S.tr + D * D;
-            static_assert(32 * 36 <= 32 * OLD && 32 * 36 <= (ORB_KCAP + 4) * 4, "squaring scratch");
+            double* Ma_re = S.M[0]; double* Ma_im = S.M[1];
+            double* Mb_re = S.M[2];     double* Mb_im = S.M[REAL_H ? 2 : 3];
+            
             for (int i = tid; i < D * D; i += 128) {
                 const int r = i / D, c = i % D;
                 Ma_re[r * LDM + c] = -G_im[r * OLD + c] - ((r == c) ? mu : 0.0);
@@ -733,6 +739,68 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
             cheb_site_ranges(S.jw, S.kd, N, dlo, dhi, dasym);
             plan = cheb_make_plan(spread, dlo, dhi, dasym, P.times[T - 1] - P.times[0], cheb_zcap, ORB_KCAP);
         }
+        if (tid == 0) {
+            R[NF * 32 + 72] = plan.R; R[NF * 32 + 73] = plan.S; R[NF * 32 + 74] = plan.ac; R[NF * 32 + 75] = plan.tau_max;
+            if (cost != nullptr) {
+                const double span = P.times[T - 1] - P.times[0];
+                const double steps = ceil(span / plan.tau_max);
+                const int k1 = min(cheb_terms(fmin(span, plan.tau_max) * plan.S), ORB_KCAP);
+                cost[b] = (float)(fmax(steps, 1.0) * (double)k1);
+            }
+        }
+    }
+}
+template __global__ void prepare32_kernel<true>(const DevProblem, const long long, const double*, double*, float*, const double);
+template __global__ void prepare32_kernel<false>(const DevProblem, const long long, const double*, double*, float*, const double);
+
+
+template <bool REAL_H>
+__global__ void __launch_bounds__(128, ORB_CTAS)
+eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double* __restrict__ prep,
+                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
+                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
+                      const int sms) {
+    extern __shared__ __align__(16) unsigned char orbit_smem_raw[];
+    OrbitScratch& S = *reinterpret_cast<OrbitScratch*>(orbit_smem_raw);
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int T = P.n_times, K = P.n_obs;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) S.fetch = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int bidx = S.fetch;
+        if ((long long)bidx >= n_models) break;
+        const long long b = (order != nullptr) ? order[bidx] : bidx;
+
+        // ---- the prepare kernel's record of this model: A fragments (coalesced), weights, diagonal, plan
+        constexpr int NF = REAL_H ? 16 : 32, REC = orbit_rec_doubles<REAL_H>();
+        const double* const R = prep + (size_t)b * REC;
+        ChebPlan plan;
+        plan.R = R[NF * 32 + 72]; plan.S = R[NF * 32 + 73]; plan.ac = R[NF * 32 + 74]; plan.tau_max = R[NF * 32 + 75];
+        if (!(plan.R == plan.R)) {       // not evaluable (non-finite parameters or an absurd step count): reported, not attempted
+            if (tid == 0) {
+                if (loss != nullptr) loss[b] = nan("");
+                if (status != nullptr) status[b] = -1;
+            }
+            continue;
+        }
+        double aG_re[4][2][2], aG_im[4][2][2];
+#pragma unroll
+        for (int X = 0; X < 4; ++X)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const int f = (2 * X + kk) * 2 + ks;
+                    aG_im[X][kk][ks] = R[f * 32 + lane];
+                    aG_re[X][kk][ks] = REAL_H ? 0.0 : R[(16 + f) * 32 + lane];
+                }
+        if (tid < 40) S.jw[tid] = R[NF * 32 + tid];
+        if (tid >= 64 && tid < 96) S.gdiag[tid - 64] = R[NF * 32 + 40 + (tid - 64)];
+
         const double sc = 2.0 / plan.R;
 #pragma unroll
         for (int X = 0; X < 4; ++X)
@@ -740,7 +808,7 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
             for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) { aG_re[X][kk][ks] *= sc; aG_im[X][kk][ks] *= sc; }
-        __syncthreads();     // G and the scratch planes have been consumed
+        __syncthreads();     // jw and the diagonal are in shared memory
 
         OrbitCtx C;
         C.P = &P; C.S = &S; C.b = b; C.expect = expect;
@@ -772,32 +840,64 @@ eval_cta_orbit_kernel(const DevProblem P, const long long n_models, const double
     }
 }
 
-template __global__ void eval_cta_orbit_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double, const int);
-template __global__ void eval_cta_orbit_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double, const int);
+template __global__ void eval_cta_orbit_kernel<true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const int);
+template __global__ void eval_cta_orbit_kernel<false>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const int);
 
+// eml_warp_mma.cu: one-CTA counting sort of per-model costs, largest first
+void launch_order_from_cost(int n_models, const float* cost, int* order, cudaStream_t stream);
+
+size_t cta_orbit_prep_bytes_per_model(bool real_h) {
+    return sizeof(double) * (size_t)(real_h ? orbit_rec_doubles<true>() : orbit_rec_doubles<false>());
+}
+
+// order: ordering buffer of the plan (2 * 2^18 ints: order + float cost scratch) or nullptr; prep_ws: records for prep_cap models
 cudaError_t launch_cta_orbit(const DevProblem& P, long long n_models, const double* params, const int* target_set, double* expect,
-                             double* loss, int* status, unsigned int* counter, const int* use_order, bool real_h, cudaStream_t stream) {
+                             double* loss, int* status, unsigned int* counter, int* order, bool real_h, double* prep_ws,
+                             long long prep_cap, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (prep_ws == nullptr || prep_cap < 1) return cudaErrorInvalidValue;
     using Kern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*,
-                          const int*, const double, const int);
+                          const int*, const int);
+    using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, const double);
     const Kern kern = real_h ? (Kern)eval_cta_orbit_kernel<true> : (Kern)eval_cta_orbit_kernel<false>;
+    const PrepKern prep = real_h ? (PrepKern)prepare32_kernel<true> : (PrepKern)prepare32_kernel<false>;
     const size_t smem = sizeof(OrbitScratch);
-    static int per_sm_cache[64][2] = {{0}};
+    const size_t psmem = real_h ? sizeof(Prep32Scratch<true>) : sizeof(Prep32Scratch<false>);
+    const size_t rec = real_h ? orbit_rec_doubles<true>() : orbit_rec_doubles<false>();
+    static int per_sm_cache[64][2] = {{0}}, prep_per_sm_cache[64][2] = {{0}};
     int per_sm = (dev < 64) ? per_sm_cache[dev][real_h ? 1 : 0] : 0;
+    int prep_per_sm = (dev < 64) ? prep_per_sm_cache[dev][real_h ? 1 : 0] : 0;
     if (per_sm == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&prep_per_sm, prep, 128, psmem)) != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        if (dev < 64) per_sm_cache[dev][real_h ? 1 : 0] = per_sm;
+        if (prep_per_sm < 1) prep_per_sm = 1;
+        if (dev < 64) { per_sm_cache[dev][real_h ? 1 : 0] = per_sm; prep_per_sm_cache[dev][real_h ? 1 : 0] = prep_per_sm; }
     }
-    long long ctas = n_models;
-    if (ctas > (long long)per_sm * sms) ctas = (long long)per_sm * sms;
     const double zcap = cheb_zcap_for(ORB_KCAP);
-    kern<<<(unsigned)ctas, 128, smem, stream>>>(P, n_models, params, target_set, expect, loss, status, counter, use_order, zcap, sms);
-    return cudaGetLastError();
+    for (long long off = 0; off < n_models; off += prep_cap) {
+        const long long n = (n_models - off < prep_cap) ? n_models - off : prep_cap;
+        if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+        // longest first, by the generator applications the prepare kernel computes, when CTAs take more than one model
+        const bool sort = order != nullptr && n > (long long)per_sm * sms && n <= (1 << 18);
+        float* const cost = sort ? reinterpret_cast<float*>(order + (1 << 18)) : nullptr;
+        long long pctas = n;
+        if (pctas > (long long)prep_per_sm * sms) pctas = (long long)prep_per_sm * sms;
+        prep<<<(unsigned)pctas, 128, psmem, stream>>>(P, n, params + off * P.n_params, prep_ws, cost, zcap);
+        if (sort) launch_order_from_cost((int)n, cost, order, stream);
+        long long ctas = n;
+        if (ctas > (long long)per_sm * sms) ctas = (long long)per_sm * sms;
+        kern<<<(unsigned)ctas, 128, smem, stream>>>(P, n, prep_ws, target_set ? target_set + off : nullptr,
+                                                   expect ? expect + (size_t)off * P.n_obs * P.n_times * 2 : nullptr, loss ? loss + off : nullptr,
+                                                   status ? status + off : nullptr, counter, sort ? order : nullptr, sms);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace eml

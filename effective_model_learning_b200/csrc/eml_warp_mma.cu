@@ -2146,6 +2146,11 @@ void launch_model_order(const DevProblem& P, long long n_models, const double* p
     order_models_kernel<<<1, 1024, 0, stream>>>((int)n_models, cost, order);
 }
 
+// one-CTA counting sort of per-model costs, largest first (used by the d = 32 orbit kernel's launcher)
+void launch_order_from_cost(int n_models, const float* cost, int* order, cudaStream_t stream) {
+    order_models_kernel<<<1, 1024, 0, stream>>>(n_models, cost, order);
+}
+
 bool warp_mma_supported(const DevProblem& P, bool hermitian) {
     return hermitian && (P.n_tls == 3 || P.n_tls == 4) && P.n_params <= MAXP;
 }

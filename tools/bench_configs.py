@@ -16,6 +16,7 @@ hyper = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperpara
 ts = np.linspace(0, 2.5, 200)
 rows = []
 for name, Q, D, B, reps in (('C1 d=4, 1 chain', 1, 1, 1, 200), ('d=4, 4096 chains', 1, 1, 4096, 20),
+                            ('d=4, 8192 chains (two models per warp)', 1, 1, 8192, 20), ('d=4, 65536 chains (two models per warp)', 1, 1, 65536, 5),
                             ('C2 d=8, 1024 chains', 1, 2, 1024, 50), ('d=8, 8192 chains', 1, 2, 8192, 20),
                             ('C3 d=16, 4096 chains', 1, 3, 4096, 20), ('d=16, 16384 chains', 1, 3, 16384, 10), ('d=16, 65536 chains', 1, 3, 65536, 3),
                             ('C4 d=32, 512 chains', 2, 3, 512, 3), ('d=32, 2048 chains', 2, 3, 2048, 2)):
