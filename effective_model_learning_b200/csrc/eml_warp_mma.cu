@@ -152,7 +152,7 @@ struct alignas(16) PrepScratch {
     double kd[8];
     double colsum[16];
     double misc[4];
-    alignas(16) double mat[(REAL_H ? 2 : 4) * D * D];
+    alignas(16) double mat[REAL_H ? 2 * D * (D + 4) : 4 * D * D];      // real H: row stride D + 4
 };
 
 // Phase clocks (profiling builds only, -DEML_PROFILE_PHASES): warp-cycles spent in set-up, recurrence, outputs, epilogue,
@@ -499,11 +499,14 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
         mu *= 1.0 / D;
+        // (real H: row stride D + 4, which makes the fragment loads of the DMMA squarings bank-conflict free: with stride D
+        //  the eight rows of an A fragment hit the same banks -- 56 % of the kernel's shared-memory wavefronts were conflicts)
+        constexpr int LDM = REAL_H ? D + 4 : D;
         double* Ma = S.mat;                                   // [re | im] planes of D x D (real H: re only)
-        double* Mb = S.mat + (REAL_H ? 1 : 2) * D * D;
+        double* Mb = S.mat + (REAL_H ? D * LDM : 2 * D * D);
         for (int i = lane; i < D * D; i += 32) {
             const int r = i / D, c = i % D;
-            Ma[i] = -S.G_im[r][c] - ((r == c) ? mu : 0.0);
+            Ma[r * LDM + c] = -S.G_im[r][c] - ((r == c) ? mu : 0.0);
             if (!REAL_H) Ma[D * D + i] = (r == c) ? 0.0 : S.G_re[r][c];
         }
         __syncwarp();
@@ -517,8 +520,8 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
                         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks)
-                            dmma(d0, d1, Ma[(8 * I + g) * D + 4 * ks + t], Ma[(4 * ks + t) * D + 8 * J + g]);
-                        *reinterpret_cast<double2*>(&Mb[(8 * I + g) * D + 8 * J + 2 * t]) = make_double2(d0, d1);
+                            dmma(d0, d1, Ma[(8 * I + g) * LDM + 4 * ks + t], Ma[(4 * ks + t) * LDM + 8 * J + g]);
+                        *reinterpret_cast<double2*>(&Mb[(8 * I + g) * LDM + 8 * J + 2 * t]) = make_double2(d0, d1);
                     }
             } else
             for (int i = lane; i < D * D; i += 32) {
@@ -540,7 +543,7 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
         double cs = 0.0;
         if (lane < D)
             for (int r = 0; r < D; ++r)
-                cs += REAL_H ? fabs(Ma[r * D + lane]) : hypot(Ma[r * D + lane], Ma[D * D + r * D + lane]);
+                cs += REAL_H ? fabs(Ma[r * LDM + lane]) : hypot(Ma[r * D + lane], Ma[D * D + r * D + lane]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
         spread = fmin(spread, 2.0 * sqrt(sqrt(sqrt(cs))) * (1.0 + 1e-12));
