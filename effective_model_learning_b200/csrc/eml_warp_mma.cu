@@ -2048,7 +2048,8 @@ eval_pack2_kernel(const DevProblem P, const long long n_models, const int* __res
                     }
                 };
                 if (need_acc) run_terms(std::true_type{}); else run_terms(std::false_type{});
-                {
+                {   // a non-finite or absurd last term means an enclosure failed.  Both models of the pair are reported: 0 x inf in the
+                    // block-diagonal products lets a diverging model poison its partner's rows, so neither result can be trusted
                     const double chk = fabs(v_re[0]) + fabs(v_im[0]) + fabs(v_re[1]) + fabs(v_im[1]);
                     if (!UNI(chk < 1e300)) capped = true;
                 }
