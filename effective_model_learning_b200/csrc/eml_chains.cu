@@ -331,22 +331,19 @@ __device__ inline double xi_product_warp(const ChainHyperDev& H, const int (&cc)
         const bool tw = have[i] && tweakable(cc[i], row[i]);
         const int pc = pclass(cc[i]);
         const double x = tw ? xi(row[i], jump[pc], H.lo[pc], H.hi[pc]) : 1.0;
-        const unsigned tm = __ballot_sync(0xffffffffu, tw);
+        unsigned tm = __ballot_sync(0xffffffffu, tw);
 #pragma unroll 1
-        for (int l = 0; l < 32; ++l) {
-            const double v = __shfl_sync(0xffffffffu, x, l);
-            if ((tm >> l) & 1u) out *= v;
+        while (tm) {       // in parameter order
+            const int l = __ffs(tm) - 1;
+            tm &= tm - 1u;
+            out *= __shfl_sync(0xffffffffu, x, l);
         }
     }
     return out;
 }
 
-__global__ void chains_propose_warp_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo,
-                                                                  const long long c_hi, const unsigned long long seed,
-                                                                  const long long first_chain) {
-    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (c >= c_hi) return;      // warp-uniform
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void propose_warp(const ChainHyperDev& H, const ChainState& S, const long long c, const int lane,
+                                             const unsigned long long seed, const long long first_chain) {
     const int P = H.n_params, nq = (P + 31) >> 5;
     double* cur = S.cur + c * P;
     double* prop = S.prop + c * P;
@@ -518,13 +515,10 @@ __global__ void chains_propose_warp_kernel(const ChainHyperDev H, const ChainSta
     }
 }
 
-__global__ void chains_accept_warp_kernel(const ChainHyperDev H, const ChainState S, const int* __restrict__ eval_status,
-                                                                 const long long c_lo, const long long c_hi, const unsigned long long seed,
-                                                                 const long long first_chain, double* hist_loss, double* hist_aprob,
-                                                                 int* hist_code, double* hist_params) {
-    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (c >= c_hi) return;      // warp-uniform
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void accept_warp(const ChainHyperDev& H, const ChainState& S, const int* __restrict__ eval_status,
+                                            const long long c, const int lane, const unsigned long long seed,
+                                            const long long first_chain, double* hist_loss, double* hist_aprob,
+                                            int* hist_code, double* hist_params) {
     const int P = H.n_params;
     Rng rng{chain_key(seed, first_chain + c), S.rng_ctr[c]};
     const double Lp = S.prop_loss[c], Lc = S.cur_loss[c];
@@ -569,6 +563,36 @@ __global__ void chains_accept_warp_kernel(const ChainHyperDev H, const ChainStat
         st[4] = S.counters[c * 4 + 1]; st[5] = S.counters[c * 4 + 0];
         st[6] = S.last_ratio[c]; st[7] = n_proc;
     }
+}
+
+// eight CTAs (32 chains) per SM: 4096 chains are a single wave on 148 SMs
+__global__ void __launch_bounds__(128, 8) chains_propose_warp_kernel(const ChainHyperDev H, const ChainState S, const long long c_lo,
+                                                                     const long long c_hi, const unsigned long long seed,
+                                                                     const long long first_chain) {
+    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= c_hi) return;      // warp-uniform
+    propose_warp(H, S, c, threadIdx.x & 31, seed, first_chain);
+}
+__global__ void __launch_bounds__(128, 8) chains_accept_warp_kernel(const ChainHyperDev H, const ChainState S, const int* __restrict__ eval_status,
+                                                                    const long long c_lo, const long long c_hi, const unsigned long long seed,
+                                                                    const long long first_chain, double* hist_loss, double* hist_aprob,
+                                                                    int* hist_code, double* hist_params) {
+    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= c_hi) return;      // warp-uniform
+    accept_warp(H, S, eval_status, c, threadIdx.x & 31, seed, first_chain, hist_loss, hist_aprob, hist_code, hist_params);
+}
+// accept / reject of step i and the proposal of step i + 1 in one launch (the same random-stream order as the two kernels)
+__global__ void __launch_bounds__(128, 8) chains_accept_propose_warp_kernel(const ChainHyperDev H, const ChainState S,
+                                                                            const int* __restrict__ eval_status, const long long c_lo,
+                                                                            const long long c_hi, const unsigned long long seed,
+                                                                            const long long first_chain, double* hist_loss,
+                                                                            double* hist_aprob, int* hist_code, double* hist_params) {
+    const long long c = c_lo + (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= c_hi) return;      // warp-uniform
+    const int lane = threadIdx.x & 31;
+    accept_warp(H, S, eval_status, c, lane, seed, first_chain, hist_loss, hist_aprob, hist_code, hist_params);
+    __syncwarp();       // the chain's scalars and rows written by the accept part are visible to every lane
+    propose_warp(H, S, c, lane, seed, first_chain);
 }
 
 __global__ void chains_init_kernel(const ChainHyperDev H, const ChainState S, const long long n_chains) {
@@ -764,25 +788,29 @@ int eml_chains_run(EmlChains* ch, int64_t n_steps, double* hist_loss, double* hi
             static const bool thread_kernels = [] { const char* e = std::getenv("EML_CHAIN_THREAD_KERNELS"); return e && e[0] == '1'; }();
             const bool warp_kernels = !thread_kernels && P <= 32 * eml::CH_MAXQ;
             const unsigned wblocks = (unsigned)((cnt + 3) / 4);       // a warp per chain, four chains per CTA
-            if (warp_kernels) eml::chains_propose_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
-            else eml::chains_propose_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            // warp kernels: the accept of step i and the proposal of step i + 1 are one launch (EML_CHAIN_FUSED=0: two)
+            static const bool fused_on = [] { const char* e = std::getenv("EML_CHAIN_FUSED"); return !(e && e[0] == '0'); }();
+            const bool fused = warp_kernels && fused_on;
+            if (warp_kernels) {
+                if (!fused || i == 0) eml::chains_propose_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            } else {
+                eml::chains_propose_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, lo, hi, ch->seed, ch->first_chain);
+            }
             // the generator applications each chain's previous proposal needed order this step's models (longest first)
             int rc = eml_eval_batch_hinted(ch->plan, cnt, ch->S.prop + lo * P, ch->d_target_set ? ch->d_target_set + lo : nullptr,
                                            nullptr, ch->S.prop_loss + lo, ch->d_status + lo, gs, ch->d_status + lo,
                                            ch->g_counter[g], ch->g_order[g], ch->g_prep[g], cnt);
             if (rc != EML_OK) return rc;
-            if (warp_kernels)
-                eml::chains_accept_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
-                                                                       hist_loss ? hist_loss + i * ch->n : nullptr,
-                                                                       hist_aprob ? hist_aprob + i * ch->n : nullptr,
-                                                                       hist_code ? hist_code + i * ch->n : nullptr,
-                                                                       hist_params ? hist_params + i * ch->n * P : nullptr);
+            double* const hl = hist_loss ? hist_loss + i * ch->n : nullptr;
+            double* const ha = hist_aprob ? hist_aprob + i * ch->n : nullptr;
+            int* const hc = hist_code ? hist_code + i * ch->n : nullptr;
+            double* const hp = hist_params ? hist_params + i * ch->n * P : nullptr;
+            if (fused && i + 1 < n_steps)
+                eml::chains_accept_propose_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain, hl, ha, hc, hp);
+            else if (warp_kernels)
+                eml::chains_accept_warp_kernel<<<wblocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain, hl, ha, hc, hp);
             else
-                eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain,
-                                                                 hist_loss ? hist_loss + i * ch->n : nullptr,
-                                                                 hist_aprob ? hist_aprob + i * ch->n : nullptr,
-                                                                 hist_code ? hist_code + i * ch->n : nullptr,
-                                                                 hist_params ? hist_params + i * ch->n * P : nullptr);
+                eml::chains_accept_kernel<<<blocks, 128, 0, gs>>>(ch->H, ch->S, ch->d_status, lo, hi, ch->seed, ch->first_chain, hl, ha, hc, hp);
         }
     }
     // join: the caller's stream continues after both groups are done
