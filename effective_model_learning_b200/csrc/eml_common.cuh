@@ -2,7 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 #include "eml_b200.h"
+
+// Index checks of the shared-memory tables (trace table, coefficient table, transposition tiles, prepare records): compiled
+// in with -DEML_DEBUG_BOUNDS (tools/build_variant.sh dbg -DEML_DEBUG_BOUNDS), a violation traps the kernel.  The pool's
+// compute-sanitizer is closed, so the GPU suite is run once per round against this build instead.
+#ifdef EML_DEBUG_BOUNDS
+#define EML_CHECK(cond) do { if (!(cond)) { printf("eml bounds check failed: %s (%s line %d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define EML_CHECK(cond) do { } while (0)
+#endif
 
 namespace eml {
 

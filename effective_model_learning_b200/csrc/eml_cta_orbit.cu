@@ -231,6 +231,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
     const int slot0 = DG ? 0 : 2 + 2 * ROLE;
     const int xs0 = xt_addr_o(g, 2 * t), xs1 = xt_addr_o(g, 2 * t + 1), xl = xt_addr_o(2 * t, g);
     auto xt_put = [&](const int buf, const int i, const double (&xr)[2], const double (&xi)[2]) {
+        EML_CHECK(buf >= 0 && buf < ORB_XTBUF && slot0 + i >= 0 && slot0 + i < 10 && xs0 < 64 && xs1 < 64 && xl + 1 < 64);
         double* const X = S.xt[buf][slot0 + i];
         X[xs0] = xr[0]; X[xs1] = xr[1]; X[64 + xs0] = xi[0]; X[64 + xs1] = xi[1];
     };
@@ -241,6 +242,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
         ci = *reinterpret_cast<const double2*>(X + 64 + xl);
     };
     auto publish = [&](const int vb, const int I, const int J, const double (&xr)[2], const double (&xi)[2]) {
+        EML_CHECK((vb == 0 || vb == 1) && I >= 0 && I < 4 && J >= 0 && J < 4);
         *reinterpret_cast<double2*>(&S.Vs[vb][0][(8 * I + g) * OLD + 8 * J + 2 * t]) = make_double2(xr[0], xr[1]);
         *reinterpret_cast<double2*>(&S.Vs[vb][1][(8 * I + g) * OLD + 8 * J + 2 * t]) = make_double2(xi[0], xi[1]);
     };
@@ -270,6 +272,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
             double kk = (hb ? v1 : v0) + __shfl_sync(0xffffffffu, hb ? v0 : v1, dl4);
             kk += __shfl_sync(0xffffffffu, kk, dl2);
             kk += __shfl_sync(0xffffffffu, kk, dl1);
+            EML_CHECK(k >= 0 && k <= ORB_KCAP);
             if (diag_lane && (g & 3) == 0) S.tr[k * 4 + (DG ? 0 : 2) + (g >> 2)] = kk;
         }
     };
@@ -317,6 +320,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
                 const double tz = 2.0 / (tau_end * Rb);
                 double jn = 1.0, jn1 = 0.0, ssum = 0.0;
                 for (int k = Kc; k >= 1; --k) {
+                    EML_CHECK(k <= ORB_KCAP + 1);
                     if ((k & 127) == (int)threadIdx.x) S.cJ[k] = jn;
                     if (!(k & 1)) ssum += jn;
                     const double jm = fma((double)k * tz, jn, -jn1);
@@ -486,6 +490,7 @@ __device__ __forceinline__ void orbit_series(const OrbitCtx& C, const double (&a
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int kk = k - j;
+                            EML_CHECK(kk >= 1 && kk <= Kc + 3 && kk <= ORB_KCAP + 3);
                             const double2 ta = *reinterpret_cast<const double2*>(&S.tr[kk * 4]);
                             const double2 tb = *reinterpret_cast<const double2*>(&S.tr[kk * 4 + 2]);
                             jn = __hiloint2double(kk == Kp ? 0x3ff00000 : __double2hiint(jn), __double2loint(jn));   // exactly 0.0 before the start

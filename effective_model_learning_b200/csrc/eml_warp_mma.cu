@@ -180,14 +180,6 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // 1/(j+1) for the Taylor recurrences
 __constant__ double INV_TABLE[MCAP + 2];
 
-// Index checks of the shared-memory tables (trace table, coefficient table, transposition tiles, prepare records): compiled
-// in with -DEML_DEBUG_BOUNDS (tools/build_variant.sh dbg -DEML_DEBUG_BOUNDS), a violation traps the kernel.  The pool's
-// compute-sanitizer is closed, so the GPU suite is run once per round against this build instead.
-#ifdef EML_DEBUG_BOUNDS
-#define EML_CHECK(cond) do { if (!(cond)) { printf("eml bounds check failed: %s (line %d)\n", #cond, __LINE__); __trap(); } } while (0)
-#else
-#define EML_CHECK(cond) do { } while (0)
-#endif
 // warp-uniform predicate the compiler can SEE is uniform (vote result): keeps shuffles free of divergence guards
 #define UNI(c) (__all_sync(0xffffffffu, (c)) != 0)
 
