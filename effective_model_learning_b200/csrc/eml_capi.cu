@@ -352,13 +352,14 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
     if (eml::warp_mma_supported(plan->Pw, herm)) EML_TRY(compile_linear_program(plan, d));
     {
         void* c = nullptr;
-        cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int));
+        cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int) * EML_FETCH_WS_WORDS);
         if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
         plan->owned.push_back(c);
+        if (cudaMemset(c, 0, sizeof(unsigned int) * EML_FETCH_WS_WORDS) != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMemset(counter)"); }
         plan->d_counter = (unsigned int*)c;
         if (eml::warp_mma_supported(plan->Pw, herm) || eml::cta_mma_supported(P, herm)) {
             void* o = nullptr;
-            ce = cudaMalloc(&o, sizeof(int) * 2 * (1 << 18));   // order + cost scratch
+            ce = cudaMalloc(&o, sizeof(int) * EML_ORDER_WS_INTS);   // order + cost scratch, or the cost-bin lists
             if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(order)"); }
             plan->owned.push_back(o);
             plan->d_order = (int*)o;
@@ -439,7 +440,7 @@ static int ensure_prep(EmlPlan* plan, long long n_models) {
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                           double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,
                           int* order_ws, double* prep_ws, long long prep_cap) {
-    // counter_ws / order_ws / prep_ws: caller-owned work-fetch counter, ordering buffer (2 * 2^18 ints) and prepare
+    // counter_ws / order_ws / prep_ws: caller-owned work-fetch counter, ordering buffer (EML_ORDER_WS_INTS ints) and prepare
     // workspace (prep_cap models x eml_plan_prep_bytes_per_model), so that several evaluations of one plan can be in
     // flight on different streams; NULL = the plan's own
     if (!plan) return fail(EML_ERR_INVALID_ARGUMENT, "plan is NULL");

@@ -751,8 +751,9 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
     for (int g = 0; g < ch->n_groups; ++g) {
         ch->group_lo[g] = g * n_chains / ch->n_groups;
         ch->group_hi[g] = (g + 1) * n_chains / ch->n_groups;
-        CH_TRY(dalloc(ch, &ch->g_counter[g], 1));
-        CH_TRY(dalloc(ch, &ch->g_order[g], (size_t)2 * (1 << 18)));
+        CH_TRY(dalloc(ch, &ch->g_counter[g], EML_FETCH_WS_WORDS));
+        EML_CUDA(cudaMemset(ch->g_counter[g], 0, sizeof(unsigned int) * EML_FETCH_WS_WORDS));
+        CH_TRY(dalloc(ch, &ch->g_order[g], EML_ORDER_WS_INTS));
         CH_TRY(dalloc(ch, &ch->g_prep[g], eml_plan_prep_bytes_per_model(plan) / sizeof(double) * (size_t)(ch->group_hi[g] - ch->group_lo[g])));
         if (cudaStreamCreateWithFlags(&ch->gstream[g], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ch->join[g], cudaEventDisableTiming) != cudaSuccess) {

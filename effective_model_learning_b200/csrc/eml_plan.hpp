@@ -36,8 +36,8 @@ struct EmlPlan {
     int *h_tset = nullptr, *h_status = nullptr;
     double* d_targets = nullptr;
     size_t targets_bytes = 0;
-    unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel
-    int* d_order = nullptr;             // LPT model order (capacity 2^18 models) followed by the float cost scratch
+    unsigned int* d_counter = nullptr;  // work-fetch counter of the persistent warp kernel (EML_FETCH_WS_WORDS words)
+    int* d_order = nullptr;             // ordering workspace (EML_ORDER_WS_INTS ints)
     double* d_prep = nullptr;           // records of the prepare kernel (Chebyshev warp kernels), prep_cap models
     long long prep_cap = 0;
     // Small host batches (a single chain's total_dev: ONE model per call) are bound by the launch calls of the host:
@@ -50,6 +50,13 @@ struct EmlPlan {
         host_graphs.clear();
     }
 };
+
+// words of a work-fetch workspace: the evaluator's counter ([0]) and, 16-byte aligned behind it, the counts of the 256 cost
+// bins the prepare kernel sorts the models of a launch into (eml_warp_mma.cu: ORDER_HIST_OFF, ORDER_BINS)
+constexpr size_t EML_FETCH_WS_WORDS = 4 + 256;
+// ints of an ordering workspace: the sorted model order (2^18) + float cost scratch (2^18) of large launches, or the 256
+// cost-bin lists of 4096 entries of launches up to 4096 models
+constexpr size_t EML_ORDER_WS_INTS = (size_t)1 << 20;
 
 int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set, double* expect,
                           double* loss, int32_t* status, void* stream, const int32_t* cost_hint, unsigned int* counter_ws,

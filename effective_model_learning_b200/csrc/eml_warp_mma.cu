@@ -373,6 +373,53 @@ __device__ __forceinline__ double assemble_generator(SC& S, const DevProblem& P,
 //      persistent warps of the evaluator are ordered by.  Persistent CTAs: the plan's linear program (eml_common.cuh) is
 //      staged in shared memory once per CTA, then every warp takes models gw, gw + (warps of the grid), ...; the scalar
 //      tail (site ranges, the six enclosure candidates) is spread over lanes (eml_cheb.cuh: *_warp).
+// ---- Longest-first order WITHOUT an ordering pass (launches of at most ORDER_LIST_CAP models): the prepare kernel drops
+//      every model into the list of its cost bin (bins of (kcap + 1) / ORDER_BINS generator applications, most expensive
+//      first; multi-step models beyond kcap applications share bin 0); an evaluator warp turns its fetch ticket into
+//      (bin, position) with a prefix sum over the bin counts (one 32-byte load per lane and a shuffle scan per fetch).
+//      Workspace words: [0] the fetch counter, [ORDER_HIST_OFF ...] the bin counts -- zeroed by ONE memset node per launch.
+constexpr int ORDER_LIST_CAP = 4096;
+constexpr int ORDER_HIST_OFF = 4;      // 16-byte aligned behind the counter
+static_assert(ORDER_BINS * ORDER_LIST_CAP <= 2 * ORDER_MAX_MODELS * 2, "the bin lists live in the ordering buffer (2^20 ints)");
+static_assert(ORDER_BINS == 256, "eight bins per lane");
+__device__ __forceinline__ void order_list_put(unsigned int* __restrict__ fetch_ws, int* __restrict__ lists, const float cost,
+                                               const float bin_scale, const int b) {
+    const int bin = ORDER_BINS - 1 - min(ORDER_BINS - 1, (int)(cost * bin_scale));
+    const unsigned int at = atomicAdd(&fetch_ws[ORDER_HIST_OFF + bin], 1u);
+    EML_CHECK(at < (unsigned int)ORDER_LIST_CAP);
+    lists[bin * ORDER_LIST_CAP + (int)at] = b;
+}
+// model of fetch ticket `rank` (< the number of models of the launch); every lane returns it
+__device__ __forceinline__ int order_list_get(const unsigned int* __restrict__ fetch_ws, const int* __restrict__ lists,
+                                              const unsigned int rank, const int lane) {
+    const uint4* const h = reinterpret_cast<const uint4*>(fetch_ws + ORDER_HIST_OFF) + 2 * lane;
+    const uint4 a = __ldcg(h), c = __ldcg(h + 1);
+    const unsigned int cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    unsigned int tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += cnt[i];
+    unsigned int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    const unsigned int before = inc - tot;
+    int found = -1;
+    if (rank >= before && rank < inc) {
+        unsigned int r = rank - before;
+        int i = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (i == j && r >= cnt[j]) { r -= cnt[j]; i = j + 1; }
+        found = ((8 * lane + i) * ORDER_LIST_CAP) + (int)r;
+    }
+    const unsigned int who = __ballot_sync(0xffffffffu, found >= 0);
+    EML_CHECK(who != 0u);
+    found = __shfl_sync(0xffffffffu, found, __ffs(who) - 1);
+    return lists[found];
+}
+
 template <int TL, bool REAL_H, bool PARITY>
 __host__ __device__ constexpr int prep_fragments() { return (REAL_H ? 1 : 2) * TL * (PARITY ? 2 : 2 * TL); }
 template <int TL, bool REAL_H, bool PARITY>
@@ -383,7 +430,9 @@ constexpr int PREP_LIN_STAGE_MAX = 40 * 1024;      // largest linear program sta
 template <int TL, bool REAL_H, bool PARITY>
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prepare_models_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params, double* __restrict__ rec,
-                      float* __restrict__ cost, const double cheb_zcap, const int kcap, const int stage_lin) {
+                      float* __restrict__ cost, int* __restrict__ lists, unsigned int* __restrict__ fetch_ws,
+                      const double cheb_zcap, const int kcap, const int stage_lin) {
+    // cost: per-model cost for the ordering kernel (launches beyond ORDER_LIST_CAP models), or lists: the cost-bin lists
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL, KSE = PARITY ? 2 : KS;
     constexpr int NA = prep_fragments<TL, REAL_H, PARITY>(), REC = prep_record_doubles<TL, REAL_H, PARITY>();
     auto phys = [](const int x) { return PARITY ? x ^ (((x ^ (x >> 1) ^ (x >> 2)) & 1) << 3) : x; };
@@ -405,6 +454,7 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
         __syncthreads();
     }
     const double span = P.times[P.n_times - 1] - P.times[0];
+    const float bin_scale = (float)ORDER_BINS / (float)(kcap + 1);
     const long long warps_in_grid = (long long)gridDim.x * PREP_WARPS;
     for (long long b = (long long)blockIdx.x * PREP_WARPS + (threadIdx.x >> 5); b < n_models; b += warps_in_grid) {
     double* const R = rec + (size_t)b * REC;
@@ -544,17 +594,20 @@ prepare_models_kernel(const DevProblem P, const long long n_models, const double
     if (!(nu * span < 1e5)) {
         if (lane < 4) R[NA * 32 + 48 + lane] = nan("");
         if (lane == 0 && cost != nullptr) cost[b] = 0.f;
+        if (lane == 0 && lists != nullptr) order_list_put(fetch_ws, lists, 0.f, bin_scale, (int)b);
     } else {
         double dlo, dhi, dasym;
         cheb_site_ranges_warp(S.jw, S.kd, N, lane, dlo, dhi, dasym);
         const ChebPlan plan = cheb_make_plan_warp(spread, dlo, dhi, dasym, span, cheb_zcap, kcap, lane);
         if (lane == 0) {
             R[NA * 32 + 48] = plan.R; R[NA * 32 + 49] = plan.S; R[NA * 32 + 50] = plan.ac; R[NA * 32 + 51] = plan.tau_max;
-            if (cost != nullptr) {
+            if (cost != nullptr || lists != nullptr) {
                 // generator applications: one macro step when the span fits (exact), else about span / tau_max full steps
                 const double steps = ceil(span / plan.tau_max);
                 const int k1 = min(cheb_terms(fmin(span, plan.tau_max) * plan.S), kcap);
-                cost[b] = (float)(fmax(steps, 1.0) * (double)k1);
+                const float c = (float)(fmax(steps, 1.0) * (double)k1);
+                if (cost != nullptr) cost[b] = c;
+                else order_list_put(fetch_ws, lists, c, bin_scale, (int)b);
             }
         }
     }
@@ -572,7 +625,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, LAT ? EML_LAT_WARPS_PER_SM
 eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double* __restrict__ params,
                      const int* __restrict__ target_set, double* __restrict__ expect, double* __restrict__ loss,
                      int* __restrict__ status, unsigned int* __restrict__ counter, const int* __restrict__ order,
-                     const double* __restrict__ prep) {
+                     const double* __restrict__ prep, const int binned) {
     constexpr int N = 2 + TL, D = 8 * TL, KS = 2 * TL;      // sites, Hilbert dimension, k-steps of 4
     constexpr int NY = (TL == 1) ? 4 : 2, WQ = 8 * NY;      // dense-output accumulators per lane, outputs per expansion
     static_assert(!PARITY || (CHEB && TL == 2), "the parity-blocked variant exists for the d = 16 Chebyshev kernel");
@@ -629,7 +682,8 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
         if (lane == 0) bidx = atomicAdd(counter, 1u);
         bidx = __shfl_sync(0xffffffffu, bidx, 0);
         if (UNI((long long)bidx >= n_models)) break;
-        const long long b = (order != nullptr) ? order[bidx] : bidx;
+        // (binned: `order` holds the cost-bin lists of the prepare kernel and the ticket is resolved here)
+        const long long b = (order == nullptr) ? (long long)bidx : binned ? (long long)order_list_get(counter, order, bidx, lane) : (long long)order[bidx];
 
         double a_re[TL][KS], a_im[TL][KS];
         if constexpr (CHEB) {
@@ -1753,12 +1807,12 @@ eval_warp_mma_kernel(const DevProblem P, const long long n_models, const double*
     }
 }
 
-#define EML_WARP_INST(TL, RH, CH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA, SB>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+#define EML_WARP_INST(TL, RH, CH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, CH, PA, SB>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*, const int);
 EML_WARP_INST(1, true, false, false, false) EML_WARP_INST(1, false, false, false, false) EML_WARP_INST(2, true, false, false, false) EML_WARP_INST(2, false, false, false, false)
 EML_WARP_INST(1, true, true, false, false) EML_WARP_INST(1, false, true, false, false) EML_WARP_INST(2, true, true, false, false) EML_WARP_INST(2, false, true, false, false)
 EML_WARP_INST(2, true, true, true, false) EML_WARP_INST(2, false, true, true, false)
 EML_WARP_INST(2, true, true, true, true) EML_WARP_INST(2, false, true, true, true)
-#define EML_WARP_INST_LAT(TL, RH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, true, PA, SB, true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+#define EML_WARP_INST_LAT(TL, RH, PA, SB) template __global__ void eval_warp_mma_kernel<TL, RH, true, PA, SB, true>(const DevProblem, const long long, const double*, const int*, double*, double*, int*, unsigned int*, const int*, const double*, const int);
 EML_WARP_INST_LAT(1, true, false, false) EML_WARP_INST_LAT(1, false, false, false) EML_WARP_INST_LAT(2, true, false, false) EML_WARP_INST_LAT(2, false, false, false)
 EML_WARP_INST_LAT(2, true, true, false) EML_WARP_INST_LAT(2, false, true, false) EML_WARP_INST_LAT(2, true, true, true) EML_WARP_INST_LAT(2, false, true, true)
 
@@ -1787,7 +1841,7 @@ template <bool REAL_H>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 16 / WARPS_PER_CTA)
 eval_pack2_kernel(const DevProblem P, const long long n_models, const int* __restrict__ target_set, double* __restrict__ expect,
                   double* __restrict__ loss, int* __restrict__ status, unsigned int* __restrict__ counter,
-                  const int* __restrict__ order, const double* __restrict__ prep) {
+                  const int* __restrict__ order, const double* __restrict__ prep, const int binned) {
     constexpr int N = 3, D = 8, KCAP = Pack2Scratch::KCAP;
     constexpr int NA = prep_fragments<1, REAL_H, false>(), REC = prep_record_doubles<1, REAL_H, false>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1816,8 +1870,11 @@ eval_pack2_kernel(const DevProblem P, const long long n_models, const int* __res
         if (UNI((long long)bidx >= n_units)) break;
         long long bm[2];
         bool live[2] = {true, 2LL * bidx + 1 < n_models};
-        bm[0] = (order != nullptr) ? order[2LL * bidx] : 2LL * bidx;
-        bm[1] = live[1] ? ((order != nullptr) ? order[2LL * bidx + 1] : 2LL * bidx + 1) : bm[0];
+        auto ranked = [&](const long long r) -> long long {
+            return (order == nullptr) ? r : binned ? (long long)order_list_get(counter, order, (unsigned int)r, lane) : (long long)order[r];
+        };
+        bm[0] = ranked(2LL * bidx);
+        bm[1] = live[1] ? ranked(2LL * bidx + 1) : bm[0];
         // a model that cannot be evaluated (non-finite parameters or an absurd step count: R = NaN) is reported and its slot
         // runs a copy of its partner, so that nothing non-finite enters the shared tile
         long long src[2] = {bm[0], bm[1]};
@@ -2121,8 +2178,8 @@ eval_pack2_kernel(const DevProblem P, const long long n_models, const int* __res
         __syncwarp();
     }
 }
-template __global__ void eval_pack2_kernel<true>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
-template __global__ void eval_pack2_kernel<false>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+template __global__ void eval_pack2_kernel<true>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*, const int);
+template __global__ void eval_pack2_kernel<false>(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*, const int);
 
 __global__ void __launch_bounds__(256) hint_cost_kernel(const int n_models, const int* __restrict__ hint, float* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2165,8 +2222,8 @@ static cudaError_t init_inv_table() {
 }
 
 using WarpKern = void (*)(const DevProblem, const long long, const double*, const int*, double*, double*, int*,
-                          unsigned int*, const int*, const double*);
-using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, const double, const int, const int);
+                          unsigned int*, const int*, const double*, const int);
+using PrepKern = void (*)(const DevProblem, const long long, const double*, double*, float*, int*, unsigned int*, const double, const int, const int);
 
 struct WarpVariant {
     WarpKern eval = nullptr;
@@ -2247,7 +2304,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
     // two d = 4 (d = 2) models per warp: launches with more models than warp slots (EML_PACK2=0 switches it off)
     static const int pack2_mode = [] { const char* e = std::getenv("EML_PACK2"); return e ? std::atoi(e) : 1; }();      // 2: whenever n > slots
     const bool pack2_on = pack2_mode != 0;
-    using PackKern = void (*)(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*);
+    using PackKern = void (*)(const DevProblem, const long long, const int*, double*, double*, int*, unsigned int*, const int*, const double*, const int);
     const PackKern pack_kern = real_h ? (PackKern)eval_pack2_kernel<true> : (PackKern)eval_pack2_kernel<false>;
     const size_t pack_smem = WARPS_PER_CTA * sizeof(Pack2Scratch);
     const bool pack2_possible = pack2_on && pack2_ok && chebyshev && !tl2;
@@ -2276,11 +2333,15 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         double* ex_ = expect ? expect + (size_t)off * P.n_obs * P.n_times * 2 : nullptr;
         double* lo_ = loss ? loss + off : nullptr;
         int* st_ = status ? status + off : nullptr;
-        if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
         // Model order: longest first.  Chebyshev variants: by the generator applications the prepare kernel computes (exact);
         // Taylor variants: by the caller's measured cost or a proxy computed from the parameters.
         const bool sort = order != nullptr && n > (long long)WARPS_PER_CTA * max_ctas && n <= ORDER_MAX_MODELS;
         float* cost = (order != nullptr && n <= ORDER_MAX_MODELS) ? reinterpret_cast<float*>(order + ORDER_MAX_MODELS) : nullptr;
+        // up to ORDER_LIST_CAP models: cost-bin lists filled by the prepare kernel instead of an ordering kernel
+        static const bool lists_on = [] { const char* e = std::getenv("EML_ORDER_LISTS"); return !(e && e[0] == '0'); }();
+        const int binned = (chebyshev && sort && lists_on && n <= ORDER_LIST_CAP) ? 1 : 0;
+        // the fetch counter, and the bin counts behind it when they are used: one memset node
+        if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (binned ? ORDER_HIST_OFF + ORDER_BINS : 1), stream)) != cudaSuccess) return e;
         if (chebyshev) {
             // persistent CTAs (the staged linear program is loaded once per CTA); as many as fit the device
             const size_t lin_bytes = (size_t)(P.lin_rows + P.lin_nnz) * 16;
@@ -2291,15 +2352,16 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
             if (prep_per_sm < 1) prep_per_sm = 1;
             long long pctas = (n + PREP_WARPS - 1) / PREP_WARPS;
             if (pctas > (long long)sms * prep_per_sm) pctas = (long long)sms * prep_per_sm;
-            v.prep<<<(unsigned)pctas, PREP_WARPS * 32, psmem, stream>>>(P, n, p_, prep_ws, sort ? cost : nullptr, zcap, kcap, stage);
-            if (sort) order_models_kernel<<<1, 1024, 0, stream>>>((int)n, cost, order);
+            v.prep<<<(unsigned)pctas, PREP_WARPS * 32, psmem, stream>>>(P, n, p_, prep_ws, (sort && !binned) ? cost : nullptr,
+                                                                         binned ? order : nullptr, counter, zcap, kcap, stage);
+            if (sort && !binned) order_models_kernel<<<1, 1024, 0, stream>>>((int)n, cost, order);
         } else if (sort) {
             launch_model_order(P, n, p_, order, cost_hint ? cost_hint + off : nullptr, stream);
         }
         if (pack2) {
             long long pc = ((n + 1) / 2 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
             if (pc > (long long)sms * per_sm_pack) pc = (long long)sms * per_sm_pack;
-            pack_kern<<<(unsigned)pc, WARPS_PER_CTA * 32, pack_smem, stream>>>(P, n, ts_, ex_, lo_, st_, counter, sort ? order : nullptr, prep_ws);
+            pack_kern<<<(unsigned)pc, WARPS_PER_CTA * 32, pack_smem, stream>>>(P, n, ts_, ex_, lo_, st_, counter, sort ? order : nullptr, prep_ws, binned);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             continue;
         }
@@ -2309,7 +2371,7 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         const bool lat = lat_on && v.eval_lat != nullptr && ctas <= (long long)sms * per_sm_lat;
         if (ctas > max_ctas) ctas = max_ctas;
         (lat ? v.eval_lat : v.eval)<<<(unsigned)ctas, WARPS_PER_CTA * 32, v.smem, stream>>>(P, n, p_, ts_, ex_, lo_, st_, counter, sort ? order : nullptr,
-                                                                      prep_ws);
+                                                                      prep_ws, binned);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
