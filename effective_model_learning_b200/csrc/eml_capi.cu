@@ -18,7 +18,7 @@ size_t generic_smem_bytes(int n, int n_params);
 cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
                             double* expect, double* loss, int* status, unsigned int* counter, int* order, bool real_h, bool chebyshev,
                             bool parity_h, bool sector_b, const int* cost_hint, double* prep_ws, long long prep_cap, bool pack2_ok,
-                            cudaStream_t stream);
+                            bool pdl_ok, cudaStream_t stream);
 size_t warp_prep_bytes_per_model(const DevProblem& P, bool real_h, bool chebyshev, bool parity_h, bool sector_b);
 bool jump_op_is_diag_flip_real(const double* op);
 cudaError_t launch_cta_mma(const DevProblem& P, long long n_models, const double* params, const int* target_set,
@@ -355,7 +355,8 @@ int eml_plan_create(const EmlProblemDesc* d, int device, const EmlOptions* opts,
         cudaError_t ce = cudaMalloc(&c, sizeof(unsigned int) * EML_FETCH_WS_WORDS);
         if (ce != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMalloc(counter)"); }
         plan->owned.push_back(c);
-        if (cudaMemset(c, 0, sizeof(unsigned int) * EML_FETCH_WS_WORDS) != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMemset(counter)"); }
+        // zero once: the evaluators leave the workspace zero behind them (eml_warp_mma.cu: fetch_ws_release)
+        if (cudaMemset(c, 0, sizeof(unsigned int) * EML_FETCH_WS_WORDS) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { eml_plan_destroy(plan); return fail(EML_ERR_CUDA, "cudaMemset(counter)"); }
         plan->d_counter = (unsigned int*)c;
         if (eml::warp_mma_supported(plan->Pw, herm) || eml::cta_mma_supported(P, herm)) {
             void* o = nullptr;
@@ -462,7 +463,8 @@ int eml_eval_batch_hinted(EmlPlan* plan, int64_t n_models, const double* params,
     if (plan->kernel == EML_KERNEL_WARP_MMA || plan->kernel == EML_KERNEL_WARP_CHEB)
         e = eml::launch_warp_mma(plan->Pw, n_models, params, target_set, expect, loss, status, counter, order, plan->real_h,
                                  plan->kernel == EML_KERNEL_WARP_CHEB, plan->parity_h, plan->sector_b, cost_hint, prep_ws, prep_cap,
-                                 plan->P.n_tls <= 2, (cudaStream_t)stream);
+                                 plan->P.n_tls <= 2, /* pdl_ok: not for the chain engine's launches (measured slower there) */ counter_ws == nullptr,
+                                 (cudaStream_t)stream);
     else if (plan->kernel == EML_KERNEL_CTA_MMA || plan->kernel == EML_KERNEL_CTA_CHEB)
         e = eml::launch_cta_mma(plan->P, n_models, params, target_set, expect, loss, status, counter, order,
                                 plan->real_h, plan->kernel == EML_KERNEL_CTA_CHEB, plan->parity_h, cost_hint, prep_ws, prep_cap,

@@ -753,6 +753,7 @@ int eml_chains_create(EmlPlan* plan, const EmlChainHyper* h, int64_t n_chains, c
         ch->group_hi[g] = (g + 1) * n_chains / ch->n_groups;
         CH_TRY(dalloc(ch, &ch->g_counter[g], EML_FETCH_WS_WORDS));
         EML_CUDA(cudaMemset(ch->g_counter[g], 0, sizeof(unsigned int) * EML_FETCH_WS_WORDS));
+        EML_CUDA(cudaDeviceSynchronize());      // (the group streams do not synchronise with the stream of the memset)
         CH_TRY(dalloc(ch, &ch->g_order[g], EML_ORDER_WS_INTS));
         CH_TRY(dalloc(ch, &ch->g_prep[g], eml_plan_prep_bytes_per_model(plan) / sizeof(double) * (size_t)(ch->group_hi[g] - ch->group_lo[g])));
         if (cudaStreamCreateWithFlags(&ch->gstream[g], cudaStreamNonBlocking) != cudaSuccess ||
