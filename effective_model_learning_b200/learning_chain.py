@@ -58,8 +58,23 @@ _NOT_HYPERPARAMS = ('self', 'initial', 'target_times', 'target_datasets', 'targe
                     'iterations_till_progress_update')
 
 
+_erf, _SQRT2 = sp.special.erf, np.sqrt(2)
+
+
+def _weighted_choice(p) -> int:
+    """
+    Index drawn with probabilities p -- what np.random.choice(len(p), p=p) returns, from the same single draw of the
+    global stream (numpy's legacy RandomState.choice: cdf = p.cumsum(); cdf /= cdf[-1]; searchsorted(random_sample(),
+    side='right')), without its per-call validation of p and conversion of the label list (about a fifth of a chain
+    step's host time).  tests/test_host.py compares the two draw for draw.
+    """
+    cdf = np.array(p, dtype=np.float64).cumsum()
+    cdf /= cdf[-1]
+    return int(cdf.searchsorted(np.random.random_sample(), side='right'))
+
+
 def _Phi(y):
-    return 1 / 2 * (1 + sp.special.erf(y / np.sqrt(2)))
+    return 1 / 2 * (1 + _erf(y / _SQRT2))
 
 
 class LearningChain:
@@ -177,21 +192,39 @@ class LearningChain:
 
     def _move_weights(self, model):
         """priority x number of ways, per move type, in label order."""
-        return [self.next_step_priorities_dict[x] * self.step(model, x, update=False)[1]
+        if not self.process_handler:
+            self.initialise_process_handler()
+        # every jump move counted in one pass over the model (the same numbers step(model, x, update=False) returns one
+        # move at a time); None: a library is missing -- the per-move path raises the reference's error for it
+        ways = self.process_handler.count_moves(model)
+        if ways is None:
+            return [self.next_step_priorities_dict[x] * self.step(model, x, update=False)[1]
+                    for x in self.next_step_labels]
+        priorities = self.next_step_priorities_dict
+        return [priorities[x] * (1 if x == 'tweak all parameters' else ways[_JUMP_METHODS[x]] if x in _JUMP_METHODS
+                                 else self.step(model, x, update=False)[1])
                 for x in self.next_step_labels]
 
     def _xi_product(self, model):
         """Product of truncated-Gaussian normalisers over every tweakable parameter of `model`."""
         jl, bounds = self.params_handler.jump_lengths, self.params_bounds
-        out = 1
+        # one vectorised evaluation of xi() over all parameters (the same IEEE operations element by element), then the
+        # product in the reference's parameter order
+        m, s, a, b = [], [], [], []
         for tls in model.TLSs:
             if not tls.is_qubit:
-                out *= self.xi(tls.energy, jl['energies'], *bounds['energies'])
+                m.append(tls.energy); s.append(jl['energies']); a.append(bounds['energies'][0]); b.append(bounds['energies'][1])
             for rate in tls.Ls.values():
-                out *= self.xi(rate, jl['Ls'], *bounds['Ls'])
+                m.append(rate); s.append(jl['Ls']); a.append(bounds['Ls'][0]); b.append(bounds['Ls'][1])
             for partner in tls.couplings:
                 for coupling in tls.couplings[partner]:
-                    out *= self.xi(coupling[0], jl['couplings'], *bounds['couplings'])
+                    m.append(coupling[0]); s.append(jl['couplings'])
+                    a.append(bounds['couplings'][0]); b.append(bounds['couplings'][1])
+        out = 1
+        if m:
+            m, s = np.array(m, dtype=np.float64), np.array(s, dtype=np.float64)
+            for v in self.xi(m, s, np.array(a, dtype=np.float64), np.array(b, dtype=np.float64)).tolist():
+                out *= v
         return out
 
     def _gamma_prior_density(self, model):
@@ -263,7 +296,7 @@ class LearningChain:
 
             weights = self._move_weights(proposal)
             norm = sum(weights)
-            next_step = str(np.random.choice(self.next_step_labels, p=[w / norm for w in weights]))
+            next_step = self.next_step_labels[_weighted_choice([w / norm for w in weights])]
             self.run_step_type_tracker.append(next_step)
             tweak = next_step == 'tweak all parameters'
             if tweak:
@@ -290,7 +323,8 @@ class LearningChain:
                     p_there = self._xi_product(proposal)
                     p_back = self._xi_product(self.current)
             else:
-                p_there = self.next_step_priorities_dict[next_step] / sum(self._move_weights(self.current))
+                # (`proposal` was a copy of the current model when `weights` was computed: sum(weights) is the current model's)
+                p_there = self.next_step_priorities_dict[next_step] / norm
                 p_back = (self.next_step_priorities_dict[self.complementary_step(next_step)]
                           / sum(self._move_weights(proposal)))
 
@@ -433,9 +467,13 @@ class LearningChain:
 
     def prior(self, model, return_minus_log_of: bool = False) -> float:
         """exp(-(number of processes)/complexity_factor), or its minus log."""
-        ph = self.process_handler
-        total_complexity = (ph.count_Ls(model) + ph.count_defect2defect_couplings(model)
-                            + ph.count_qubit2defect_couplings(model))
+        # Lindblad processes + defect-defect + qubit-defect couplings (process_handler.count_*; qubit-qubit ones do not count)
+        total_complexity = 0
+        for tls in model.TLSs:
+            total_complexity += len(tls.Ls)
+            for partner, held in tls.couplings.items():
+                if not (tls.is_qubit and partner.is_qubit):
+                    total_complexity += len(held)
         if return_minus_log_of:
             return total_complexity / self.complexity_factor
         return np.exp(-1 * total_complexity / self.complexity_factor)

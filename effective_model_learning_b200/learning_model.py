@@ -13,6 +13,7 @@ import numpy as np
 from . import basic_model
 
 _MAX_ATTEMPTS = 10
+_IMMUTABLE = (bool, int, float, str, type(None))
 _SHORT2LONG = {'sx': 'sigmax', 'sy': 'sigmay', 'sz': 'sigmaz', 'sp': 'sigmap', 'sm': 'sigmam'}
 
 
@@ -41,7 +42,12 @@ class LearningModel(basic_model.BasicModel):
         memo[id(self)] = new
         for k, v in self.__dict__.items():
             if k not in ('TLSs', 'TLS_labels', '_cache'):
-                new.__dict__[k] = copy.deepcopy(v, memo)
+                if type(v) in _IMMUTABLE:
+                    new.__dict__[k] = v
+                elif type(v) is dict and all(type(a) in _IMMUTABLE and type(b) in _IMMUTABLE for a, b in v.items()):
+                    new.__dict__[k] = dict(v)      # flat dictionaries of numbers (jump_lengths)
+                else:
+                    new.__dict__[k] = copy.deepcopy(v, memo)
         new._cache = {}
         new.TLSs = []
         twin = {}

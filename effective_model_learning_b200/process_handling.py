@@ -150,6 +150,44 @@ class ProcessHandler:
     def remove_random_defect2defect_coupling(self, model, update: bool = True):
         return self._remove_coupling(model, False, update)
 
+    def count_moves(self, model):
+        """
+        {move method name: number of possible modifications} for all twelve add / remove moves in one pass -- the counts
+        the methods return with update=False.  None when a library is not a dict (the methods raise for that).
+        """
+        libs = (self.qubit_Ls_library, self.defect_Ls_library, self.qubit2defect_couplings_library,
+                self.defect2defect_couplings_library)
+        if not all(isinstance(lib, dict) for lib in libs):
+            return None
+        qL, dL, qd, dd = libs
+        n = dict.fromkeys(('add_random_qubit_L', 'add_random_defect_L', 'remove_random_qubit_L', 'remove_random_defect_L',
+                           'add_random_qubit2defect_coupling', 'remove_random_qubit2defect_coupling',
+                           'add_random_defect2defect_coupling', 'remove_random_defect2defect_coupling'), 0)
+        for tls in model.TLSs:
+            if tls.is_qubit:
+                n['add_random_qubit_L'] += sum(1 for name in qL if name not in tls.Ls)
+                n['remove_random_qubit_L'] += len(tls.Ls)
+            else:
+                n['add_random_defect_L'] += sum(1 for name in dL if name not in tls.Ls)
+                n['remove_random_defect_L'] += len(tls.Ls)
+            for partner, held in tls.couplings.items():
+                kind = int(tls.is_qubit) + int(partner.is_qubit)
+                if kind == 1:
+                    n['remove_random_qubit2defect_coupling'] += len(held)
+                elif kind == 0:
+                    n['remove_random_defect2defect_coupling'] += len(held)
+        for qubit_defect, library, key in ((True, qd, 'add_random_qubit2defect_coupling'),
+                                           (False, dd, 'add_random_defect2defect_coupling')):
+            kinds = [frozenset(_as_pairs(kind)) for kind in library]
+            for a, b in self._pairs(model, qubit_defect):
+                held = a.couplings.get(b, []) + b.couplings.get(a, [])
+                if not held:
+                    n[key] += len(kinds)
+                    continue
+                present = {frozenset(tuple(p) for p in op_pairs) for _, op_pairs in held}
+                n[key] += sum(1 for kind in kinds if kind not in present)
+        return n
+
     # ------------------------------------------------------------------ libraries
     def define_qubit_Ls_library(self, qubit_Ls_library) -> None:
         self.qubit_Ls_library = qubit_Ls_library

@@ -152,6 +152,78 @@ def test_deepcopy_is_independent():
     assert m.TLSs[1].Ls.get('sigmax') != 0.123 and m.TLSs[1].energy != 9.0
 
 
+def test_one_pass_move_counts_and_vectorised_normalisers_equal_the_per_move_path(oracle_backend):
+    """
+    The chain's hot loop counts all twelve jump moves in one pass (ProcessHandler.count_moves) and evaluates the
+    truncated-Gaussian normalisers in one vectorised call: both must give what the reference-shaped methods give one
+    move / one parameter at a time (process_handling.py update=False counts; learning_chain.py:979-994 xi), bit for bit.
+    """
+    from effective_model_learning_b200.learning_chain import _JUMP_METHODS
+    cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    cfg['iterations_till_progress_update'] = False
+    ts = np.linspace(0, 1, 5)
+    np.random.seed(7)
+    chain = eml.LearningChain(target_times=ts, target_datasets=[np.zeros(5)] * 3, target_observables=OBS3, initial=(1, 3),
+                              qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'], **cfg)
+    chain.initialise_process_handler()
+    chain.initialise_params_handler()
+    model = copy.deepcopy(chain.current)
+    moves = [m for m in chain.next_step_labels if m != 'tweak all parameters']
+    seen_nonzero = set()
+    for it in range(300):
+        ways = chain.process_handler.count_moves(model)
+        for label in moves:
+            assert ways[_JUMP_METHODS[label]] == chain.step(model, label, update=False)[1], (it, label)
+            if ways[_JUMP_METHODS[label]]:
+                seen_nonzero.add(label)
+        assert chain._move_weights(model) == [chain.next_step_priorities_dict[x] * chain.step(model, x, update=False)[1]
+                                              for x in chain.next_step_labels]
+        # the per-parameter product, as the reference writes it
+        jl, bounds = chain.params_handler.jump_lengths, chain.params_bounds
+        want = 1
+        for tls in model.TLSs:
+            if not tls.is_qubit:
+                want *= chain.xi(tls.energy, jl['energies'], *bounds['energies'])
+            for rate in tls.Ls.values():
+                want *= chain.xi(rate, jl['Ls'], *bounds['Ls'])
+            for partner in tls.couplings:
+                for coupling in tls.couplings[partner]:
+                    want *= chain.xi(coupling[0], jl['couplings'], *bounds['couplings'])
+        assert chain._xi_product(model) == want
+        prior_want = np.exp(-(chain.process_handler.count_Ls(model) + chain.process_handler.count_defect2defect_couplings(model)
+                              + chain.process_handler.count_qubit2defect_couplings(model)) / chain.complexity_factor)
+        assert chain.prior(model) == prior_want
+        # random walk through model space: a random available jump move, now and then a tweak
+        label = moves[np.random.choice(len(moves))]
+        model, _ = chain.step(model, label, update=True)
+        if it % 5 == 0:
+            model, _ = chain.step(model, 'tweak all parameters', update=True)
+    assert seen_nonzero == set(moves)
+    # a missing library: the per-move path (and its error) is kept
+    chain.process_handler.qubit_Ls_library = False
+    assert chain.process_handler.count_moves(model) is None
+    with pytest.raises(RuntimeError, match='library not specified'):
+        chain._move_weights(model)
+
+
+def test_weighted_choice_is_numpys_choice_draw_for_draw():
+    """learning_chain._weighted_choice against np.random.choice(labels, p=p) (reference learning_chain.py:446-449) on one stream."""
+    from effective_model_learning_b200.learning_chain import _weighted_choice
+    gen = np.random.default_rng(11)
+    labels = [f'move {i}' for i in range(13)]
+    cases = []
+    for _ in range(2000):
+        w = gen.integers(0, 12, size=13).astype(float) * gen.choice([0.0, 1.0, 10.0], size=13)
+        if w.sum() > 0:
+            cases.append([x / w.sum() for x in w.tolist()])
+    np.random.seed(5)
+    want = [str(np.random.choice(labels, p=p)) for p in cases]
+    tail_want = np.random.uniform()
+    np.random.seed(5)
+    got = [labels[_weighted_choice(p)] for p in cases]
+    assert got == want and np.random.uniform() == tail_want
+
+
 @pytest.mark.parametrize('D', [1, 2, 3])
 def test_chain_replays_reference_trajectory(oracle_backend, D):
     """
