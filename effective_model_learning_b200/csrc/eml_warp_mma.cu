@@ -2400,7 +2400,10 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
             if (pc > (long long)sms * per_sm_pack) pc = (long long)sms * per_sm_pack;
             cfg.gridDim = dim3((unsigned)pc);
             cfg.dynamicSmemBytes = pack_smem;
-            if ((e = cudaLaunchKernelEx(&cfg, pack_kern, P, n, ts_, ex_, lo_, st_, counter, order_arg, (const double*)prep_ws, binned)) != cudaSuccess) return e;
+            if ((e = cudaLaunchKernelEx(&cfg, pack_kern, P, n, ts_, ex_, lo_, st_, counter, order_arg, (const double*)prep_ws, binned)) != cudaSuccess) {
+                cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (ORDER_HIST_OFF + ORDER_BINS), stream);      // no evaluator ran: it would have left the workspace zero
+                return e;
+            }
             continue;
         }
         long long ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -2411,7 +2414,10 @@ cudaError_t launch_warp_mma(const DevProblem& P, long long n_models, const doubl
         cfg.gridDim = dim3((unsigned)ctas);
         cfg.dynamicSmemBytes = v.smem;
         if ((e = cudaLaunchKernelEx(&cfg, lat ? v.eval_lat : v.eval, P, n, p_, ts_, ex_, lo_, st_, counter, order_arg, (const double*)prep_ws,
-                                    binned)) != cudaSuccess) return e;
+                                    binned)) != cudaSuccess) {
+            cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (ORDER_HIST_OFF + ORDER_BINS), stream);      // as above
+            return e;
+        }
     }
     return cudaSuccess;
 }
