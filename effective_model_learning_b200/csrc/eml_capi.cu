@@ -521,6 +521,11 @@ static bool zero_copy_on() {
     static const bool on = [] { const char* e = std::getenv("EML_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
     return on;
 }
+// EML_HOST_ZEROCOPY=2: loss / status written to host memory by the kernels, but the parameters copied by the DMA engine
+static bool zero_copy_params_on() {
+    static const bool on = [] { const char* e = std::getenv("EML_HOST_ZEROCOPY"); return !(e && (e[0] == '0' || e[0] == '2')); }();
+    return on;
+}
 
 int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, const int32_t* target_set,
                         double* expect, double* loss) {
@@ -605,7 +610,7 @@ int eml_eval_batch_host(EmlPlan* plan, int64_t n_models, const double* params, c
     const bool expect_pinned = expect && pinned_device_ptr(expect) != nullptr;
     const bool params_pinned = params_dev != nullptr, loss_pinned = loss_dev != nullptr;
     const double* params_arg = plan->d_params;
-    if (params_pinned && zc) {
+    if (params_pinned && zc && zero_copy_params_on()) {
         params_arg = params_dev;
     } else if (params_pinned) {
         EML_CUDA(cudaMemcpyAsync(plan->d_params, params, np * sizeof(double), cudaMemcpyHostToDevice, s));

@@ -25,7 +25,8 @@ np.random.seed(1000)
 chain = eml.LearningChain(target_times=ts, target_datasets=targets, target_observables=OBS3, initial=(1, D),
                           qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'],
                           max_chain_steps=steps, **cfg)
-chain.run(20)
+with np.errstate(over='ignore'):
+    chain.run(20)
 prof = cProfile.Profile()
 t0 = time.perf_counter()
 prof.enable()

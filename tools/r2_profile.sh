@@ -8,7 +8,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_ref
 python bench.py --workload multiset > gpurun_out/r02_bench_multiset_1gpu.json 2>> gpurun_out/r02_bench_final.err
 python tools/bench_configs.py > gpurun_out/r02_bench_configs.jsonl 2>&1
 python tools/bench_chains.py > gpurun_out/r02_bench_chains.jsonl 2>&1
-python tools/bench_single_chain.py 1 1000 2>&1 | head -1 > gpurun_out/r02_bench_single_chain.json
+python tools/bench_single_chain.py 1 1000 2>/dev/null | head -1 > gpurun_out/r02_bench_single_chain.json
 # launch list of the bench command (cold-cache, serialised: compare shares)
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sustain-seconds 0 --chain-steps 20 --chain-burn-in 5 > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_final.csv \
