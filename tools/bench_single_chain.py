@@ -27,13 +27,17 @@ chain = eml.LearningChain(target_times=ts, target_datasets=targets, target_obser
                           max_chain_steps=steps, **cfg)
 with np.errstate(over='ignore'):
     chain.run(20)
+profile = len(sys.argv) > 3 and sys.argv[3] == 'profile'      # cProfile slows the host loop: the steps/s figure is taken without it
 prof = cProfile.Profile()
 t0 = time.perf_counter()
-prof.enable()
+if profile:
+    prof.enable()
 with np.errstate(over='ignore'):
     chain.run(steps)
-prof.disable()
+if profile:
+    prof.disable()
 dt = time.perf_counter() - t0
 print(json.dumps({'config': f'C1 single chain, 1 qubit + {D} defects', 'steps': steps + 1, 'seconds': dt,
-                  'steps_per_s': (steps + 1) / dt, 'best_loss': chain.best_loss}))
-pstats.Stats(prof).sort_stats('cumulative').print_stats(14)
+                  'steps_per_s': (steps + 1) / dt, 'best_loss': chain.best_loss, 'profiled': profile}))
+if profile:
+    pstats.Stats(prof).sort_stats('cumulative').print_stats(14)
