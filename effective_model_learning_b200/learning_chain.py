@@ -194,6 +194,8 @@ class LearningChain:
         """priority x number of ways, per move type, in label order."""
         if not self.process_handler:
             self.initialise_process_handler()
+        if not self.params_handler:      # (as step() does)
+            self.initialise_params_handler()
         # every jump move counted in one pass over the model (the same numbers step(model, x, update=False) returns one
         # move at a time); None: a library is missing -- the per-move path raises the reference's error for it
         ways = self.process_handler.count_moves(model)
@@ -207,6 +209,8 @@ class LearningChain:
 
     def _xi_product(self, model):
         """Product of truncated-Gaussian normalisers over every tweakable parameter of `model`."""
+        if not self.params_handler:
+            self.initialise_params_handler()
         jl, bounds = self.params_handler.jump_lengths, self.params_bounds
         # one vectorised evaluation of xi() over all parameters (the same IEEE operations element by element), then the
         # product in the reference's parameter order

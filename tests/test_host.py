@@ -165,9 +165,13 @@ def test_one_pass_move_counts_and_vectorised_normalisers_equal_the_per_move_path
     np.random.seed(7)
     chain = eml.LearningChain(target_times=ts, target_datasets=[np.zeros(5)] * 3, target_observables=OBS3, initial=(1, 3),
                               qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'], **cfg)
-    chain.initialise_process_handler()
-    chain.initialise_params_handler()
+    # the helpers create the handlers on first use, as step() does (tests/test_gpu_chain_statistics.py calls them on a chain
+    # that never ran)
     model = copy.deepcopy(chain.current)
+    assert not chain.params_handler
+    assert chain._xi_product(model) == chain.xi(0.1, chain.params_handler.jump_lengths['energies'], *chain.params_bounds['energies']) ** 3
+    chain.params_handler = False
+    assert len(chain._move_weights(model)) == len(chain.next_step_labels) and chain.params_handler
     moves = [m for m in chain.next_step_labels if m != 'tweak all parameters']
     seen_nonzero = set()
     for it in range(300):
