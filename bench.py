@@ -349,6 +349,10 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step()
+    # the checkpoint gather of the timed region, once untimed as well (NCCL sets its channels up on the first call of a kind)
+    gathered = torch.empty((world, B), dtype=torch.float64, device=dev) if world > 1 else None
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, loss)
     barrier()
     st = status.cpu().numpy()
     if (st < 0).any():
@@ -370,8 +374,7 @@ def run_b200(args):
         k_ev[i][1].record()
     if world > 1:
         # the path's only collective: per-chain statistics gathered at a checkpoint (once per timed region)
-        gathered = [torch.empty_like(loss) for _ in range(world)]
-        dist.all_gather(gathered, loss)
+        dist.all_gather_into_tensor(gathered, loss)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
