@@ -205,7 +205,9 @@ bool jump_op_is_diag_flip_real(const double* op) {
 // Longest-processing-time-first ordering: the work of a model grows with the size of its generator, so the
 // persistent warps fetch models in order of decreasing  sum |energy| + sum strength^2 + sum rate  (a proxy for
 // the norm bound): a cost kernel (one thread per model) and a one-CTA counting sort.  Without it the last warps to finish
-// determine the kernel time (3.5 models per warp at 4096 chains).
+// determine the kernel time (3.5 models per warp at 4096 chains).  These two kernels serve the Taylor variants (proxy cost)
+// and Chebyshev launches beyond ORDER_LIST_CAP models (exact cost from the prepare kernel); Chebyshev launches up to
+// ORDER_LIST_CAP models are ordered by the prepare kernel's cost-bin lists instead (order_list_put / order_list_get below).
 constexpr int ORDER_BINS = 256;
 constexpr int ORDER_MAX_MODELS = 1 << 18;
 
