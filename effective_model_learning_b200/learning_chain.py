@@ -259,6 +259,11 @@ class LearningChain:
         k2 = 0
         i = 0
         now_annealed = False
+        # Two quantities of the CURRENT model are reused between steps instead of being recomputed from an unchanged model
+        # (same values, so the same trajectory): its move weights (valid until a jump move is accepted) and its product of
+        # truncated-Gaussian normalisers (valid until a proposal is accepted or the jump lengths change).  Local to this call:
+        # whatever happens to self.current between calls of run() is seen.
+        cur_weights = cur_xi = None
         while i <= steps:
             if bool(self.shock_anneal_at) and i == self.shock_anneal_at:
                 # switch to the annealed jump lengths and restart from the best model so far
@@ -267,6 +272,7 @@ class LearningChain:
                 i += 1
                 self.current = copy.deepcopy(self.best)
                 self.current_loss = self.best_loss
+                cur_weights = cur_xi = None
                 self.run_acceptance_tracker.append(True)
                 if self.store_all_proposals:
                     self.explored_proposals.append(copy.deepcopy(self.current))
@@ -283,8 +289,10 @@ class LearningChain:
                 self.chain_windows_acceptance_log.append(acceptance_ratio)
                 if acceptance_ratio - self.acceptance_target > self.acceptance_band:
                     self.cool_down()
+                    cur_xi = None
                 elif acceptance_ratio - self.acceptance_target < -self.acceptance_band:
                     self.heat_up()
+                    cur_xi = None
             k += 1
 
             if bool(self.iterations_till_progress_update):
@@ -298,7 +306,9 @@ class LearningChain:
 
             proposal = copy.deepcopy(self.current)
 
-            weights = self._move_weights(proposal)
+            if cur_weights is None:
+                cur_weights = self._move_weights(proposal)      # (`proposal` is still a copy of the current model)
+            weights = cur_weights
             norm = sum(weights)
             next_step = self.next_step_labels[_weighted_choice([w / norm for w in weights])]
             self.run_step_type_tracker.append(next_step)
@@ -325,12 +335,14 @@ class LearningChain:
                     params_priors_ratio = self._gamma_prior_density(proposal) / self._gamma_prior_density(self.current)
                 else:
                     p_there = self._xi_product(proposal)
-                    p_back = self._xi_product(self.current)
+                    if cur_xi is None:
+                        cur_xi = self._xi_product(self.current)
+                    p_back = cur_xi
             else:
-                # (`proposal` was a copy of the current model when `weights` was computed: sum(weights) is the current model's)
+                # (`weights` are the current model's: sum(weights) is what sum(self._move_weights(self.current)) gives)
                 p_there = self.next_step_priorities_dict[next_step] / norm
-                p_back = (self.next_step_priorities_dict[self.complementary_step(next_step)]
-                          / sum(self._move_weights(proposal)))
+                proposal_weights = self._move_weights(proposal)
+                p_back = self.next_step_priorities_dict[self.complementary_step(next_step)] / sum(proposal_weights)
 
             proposal_loss = self.total_dev(proposal)
             self._log_explored(proposal, proposal_loss)
@@ -350,8 +362,10 @@ class LearningChain:
                     self.explored_proposals.append(copy.deepcopy(proposal))
                 if tweak:
                     self.acc_tweak_steps += 1
+                    cur_xi = p_there if self.params_bounds else None      # the proposal's product is the new current model's
                 else:
                     self.acc_RJ_steps += 1
+                    cur_weights, cur_xi = proposal_weights, None
             else:
                 self.run_acceptance_tracker.append(False)
             self.run_annealing_tracker.append(now_annealed)
