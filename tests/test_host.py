@@ -210,6 +210,41 @@ def test_one_pass_move_counts_and_vectorised_normalisers_equal_the_per_move_path
         chain._move_weights(model)
 
 
+@pytest.mark.parametrize('bounded', [True, False])
+def test_run_equals_the_plain_loop_bit_for_bit(oracle_backend, bounded):
+    """
+    LearningChain.run against tests/plain_chain_loop.PlainLoopChain (everything recomputed every step, np.random.choice)
+    on the same seed: acceptance windows that rescale the jump lengths, a shock anneal in the middle, bounded and
+    unbounded parameters (learning_chain.py:454-487), two consecutive run() calls.
+    """
+    from tests.plain_chain_loop import PlainLoopChain
+    cfg = configs.get_hyperparams(list(configs.specific_experiment_chain_hyperparams)[11])
+    cfg.update(iterations_till_progress_update=False, jump_length_rescaling_factor=1.3, acceptance_window=10,
+               shock_anneal_at=40, temperature_proposal=0.01)
+    if not bounded:
+        cfg['params_bounds'] = False
+    ts = np.linspace(0, 2.5, 6)
+    truth = lo.random_library_spec(np.random.default_rng(20260012), 1, 2)
+    targets = [np.asarray(e).real for e in lo.expect_exact(truth, ts, OBS3)]
+    out = []
+    for cls in (PlainLoopChain, eml.LearningChain):
+        np.random.seed(77)
+        chain = cls(target_times=ts, target_datasets=targets, target_observables=OBS3, initial=(1, 2),
+                    qubit_initial_state=definitions.ops['plus'], defect_initial_state=definitions.ops['mm'],
+                    max_chain_steps=400, **copy.deepcopy(cfg))
+        with np.errstate(all='ignore'):
+            chain.run(60)
+            first = (list(chain.run_acceptance_tracker), list(chain.run_step_type_tracker))      # (reset by every run())
+            chain.run(35)
+        out.append((chain.explored_loss, first[0] + chain.run_acceptance_tracker, first[1] + chain.run_step_type_tracker,
+                    chain.explored_acceptance_probability, chain.chain_windows_acceptance_log,
+                    dict(chain.params_handler.jump_lengths), chain.best_loss, np.random.uniform()))
+    plain, fast = out
+    assert len(plain[0]) == 98 and 'jump to best' in plain[2] and len(set(plain[2])) >= 6 and 5 < sum(plain[1]) < 95
+    for a, b in zip(plain, fast):
+        assert a == b
+
+
 def test_weighted_choice_is_numpys_choice_draw_for_draw():
     """learning_chain._weighted_choice against np.random.choice(labels, p=p) (reference learning_chain.py:446-449) on one stream."""
     from effective_model_learning_b200.learning_chain import _weighted_choice
