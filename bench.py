@@ -546,6 +546,8 @@ def run_b200(args):
                             'kernels instead of before and after them), then cudaStreamSynchronize; EML_HOST_ZEROCOPY=0 restores '
                             'the explicit copies'},
         'gpu_launches': int(launches),
+        'gpu_launches_counted': 'evaluator kernels (eml_launch_count); each Chebyshev evaluator launch follows one prepare_models_kernel '
+                                'launch of the same library, so a step is two kernels (launch list under profiles/)',
         'roofline': roofline,
         'clocks': clocks,
     }
