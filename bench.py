@@ -426,12 +426,14 @@ def run_b200(args):
     achieved = flops_launch / (kernel_ms * 1e-3)
     canon = canonical_dense_flops(layout.n_tls, N_TIMES, 3)
     traffic = None
+    traffic_note = None
     ncu_pipes = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
             entry = json.load(f).get(f'{plan.kernel_name}:n_tls={layout.n_tls}:chains={B}')
         if entry:
             traffic = entry['bytes']
+            traffic_note = entry.get('note')
             ncu_pipes = {k: entry[k] for k in ('fp64_pipe_pct', 'tensor_fp64_pct', 'issue_pct', 'duration_ms') if k in entry}
     except (OSError, ValueError):
         pass
@@ -439,6 +441,7 @@ def run_b200(args):
         'bound': 'tensor', 'pipe': 'fp64 (DFMA/DMMA)', 'kernel': plan.kernel_name,
         'achieved': achieved / 1e12, 'peak': peak / 1e12, 'unit': 'TFLOP/s', 'frac': achieved / peak,
         'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu --set full capture of the same workload)',
+        'traffic_note': traffic_note,
         'peak_source': 'measured in this run: eml_measure_fp64_peak (register-resident DFMA / DMMA m8n8k4 chains); '
                        'MEASURED_PEAKS.json has no FP64 figure',
         'peak_dfma_tflops': fp64_fma / 1e12, 'peak_dmma_tflops': fp64_mma / 1e12,
